@@ -1,0 +1,173 @@
+/* libmuscle_b200.so — C ABI of the B200-native `binary_einsum` backend for Muscle.jl.
+ *
+ * This is the drop-in boundary: what a `struct BackendB200 <: Muscle.Backend` binds with `ccall`
+ * (julia/MuscleB200.jl). It replaces, for the pairwise-contraction hot path only,
+ *   - Muscle.binary_einsum(::BackendBase, inds_c, a, b)      src/Operations/binary_einsum.jl:76-96
+ *   - Muscle.binary_einsum!(::BackendBase, c, a, b)          src/Operations/binary_einsum.jl:98-121
+ *   - the cuTENSOR route  cuTENSOR.contract!(1, A, modes_a, …, 0, C, modes_c, …)
+ *                                                            ext/MuscleCUDAExt.jl:22-41
+ * Labels never cross the boundary: the caller flattens `Index` objects to int32 mode ids exactly
+ * as the reference does (ext/MuscleCUDAExt.jl:24-27).
+ *
+ * Conventions
+ *   - arrays are Julia `Array`s: dense or strided, COLUMN-MAJOR, complex interleaved (re,im);
+ *     strides are in ELEMENTS; `strides == NULL` means dense column-major in the given mode order.
+ *   - every entry returns an `mb200_status_t`; the message is in `mb200_last_error_string()`
+ *     (thread-local). INVALID_ARGUMENT / NOT_SUPPORTED map to Julia `ArgumentError`
+ *     (binary_einsum.jl:53-55,82-83), DIMENSION_MISMATCH to `DimensionMismatch` (src/Tensor.jl:23).
+ *   - calls are stream-ordered on the handle's stream and do not synchronise, except the `_host`
+ *     entry and `mb200_stream_sync`.
+ *   - there is NO CPU fallback: without a usable CUDA device compute entries return CUDA_ERROR.
+ */
+#ifndef MUSCLE_B200_H
+#define MUSCLE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB200_MAX_MODES 32
+
+typedef enum {
+    MB200_F32 = 0,  /* Float32    */
+    MB200_F64 = 1,  /* Float64    */
+    MB200_C64 = 2,  /* ComplexF32 */
+    MB200_C128 = 3  /* ComplexF64 */
+} mb200_dtype_t;
+
+typedef enum {
+    MB200_OK = 0,
+    MB200_INVALID_ARGUMENT = 1,   /* -> ArgumentError       */
+    MB200_NOT_SUPPORTED = 2,      /* -> ArgumentError       */
+    MB200_DIMENSION_MISMATCH = 3, /* -> DimensionMismatch   */
+    MB200_CUDA_ERROR = 4,
+    MB200_OUT_OF_MEMORY = 5,
+    MB200_INTERNAL_ERROR = 6
+} mb200_status_t;
+
+/* which kernel family a contraction is routed to (reported by mb200_plan_describe) */
+typedef enum {
+    MB200_PATH_AUTO = 0,
+    MB200_PATH_DIRECT = 1,   /* K5: single-kernel direct contraction (launch-bound / skinny sizes) */
+    MB200_PATH_GETT_F64 = 2, /* K2: FP64 DMMA (mma.sync m8n8k4 f64) gather-GEMM, C128 4M / F64    */
+    MB200_PATH_SIMT_F32 = 3, /* FP32 FFMA gather-GEMM (C64 / F32; shapes the tcgen05 path rejects) */
+    MB200_PATH_TCGEN05_TF32 = 4 /* K3: tcgen05/TMEM 3xTF32 GEMM on TMA-fed planar operands         */
+} mb200_path_t;
+
+typedef struct mb200_handle_s *mb200_handle_t;
+
+/* ---- library / handle ------------------------------------------------------------------ */
+int mb200_version(void);
+const char *mb200_last_error_string(void);
+int mb200_device_count(int *count);
+/* one handle per (device, host thread); owns plan cache, offset tables, workspace, stream */
+int mb200_create(mb200_handle_t *handle, int device);
+int mb200_destroy(mb200_handle_t handle);
+/* `cuda_stream` is a cudaStream_t (NULL = legacy default stream). Not owned. */
+int mb200_set_stream(mb200_handle_t handle, void *cuda_stream);
+int mb200_stream_sync(mb200_handle_t handle);
+/* force a kernel family (testing / benchmarking); MB200_PATH_AUTO restores the planner's choice */
+int mb200_set_path(mb200_handle_t handle, int path);
+
+/* ---- device / pinned-host memory helpers (Julia has no CUDA.jl on this path) -------------- */
+int mb200_malloc(mb200_handle_t handle, void **dptr, size_t bytes);
+int mb200_free(mb200_handle_t handle, void *dptr);
+int mb200_host_alloc(void **hptr, size_t bytes); /* pinned */
+int mb200_host_free(void *hptr);
+int mb200_memcpy_h2d(mb200_handle_t handle, void *dst, const void *src, size_t bytes); /* async on stream */
+int mb200_memcpy_d2h(mb200_handle_t handle, void *dst, const void *src, size_t bytes); /* async on stream */
+int mb200_memset(mb200_handle_t handle, void *dptr, int value, size_t bytes);
+
+/* ---- the hot path ------------------------------------------------------------------------
+ * C[modesC] = sum over modes absent from C of A[modesA] * B[modesB]        (alpha = 1, beta = 0)
+ * Mode classes: batch/hyper = in A, B and C; summed = in A and B, not C; free = in one operand and C.
+ * Rejected (INVALID_ARGUMENT): a mode repeated inside one tensor, a C mode found in neither
+ * operand, a mode of a single operand missing from C, nmodes > MB200_MAX_MODES.
+ * DIMENSION_MISMATCH: a shared mode with different extents in A and B.
+ * dtypes may differ between A and B (Float64 x ComplexF64 ...): the result dtype must be the
+ * promotion of the two (Base.promote_eltype, ext/MuscleCUDAExt.jl:16).
+ * Pointers are DEVICE pointers on the handle's device. Extents of C are implied by its modes.
+ */
+int mb200_binary_einsum(mb200_handle_t handle,
+                        void *C, int dtypeC, int nmodeC, const int32_t *modesC, const int64_t *stridesC,
+                        const void *A, int dtypeA, int nmodeA, const int32_t *modesA,
+                        const int64_t *extentsA, const int64_t *stridesA,
+                        const void *B, int dtypeB, int nmodeB, const int32_t *modesB,
+                        const int64_t *extentsB, const int64_t *stridesB);
+
+/* Same contract with HOST pointers (dense column-major only, strides must be NULL): copies A and B
+ * to the device, contracts, copies C back, synchronises. This is what replays the reference's
+ * host-array test batteries and what `e2e` in bench.py times. */
+int mb200_binary_einsum_host(mb200_handle_t handle,
+                             void *C, int dtypeC, int nmodeC, const int32_t *modesC,
+                             const void *A, int dtypeA, int nmodeA, const int32_t *modesA,
+                             const int64_t *extentsA,
+                             const void *B, int dtypeB, int nmodeB, const int32_t *modesB,
+                             const int64_t *extentsB);
+
+/* ---- planner introspection (host only; no device needed) ----------------------------------- */
+typedef struct {
+    int64_t M, N, K, L;          /* GEMM-equivalent sizes after classification (L = batch)      */
+    int32_t swapped;             /* 1: B supplies the row (M) modes so C's fastest mode is a row */
+    int32_t path;                /* mb200_path_t the planner picked                              */
+    int32_t compute_dtype;       /* promoted dtype                                               */
+    int32_t n_left, n_right, n_sum, n_batch;
+    int32_t left[MB200_MAX_MODES];  /* row modes, fastest first, in the order the kernel walks   */
+    int32_t right[MB200_MAX_MODES]; /* column modes                                               */
+    int32_t sum[MB200_MAX_MODES];   /* summed modes                                               */
+    int32_t batch[MB200_MAX_MODES]; /* batch (hyper) modes                                        */
+    int32_t a_kmajor, b_kmajor;  /* 1: the operand's unit-stride mode is a summed mode           */
+    double flops;                /* 8*M*N*K*L complex, 2*M*N*K*L real                            */
+    double bytes;                /* sizeof(T)*(|A|+|B|+|C|)                                      */
+} mb200_plan_info_t;
+
+int mb200_plan_describe(int dtypeC, int nmodeC, const int32_t *modesC, const int64_t *stridesC,
+                        int dtypeA, int nmodeA, const int32_t *modesA, const int64_t *extentsA,
+                        const int64_t *stridesA,
+                        int dtypeB, int nmodeB, const int32_t *modesB, const int64_t *extentsB,
+                        const int64_t *stridesB,
+                        mb200_plan_info_t *info);
+
+/* ---- K1: permute / matricise (Julia `permutedims(src, perm)`; perm is 0-based here) -------
+ * dst mode d = src mode perm[d]; both dense column-major. `extents` are the SOURCE extents.
+ * flags: MB200_PERMUTE_PLANAR writes a complex dst as two planes (all re, then all im). */
+#define MB200_PERMUTE_PLANAR 1u
+int mb200_permute(mb200_handle_t handle, void *dst, const void *src, int dtype, int nmode,
+                  const int64_t *extents, const int32_t *perm, uint32_t flags);
+
+/* ---- multi-GPU partition planner (host only) ------------------------------------------------
+ * One process per GPU (torch.distributed / NCCL does the plumbing). Mirrors Dagger's block
+ * sharding, ext/MuscleDaggerExt/binary_einsum.jl:64-119: splitting a free or batch mode gives
+ * independent output slabs (no collective); splitting a summed mode gives full-size partial
+ * outputs that are add-reduced (treereduce(AddComputeOp) there, ncclAllReduce(sum) here). */
+typedef enum { MB200_SHARD_NONE = 0, MB200_SHARD_FREE = 1, MB200_SHARD_BATCH = 2, MB200_SHARD_SUM = 3 } mb200_shard_kind_t;
+typedef struct {
+    int32_t kind;       /* mb200_shard_kind_t                                      */
+    int32_t mode;       /* the mode id that is split                               */
+    int64_t begin, end; /* this rank's half-open range of that mode                */
+    int32_t needs_allreduce;
+} mb200_shard_info_t;
+/* prefer_sum != 0 asks for a summed-mode slice (config 5); otherwise the slowest free/batch mode
+ * of C with extent >= nranks is split. */
+int mb200_shard_plan(int nmodeC, const int32_t *modesC,
+                     int nmodeA, const int32_t *modesA, const int64_t *extentsA,
+                     int nmodeB, const int32_t *modesB, const int64_t *extentsB,
+                     int nranks, int rank, int prefer_sum, mb200_shard_info_t *info);
+
+/* ---- counters (bench.py's gpu_launches claim) ----------------------------------------------- */
+typedef struct {
+    uint64_t launches_total;
+    uint64_t launches_direct, launches_gett_f64, launches_simt_f32, launches_tcgen05;
+    uint64_t launches_permute, launches_table, launches_convert;
+    uint64_t plans_built, plans_hit;
+} mb200_stats_t;
+int mb200_get_stats(mb200_handle_t handle, mb200_stats_t *stats);
+int mb200_reset_stats(mb200_handle_t handle);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MUSCLE_B200_H */

@@ -1,0 +1,259 @@
+"""ctypes binding of libmuscle_b200.so (include/muscle_b200.h).
+
+There is no Python/CPU implementation behind this module: if the library is missing or no B200 is
+usable, the product path raises — loudly — instead of falling back.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmuscle_b200.so")
+
+MAX_MODES = 32
+
+# dtype enum (mb200_dtype_t)
+F32, F64, C64, C128 = 0, 1, 2, 3
+_NP2ENUM = {np.dtype(np.float32): F32, np.dtype(np.float64): F64,
+            np.dtype(np.complex64): C64, np.dtype(np.complex128): C128}
+_ENUM2NP = {v: k for k, v in _NP2ENUM.items()}
+
+# status codes (mb200_status_t)
+OK, INVALID_ARGUMENT, NOT_SUPPORTED, DIMENSION_MISMATCH, CUDA_ERROR, OUT_OF_MEMORY, INTERNAL_ERROR = range(7)
+
+# kernel families (mb200_path_t)
+PATH_AUTO, PATH_DIRECT, PATH_GETT_F64, PATH_SIMT_F32, PATH_TCGEN05_TF32 = range(5)
+PATH_NAMES = {PATH_AUTO: "auto", PATH_DIRECT: "direct", PATH_GETT_F64: "gett_f64_dmma",
+              PATH_SIMT_F32: "simt_f32", PATH_TCGEN05_TF32: "tcgen05_tf32x3"}
+
+SHARD_NONE, SHARD_FREE, SHARD_BATCH, SHARD_SUM = range(4)
+
+
+class ArgumentError(ValueError):
+    """Julia `ArgumentError` (src/Operations/binary_einsum.jl:53-55, 82-83)."""
+
+
+class DimensionMismatch(ValueError):
+    """Julia `DimensionMismatch` (src/Tensor.jl:23)."""
+
+
+class B200Error(RuntimeError):
+    """CUDA / allocation / internal failure inside libmuscle_b200."""
+
+
+class PlanInfo(C.Structure):
+    _fields_ = [("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64), ("L", C.c_int64),
+                ("swapped", C.c_int32), ("path", C.c_int32), ("compute_dtype", C.c_int32),
+                ("n_left", C.c_int32), ("n_right", C.c_int32), ("n_sum", C.c_int32), ("n_batch", C.c_int32),
+                ("left", C.c_int32 * MAX_MODES), ("right", C.c_int32 * MAX_MODES),
+                ("sum", C.c_int32 * MAX_MODES), ("batch", C.c_int32 * MAX_MODES),
+                ("a_kmajor", C.c_int32), ("b_kmajor", C.c_int32),
+                ("flops", C.c_double), ("bytes", C.c_double)]
+
+
+class ShardInfo(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("mode", C.c_int32), ("begin", C.c_int64), ("end", C.c_int64),
+                ("needs_allreduce", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in (
+        "launches_total", "launches_direct", "launches_gett_f64", "launches_simt_f32", "launches_tcgen05",
+        "launches_permute", "launches_table", "launches_convert", "plans_built", "plans_hit")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+_vp, _i, _i32p, _i64p, _sz = C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.c_size_t
+
+# every symbol include/muscle_b200.h declares, with its argument types
+PROTOTYPES = {
+    "mb200_version": ([], C.c_int),
+    "mb200_last_error_string": ([], C.c_char_p),
+    "mb200_device_count": ([C.POINTER(C.c_int)], C.c_int),
+    "mb200_create": ([C.POINTER(_vp), _i], C.c_int),
+    "mb200_destroy": ([_vp], C.c_int),
+    "mb200_set_stream": ([_vp, _vp], C.c_int),
+    "mb200_stream_sync": ([_vp], C.c_int),
+    "mb200_set_path": ([_vp, _i], C.c_int),
+    "mb200_malloc": ([_vp, C.POINTER(_vp), _sz], C.c_int),
+    "mb200_free": ([_vp, _vp], C.c_int),
+    "mb200_host_alloc": ([C.POINTER(_vp), _sz], C.c_int),
+    "mb200_host_free": ([_vp], C.c_int),
+    "mb200_memcpy_h2d": ([_vp, _vp, _vp, _sz], C.c_int),
+    "mb200_memcpy_d2h": ([_vp, _vp, _vp, _sz], C.c_int),
+    "mb200_memset": ([_vp, _vp, _i, _sz], C.c_int),
+    "mb200_binary_einsum": ([_vp,
+                             _vp, _i, _i, _i32p, _i64p,
+                             _vp, _i, _i, _i32p, _i64p, _i64p,
+                             _vp, _i, _i, _i32p, _i64p, _i64p], C.c_int),
+    "mb200_binary_einsum_host": ([_vp,
+                                  _vp, _i, _i, _i32p,
+                                  _vp, _i, _i, _i32p, _i64p,
+                                  _vp, _i, _i, _i32p, _i64p], C.c_int),
+    "mb200_plan_describe": ([_i, _i, _i32p, _i64p,
+                             _i, _i, _i32p, _i64p, _i64p,
+                             _i, _i, _i32p, _i64p, _i64p,
+                             C.POINTER(PlanInfo)], C.c_int),
+    "mb200_permute": ([_vp, _vp, _vp, _i, _i, _i64p, _i32p, C.c_uint32], C.c_int),
+    "mb200_shard_plan": ([_i, _i32p, _i, _i32p, _i64p, _i, _i32p, _i64p, _i, _i, _i,
+                          C.POINTER(ShardInfo)], C.c_int),
+    "mb200_get_stats": ([_vp, C.POINTER(Stats)], C.c_int),
+    "mb200_reset_stats": ([_vp], C.c_int),
+}
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def lib() -> C.CDLL:
+    """Load libmuscle_b200.so (built in-tree by muscle.jl_b200/build.py). Raises if absent."""
+    global _lib
+    with _lib_lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise ImportError(
+                    f"{LIB_PATH} is missing: build it with `python muscle.jl_b200/build.py` "
+                    "(there is no Python or CPU fallback for binary_einsum)")
+            L = C.CDLL(LIB_PATH)
+            for name, (argtypes, restype) in PROTOTYPES.items():
+                fn = getattr(L, name)  # AttributeError if the symbol is not exported
+                fn.argtypes = argtypes
+                fn.restype = restype
+            _lib = L
+    return _lib
+
+
+def last_error() -> str:
+    return lib().mb200_last_error_string().decode("utf-8", "replace")
+
+
+def check(status: int) -> None:
+    if status == OK:
+        return
+    msg = last_error()
+    if status in (INVALID_ARGUMENT, NOT_SUPPORTED):
+        raise ArgumentError(msg)
+    if status == DIMENSION_MISMATCH:
+        raise DimensionMismatch(msg)
+    raise B200Error(f"libmuscle_b200 status {status}: {msg}")
+
+
+def fortran(x) -> np.ndarray:
+    """Column-major contiguous view/copy (Julia Array layout); 0-dim arrays stay 0-dim."""
+    x = np.asarray(x)
+    return np.ascontiguousarray(x).reshape(()) if x.ndim == 0 else np.asfortranarray(x)
+
+
+def dtype_enum(dt) -> int:
+    dt = np.dtype(dt)
+    if dt not in _NP2ENUM:
+        raise ArgumentError(f"eltype {dt} is not supported by BackendB200 "
+                            "(Float32, Float64, ComplexF32, ComplexF64)")
+    return _NP2ENUM[dt]
+
+
+def dtype_numpy(e: int) -> np.dtype:
+    return _ENUM2NP[e]
+
+
+def i32(seq):
+    seq = list(seq)
+    return (C.c_int32 * max(1, len(seq)))(*seq)
+
+
+def i64(seq):
+    seq = list(seq)
+    return (C.c_int64 * max(1, len(seq)))(*seq)
+
+
+class Handle:
+    """One mb200 handle per (process, device). The stream follows torch's current stream when
+    torch is importable, so torch.cuda.Event timing and torch allocations are ordered with our
+    launches (torch is plumbing here: device memory, streams, torch.distributed)."""
+
+    _handles: dict = {}
+    _lock = threading.Lock()
+
+    def __init__(self, device: int):
+        self.device = device
+        self._h = C.c_void_p()
+        check(lib().mb200_create(C.byref(self._h), device))
+        self._stream = 0
+
+    @classmethod
+    def get(cls, device: int | None = None) -> "Handle":
+        if device is None:
+            device = current_device()
+        with cls._lock:
+            h = cls._handles.get(device)
+            if h is None:
+                h = cls._handles[device] = Handle(device)
+        h.sync_stream_with_torch()
+        return h
+
+    @property
+    def ptr(self):
+        return self._h
+
+    def set_stream(self, stream_ptr: int):
+        if stream_ptr != self._stream:
+            check(lib().mb200_set_stream(self._h, C.c_void_p(stream_ptr)))
+            self._stream = stream_ptr
+
+    def sync_stream_with_torch(self):
+        try:
+            import torch
+            if torch.cuda.is_available():
+                self.set_stream(int(torch.cuda.current_stream(self.device).cuda_stream))
+        except ImportError:
+            pass
+
+    def synchronize(self):
+        check(lib().mb200_stream_sync(self._h))
+
+    def set_path(self, path: int):
+        check(lib().mb200_set_path(self._h, path))
+
+    def stats(self) -> dict:
+        s = Stats()
+        check(lib().mb200_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def reset_stats(self):
+        check(lib().mb200_reset_stats(self._h))
+
+
+def current_device() -> int:
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return int(torch.cuda.current_device())
+    except ImportError:
+        pass
+    return int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def plan_describe(dtype_c, modes_c, dtype_a, modes_a, ext_a, dtype_b, modes_b, ext_b,
+                  strides_c=None, strides_a=None, strides_b=None) -> PlanInfo:
+    """Host-only planner introspection (no device needed)."""
+    info = PlanInfo()
+    check(lib().mb200_plan_describe(
+        dtype_c, len(modes_c), i32(modes_c), i64(strides_c) if strides_c is not None else None,
+        dtype_a, len(modes_a), i32(modes_a), i64(ext_a), i64(strides_a) if strides_a is not None else None,
+        dtype_b, len(modes_b), i32(modes_b), i64(ext_b), i64(strides_b) if strides_b is not None else None,
+        C.byref(info)))
+    return info
+
+
+def shard_plan(modes_c, modes_a, ext_a, modes_b, ext_b, nranks, rank, prefer_sum=False) -> ShardInfo:
+    info = ShardInfo()
+    check(lib().mb200_shard_plan(len(modes_c), i32(modes_c), len(modes_a), i32(modes_a), i64(ext_a),
+                                 len(modes_b), i32(modes_b), i64(ext_b), nranks, rank,
+                                 1 if prefer_sum else 0, C.byref(info)))
+    return info

@@ -1,0 +1,556 @@
+// libmuscle_b200 — C ABI (include/muscle_b200.h). Host-side glue: handles, plan cache, offset tables,
+// dtype promotion, launches. No CPU compute path exists here: every compute entry ends in a kernel
+// launch or an error.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <list>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "kernels.cuh"
+#include "plan.hpp"
+
+using namespace mb200;
+
+namespace {
+
+struct CachedPlan {
+    Plan plan;
+    int64_t *tables = nullptr;  // one device allocation: rowA rowC colB colC kA kB batA batB batC
+    GettParams gp{};
+    DirectParams dp{};
+    std::list<std::string>::iterator lru;
+};
+
+constexpr size_t PLAN_CACHE_CAP = 128;
+
+}  // namespace
+
+struct mb200_handle_s {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int forced_path = MB200_PATH_AUTO;
+    std::unordered_map<std::string, std::unique_ptr<CachedPlan>> cache;
+    std::list<std::string> lru;
+    mb200_stats_t stats{};
+    std::mutex mu;
+};
+
+namespace {
+
+int cuda_fail(cudaError_t e, const char *what) {
+    int st = (e == cudaErrorMemoryAllocation) ? MB200_OUT_OF_MEMORY : MB200_CUDA_ERROR;
+    return fail(st, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+}
+
+#define MB200_CUDA(call)                                   \
+    do {                                                   \
+        cudaError_t e__ = (call);                          \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+#define MB200_CHECK_HANDLE(h) \
+    if (!(h)) return fail(MB200_INVALID_ARGUMENT, "handle is NULL")
+
+TableSpec spec_of(const std::vector<GroupMode> &g, int which) {
+    TableSpec s{};
+    s.n = (int)g.size();
+    for (int i = 0; i < s.n; i++) {
+        s.ext[i] = g[i].extent;
+        s.stride[i] = which == 0 ? g[i].sa : (which == 1 ? g[i].sb : g[i].sc);
+    }
+    return s;
+}
+
+int build_cached(mb200_handle_t h, CachedPlan &cp) {
+    const Plan &p = cp.plan;
+    if (p.path == MB200_PATH_DIRECT) {
+        DirectParams &d = cp.dp;
+        std::memset(&d, 0, sizeof d);
+        auto add_c = [&](const GroupMode &g, bool in_a, bool in_b) {
+            d.c_ext[d.nc] = g.extent;
+            d.c_sc[d.nc] = g.sc;
+            d.c_sa[d.nc] = in_a ? g.sa : 0;
+            d.c_sb[d.nc] = in_b ? g.sb : 0;
+            d.nc++;
+        };
+        for (auto &g : p.left) add_c(g, true, false);
+        for (auto &g : p.right) add_c(g, false, true);
+        for (auto &g : p.batch) add_c(g, true, true);
+        for (auto &g : p.sum) {
+            d.k_ext[d.nk] = g.extent;
+            d.k_sa[d.nk] = g.sa;
+            d.k_sb[d.nk] = g.sb;
+            d.nk++;
+        }
+        d.total_c = p.M * p.N * p.L;
+        d.total_k = p.K;
+        return MB200_OK;
+    }
+    // gather-GEMM: offset tables, built on the device, cached with the plan
+    const int64_t M = p.M, N = p.N, K = p.K, L = p.L;
+    const int64_t total = 2 * M + 2 * N + 2 * K + 3 * L;
+    MB200_CUDA(cudaMalloc(&cp.tables, (size_t)total * sizeof(int64_t)));
+    int64_t *t = cp.tables;
+    int64_t *rowA = t; t += M;
+    int64_t *rowC = t; t += M;
+    int64_t *colB = t; t += N;
+    int64_t *colC = t; t += N;
+    int64_t *kA = t; t += K;
+    int64_t *kB = t; t += K;
+    int64_t *batA = t; t += L;
+    int64_t *batB = t; t += L;
+    int64_t *batC = t; t += L;
+    cudaStream_t s = h->stream;
+    MB200_CUDA(launch_build_table(rowA, M, spec_of(p.left, 0), s));
+    MB200_CUDA(launch_build_table(rowC, M, spec_of(p.left, 2), s));
+    MB200_CUDA(launch_build_table(colB, N, spec_of(p.right, 1), s));
+    MB200_CUDA(launch_build_table(colC, N, spec_of(p.right, 2), s));
+    MB200_CUDA(launch_build_table(kA, K, spec_of(p.sum, 0), s));
+    MB200_CUDA(launch_build_table(kB, K, spec_of(p.sum, 1), s));
+    MB200_CUDA(launch_build_table(batA, L, spec_of(p.batch, 0), s));
+    MB200_CUDA(launch_build_table(batB, L, spec_of(p.batch, 1), s));
+    MB200_CUDA(launch_build_table(batC, L, spec_of(p.batch, 2), s));
+    h->stats.launches_table += 9;
+    h->stats.launches_total += 9;
+    GettParams &g = cp.gp;
+    g.rowA = rowA; g.rowC = rowC; g.colB = colB; g.colC = colC; g.kA = kA; g.kB = kB;
+    g.batA = batA; g.batB = batB; g.batC = batC;
+    g.M = M; g.N = N; g.K = K; g.L = L;
+    g.a_kmajor = p.a_kmajor; g.b_kmajor = p.b_kmajor;
+    return MB200_OK;
+}
+
+void evict_one(mb200_handle_t h) {
+    if (h->lru.empty()) return;
+    std::string key = h->lru.back();
+    h->lru.pop_back();
+    auto it = h->cache.find(key);
+    if (it != h->cache.end()) {
+        if (it->second->tables) {
+            cudaStreamSynchronize(h->stream);  // a launch using these tables may still be in flight
+            cudaFree(it->second->tables);
+        }
+        h->cache.erase(it);
+    }
+}
+
+// span (in elements) touched by a possibly strided tensor
+int64_t span_of(const TensorDesc &t) {
+    int64_t s = 1;
+    for (int i = 0; i < t.n; i++) {
+        if (t.ext[i] == 0) return 0;
+        s += (t.ext[i] - 1) * t.stride[i];
+    }
+    return s;
+}
+
+int contract_device(mb200_handle_t h, void *C, TensorDesc &dC, const int64_t *stridesC, const void *A,
+                    const TensorDesc &dA, const void *B, const TensorDesc &dB) {
+    Plan plan;
+    int st = make_plan(dA, dB, dC, stridesC, h->forced_path, plan);
+    if (st != MB200_OK) return st;
+    if (plan.empty_output) return MB200_OK;
+    if (!C || (!A && dA.numel() > 0) || (!B && dB.numel() > 0))
+        return fail(MB200_INVALID_ARGUMENT, "NULL data pointer");
+    MB200_CUDA(cudaSetDevice(h->device));
+
+    CachedPlan *cp;
+    auto it = h->cache.find(plan.key);
+    if (it != h->cache.end()) {
+        cp = it->second.get();
+        h->lru.erase(cp->lru);
+        h->lru.push_front(plan.key);
+        cp->lru = h->lru.begin();
+        h->stats.plans_hit++;
+    } else {
+        while (h->cache.size() >= PLAN_CACHE_CAP) evict_one(h);
+        auto fresh = std::make_unique<CachedPlan>();
+        fresh->plan = plan;
+        st = build_cached(h, *fresh);
+        if (st != MB200_OK) {
+            if (fresh->tables) cudaFree(fresh->tables);
+            return st;
+        }
+        h->lru.push_front(plan.key);
+        fresh->lru = h->lru.begin();
+        cp = fresh.get();
+        h->cache.emplace(plan.key, std::move(fresh));
+        h->stats.plans_built++;
+    }
+    const Plan &p = cp->plan;
+    cudaStream_t s = h->stream;
+
+    // row / column operands, promoted to the compute dtype when the eltypes are mixed
+    const void *R = p.swapped ? B : A;
+    const void *Q = p.swapped ? A : B;
+    const TensorDesc &dR = p.swapped ? dB : dA;
+    const TensorDesc &dQ = p.swapped ? dA : dB;
+    void *tmpR = nullptr, *tmpQ = nullptr;
+    if (dR.dtype != p.dtype) {
+        int64_t n = span_of(dR);
+        MB200_CUDA(cudaMallocAsync(&tmpR, (size_t)std::max<int64_t>(n, 1) * dtype_size(p.dtype), s));
+        MB200_CUDA(launch_convert(p.dtype, tmpR, dR.dtype, R, n, s));
+        h->stats.launches_convert++; h->stats.launches_total++;
+        R = tmpR;
+    }
+    if (dQ.dtype != p.dtype) {
+        int64_t n = span_of(dQ);
+        MB200_CUDA(cudaMallocAsync(&tmpQ, (size_t)std::max<int64_t>(n, 1) * dtype_size(p.dtype), s));
+        MB200_CUDA(launch_convert(p.dtype, tmpQ, dQ.dtype, Q, n, s));
+        h->stats.launches_convert++; h->stats.launches_total++;
+        Q = tmpQ;
+    }
+
+    cudaError_t e;
+    if (p.path == MB200_PATH_DIRECT) {
+        e = launch_direct(p.dtype, cp->dp, R, Q, C, s);
+        h->stats.launches_direct++;
+    } else {
+        GettParams g = cp->gp;
+        g.A = R; g.B = Q; g.C = C;
+        if (dtype_is_double(p.dtype)) {
+            e = launch_gett_f64(p.dtype, g, s);
+            h->stats.launches_gett_f64++;
+        } else {
+            e = launch_simt_f32(p.dtype, g, s);
+            h->stats.launches_simt_f32++;
+        }
+    }
+    h->stats.launches_total++;
+    if (tmpR) cudaFreeAsync(tmpR, s);
+    if (tmpQ) cudaFreeAsync(tmpQ, s);
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+    return MB200_OK;
+}
+
+int make_c_desc(TensorDesc &d, int dtype, int nmode, const int32_t *modes) {
+    if (!dtype_valid(dtype)) return fail(MB200_INVALID_ARGUMENT, "C: unknown dtype %d", dtype);
+    if (nmode < 0 || nmode > MB200_MAX_MODES)
+        return fail(MB200_INVALID_ARGUMENT, "C: nmode %d outside [0, %d]", nmode, MB200_MAX_MODES);
+    if (nmode > 0 && !modes) return fail(MB200_INVALID_ARGUMENT, "C: modes must not be NULL when nmode > 0");
+    d.dtype = dtype;
+    d.n = nmode;
+    for (int i = 0; i < nmode; i++) { d.modes[i] = modes[i]; d.ext[i] = 0; d.stride[i] = 0; }
+    return MB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mb200_version(void) { return 100; }
+
+const char *mb200_last_error_string(void) { return last_error().c_str(); }
+
+int mb200_device_count(int *count) {
+    if (!count) return fail(MB200_INVALID_ARGUMENT, "count is NULL");
+    *count = 0;
+    MB200_CUDA(cudaGetDeviceCount(count));
+    return MB200_OK;
+}
+
+int mb200_create(mb200_handle_t *handle, int device) {
+    if (!handle) return fail(MB200_INVALID_ARGUMENT, "handle is NULL");
+    *handle = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(MB200_CUDA_ERROR, "no usable CUDA device (%s); libmuscle_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(MB200_INVALID_ARGUMENT, "device %d outside [0, %d)", device, n);
+    MB200_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    MB200_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(MB200_NOT_SUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                    device, prop.major, prop.minor);
+    MB200_CUDA(gett_configure());
+    // keep stream-ordered temporaries cached in the pool instead of returning them to the OS
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    auto *h = new mb200_handle_s();
+    h->device = device;
+    *handle = h;
+    return MB200_OK;
+}
+
+int mb200_destroy(mb200_handle_t h) {
+    MB200_CHECK_HANDLE(h);
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (auto &kv : h->cache)
+        if (kv.second->tables) cudaFree(kv.second->tables);
+    delete h;
+    return MB200_OK;
+}
+
+int mb200_set_stream(mb200_handle_t h, void *cuda_stream) {
+    MB200_CHECK_HANDLE(h);
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->stream = (cudaStream_t)cuda_stream;
+    return MB200_OK;
+}
+
+int mb200_stream_sync(mb200_handle_t h) {
+    MB200_CHECK_HANDLE(h);
+    MB200_CUDA(cudaSetDevice(h->device));
+    MB200_CUDA(cudaStreamSynchronize(h->stream));
+    return MB200_OK;
+}
+
+int mb200_set_path(mb200_handle_t h, int path) {
+    MB200_CHECK_HANDLE(h);
+    if (path < MB200_PATH_AUTO || path > MB200_PATH_TCGEN05_TF32)
+        return fail(MB200_INVALID_ARGUMENT, "unknown path %d", path);
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->forced_path = path;
+    return MB200_OK;
+}
+
+int mb200_malloc(mb200_handle_t h, void **dptr, size_t bytes) {
+    MB200_CHECK_HANDLE(h);
+    if (!dptr) return fail(MB200_INVALID_ARGUMENT, "dptr is NULL");
+    MB200_CUDA(cudaSetDevice(h->device));
+    MB200_CUDA(cudaMalloc(dptr, bytes ? bytes : 1));
+    return MB200_OK;
+}
+
+int mb200_free(mb200_handle_t h, void *dptr) {
+    MB200_CHECK_HANDLE(h);
+    MB200_CUDA(cudaSetDevice(h->device));
+    MB200_CUDA(cudaFree(dptr));
+    return MB200_OK;
+}
+
+int mb200_host_alloc(void **hptr, size_t bytes) {
+    if (!hptr) return fail(MB200_INVALID_ARGUMENT, "hptr is NULL");
+    MB200_CUDA(cudaMallocHost(hptr, bytes ? bytes : 1));
+    return MB200_OK;
+}
+
+int mb200_host_free(void *hptr) {
+    MB200_CUDA(cudaFreeHost(hptr));
+    return MB200_OK;
+}
+
+int mb200_memcpy_h2d(mb200_handle_t h, void *dst, const void *src, size_t bytes) {
+    MB200_CHECK_HANDLE(h);
+    MB200_CUDA(cudaSetDevice(h->device));
+    MB200_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    return MB200_OK;
+}
+
+int mb200_memcpy_d2h(mb200_handle_t h, void *dst, const void *src, size_t bytes) {
+    MB200_CHECK_HANDLE(h);
+    MB200_CUDA(cudaSetDevice(h->device));
+    MB200_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+    return MB200_OK;
+}
+
+int mb200_memset(mb200_handle_t h, void *dptr, int value, size_t bytes) {
+    MB200_CHECK_HANDLE(h);
+    MB200_CUDA(cudaSetDevice(h->device));
+    MB200_CUDA(cudaMemsetAsync(dptr, value, bytes, h->stream));
+    return MB200_OK;
+}
+
+int mb200_binary_einsum(mb200_handle_t h, void *C, int dtypeC, int nmodeC, const int32_t *modesC,
+                        const int64_t *stridesC, const void *A, int dtypeA, int nmodeA, const int32_t *modesA,
+                        const int64_t *extentsA, const int64_t *stridesA, const void *B, int dtypeB, int nmodeB,
+                        const int32_t *modesB, const int64_t *extentsB, const int64_t *stridesB) {
+    MB200_CHECK_HANDLE(h);
+    TensorDesc dA, dB, dC;
+    int st;
+    if ((st = make_desc(dA, dtypeA, nmodeA, modesA, extentsA, stridesA, "A")) != MB200_OK) return st;
+    if ((st = make_desc(dB, dtypeB, nmodeB, modesB, extentsB, stridesB, "B")) != MB200_OK) return st;
+    if ((st = make_c_desc(dC, dtypeC, nmodeC, modesC)) != MB200_OK) return st;
+    std::lock_guard<std::mutex> lk(h->mu);
+    return contract_device(h, C, dC, stridesC, A, dA, B, dB);
+}
+
+int mb200_binary_einsum_host(mb200_handle_t h, void *C, int dtypeC, int nmodeC, const int32_t *modesC,
+                             const void *A, int dtypeA, int nmodeA, const int32_t *modesA,
+                             const int64_t *extentsA, const void *B, int dtypeB, int nmodeB,
+                             const int32_t *modesB, const int64_t *extentsB) {
+    MB200_CHECK_HANDLE(h);
+    TensorDesc dA, dB, dC;
+    int st;
+    if ((st = make_desc(dA, dtypeA, nmodeA, modesA, extentsA, nullptr, "A")) != MB200_OK) return st;
+    if ((st = make_desc(dB, dtypeB, nmodeB, modesB, extentsB, nullptr, "B")) != MB200_OK) return st;
+    if ((st = make_c_desc(dC, dtypeC, nmodeC, modesC)) != MB200_OK) return st;
+    std::lock_guard<std::mutex> lk(h->mu);
+    {   // validate before touching the device so argument errors do not depend on a GPU
+        Plan probe;
+        TensorDesc tmp = dC;
+        if ((st = make_plan(dA, dB, tmp, nullptr, h->forced_path, probe)) != MB200_OK) return st;
+        dC = tmp;
+    }
+    MB200_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const size_t bA = (size_t)dA.numel() * dtype_size(dA.dtype);
+    const size_t bB = (size_t)dB.numel() * dtype_size(dB.dtype);
+    const size_t bC = (size_t)dC.numel() * dtype_size(dC.dtype);
+    if (bC == 0) return MB200_OK;
+    if (!C || (!A && bA) || (!B && bB)) return fail(MB200_INVALID_ARGUMENT, "NULL data pointer");
+    void *dAp = nullptr, *dBp = nullptr, *dCp = nullptr;
+    MB200_CUDA(cudaMallocAsync(&dAp, bA ? bA : 1, s));
+    MB200_CUDA(cudaMallocAsync(&dBp, bB ? bB : 1, s));
+    MB200_CUDA(cudaMallocAsync(&dCp, bC, s));
+    if (bA) MB200_CUDA(cudaMemcpyAsync(dAp, A, bA, cudaMemcpyHostToDevice, s));
+    if (bB) MB200_CUDA(cudaMemcpyAsync(dBp, B, bB, cudaMemcpyHostToDevice, s));
+    st = contract_device(h, dCp, dC, nullptr, dAp, dA, dBp, dB);
+    if (st == MB200_OK) {
+        cudaError_t e = cudaMemcpyAsync(C, dCp, bC, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) st = cuda_fail(e, "device-to-host copy of C");
+    }
+    cudaFreeAsync(dAp, s);
+    cudaFreeAsync(dBp, s);
+    cudaFreeAsync(dCp, s);
+    return st;
+}
+
+int mb200_plan_describe(int dtypeC, int nmodeC, const int32_t *modesC, const int64_t *stridesC, int dtypeA,
+                        int nmodeA, const int32_t *modesA, const int64_t *extentsA, const int64_t *stridesA,
+                        int dtypeB, int nmodeB, const int32_t *modesB, const int64_t *extentsB,
+                        const int64_t *stridesB, mb200_plan_info_t *info) {
+    if (!info) return fail(MB200_INVALID_ARGUMENT, "info is NULL");
+    TensorDesc dA, dB, dC;
+    int st;
+    if ((st = make_desc(dA, dtypeA, nmodeA, modesA, extentsA, stridesA, "A")) != MB200_OK) return st;
+    if ((st = make_desc(dB, dtypeB, nmodeB, modesB, extentsB, stridesB, "B")) != MB200_OK) return st;
+    if ((st = make_c_desc(dC, dtypeC, nmodeC, modesC)) != MB200_OK) return st;
+    Plan plan;
+    if ((st = make_plan(dA, dB, dC, stridesC, MB200_PATH_AUTO, plan)) != MB200_OK) return st;
+    fill_info(plan, info);
+    return MB200_OK;
+}
+
+int mb200_permute(mb200_handle_t h, void *dst, const void *src, int dtype, int nmode, const int64_t *extents,
+                  const int32_t *perm, uint32_t flags) {
+    MB200_CHECK_HANDLE(h);
+    if (!dtype_valid(dtype)) return fail(MB200_INVALID_ARGUMENT, "unknown dtype %d", dtype);
+    if (nmode < 0 || nmode > MB200_MAX_MODES) return fail(MB200_INVALID_ARGUMENT, "nmode %d out of range", nmode);
+    if (nmode > 0 && (!extents || !perm)) return fail(MB200_INVALID_ARGUMENT, "extents/perm are NULL");
+    bool seen[MB200_MAX_MODES] = {false};
+    for (int d = 0; d < nmode; d++) {
+        if (perm[d] < 0 || perm[d] >= nmode || seen[perm[d]])
+            return fail(MB200_INVALID_ARGUMENT, "perm is not a permutation of 0..%d", nmode - 1);
+        seen[perm[d]] = true;
+        if (extents[d] < 0) return fail(MB200_INVALID_ARGUMENT, "negative extent");
+    }
+    if ((flags & MB200_PERMUTE_PLANAR) && !dtype_is_complex(dtype))
+        return fail(MB200_INVALID_ARGUMENT, "planar output needs a complex dtype");
+    // destination stride of every source mode
+    int64_t dstride_src[MB200_MAX_MODES];
+    int64_t st = 1, total = 1;
+    for (int d = 0; d < nmode; d++) {
+        dstride_src[perm[d]] = st;
+        st *= extents[perm[d]];
+    }
+    for (int i = 0; i < nmode; i++) total *= extents[i];
+    if (total == 0) return MB200_OK;
+    if (!dst || !src) return fail(MB200_INVALID_ARGUMENT, "NULL data pointer");
+    // canonical form: drop extent-1 modes, merge modes adjacent in both layouts
+    PermuteParams q{};
+    for (int i = 0; i < nmode; i++) {
+        if (extents[i] == 1) continue;
+        if (q.n > 0 && dstride_src[i] == q.dst_stride[q.n - 1] * q.ext[q.n - 1]) {
+            q.ext[q.n - 1] *= extents[i];
+        } else {
+            q.ext[q.n] = extents[i];
+            q.dst_stride[q.n] = dstride_src[i];
+            q.n++;
+        }
+    }
+    q.total = total;
+    q.plane_stride = (flags & MB200_PERMUTE_PLANAR) ? total : 0;
+    std::lock_guard<std::mutex> lk(h->mu);
+    MB200_CUDA(cudaSetDevice(h->device));
+    MB200_CUDA(launch_permute(dtype, q, src, dst, h->stream));
+    h->stats.launches_permute++;
+    h->stats.launches_total++;
+    return MB200_OK;
+}
+
+int mb200_shard_plan(int nmodeC, const int32_t *modesC, int nmodeA, const int32_t *modesA,
+                     const int64_t *extentsA, int nmodeB, const int32_t *modesB, const int64_t *extentsB,
+                     int nranks, int rank, int prefer_sum, mb200_shard_info_t *info) {
+    if (!info) return fail(MB200_INVALID_ARGUMENT, "info is NULL");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(MB200_INVALID_ARGUMENT, "bad rank %d / %d", rank, nranks);
+    if (nmodeA < 0 || nmodeB < 0 || nmodeC < 0 || nmodeA > MB200_MAX_MODES || nmodeB > MB200_MAX_MODES ||
+        nmodeC > MB200_MAX_MODES)
+        return fail(MB200_INVALID_ARGUMENT, "nmode out of range");
+    std::memset(info, 0, sizeof *info);
+    info->kind = MB200_SHARD_NONE;
+    info->mode = -1;
+    auto find = [](int n, const int32_t *m, int32_t x) {
+        for (int i = 0; i < n; i++)
+            if (m[i] == x) return i;
+        return -1;
+    };
+    auto set = [&](int kind, int32_t mode, int64_t ext) {
+        info->kind = kind;
+        info->mode = mode;
+        info->begin = ext * rank / nranks;
+        info->end = ext * (rank + 1) / nranks;
+        info->needs_allreduce = kind == MB200_SHARD_SUM;
+    };
+    if (nranks == 1) return MB200_OK;
+    if (prefer_sum) {
+        // slowest summed mode of A with extent >= nranks
+        for (int i = nmodeA - 1; i >= 0; i--) {
+            if (find(nmodeB, modesB, modesA[i]) >= 0 && find(nmodeC, modesC, modesA[i]) < 0 &&
+                extentsA[i] >= nranks) {
+                set(MB200_SHARD_SUM, modesA[i], extentsA[i]);
+                return MB200_OK;
+            }
+        }
+    }
+    // slowest mode of C with extent >= nranks: free (one operand) or batch (both)
+    for (int i = nmodeC - 1; i >= 0; i--) {
+        int ia = find(nmodeA, modesA, modesC[i]), ib = find(nmodeB, modesB, modesC[i]);
+        if (ia < 0 && ib < 0) return fail(MB200_INVALID_ARGUMENT, "mode %d of C is in neither operand", (int)modesC[i]);
+        int64_t ext = ia >= 0 ? extentsA[ia] : extentsB[ib];
+        if (ext >= nranks) {
+            set((ia >= 0 && ib >= 0) ? MB200_SHARD_BATCH : MB200_SHARD_FREE, modesC[i], ext);
+            return MB200_OK;
+        }
+    }
+    if (!prefer_sum) {
+        for (int i = nmodeA - 1; i >= 0; i--) {
+            if (find(nmodeB, modesB, modesA[i]) >= 0 && find(nmodeC, modesC, modesA[i]) < 0 &&
+                extentsA[i] >= nranks) {
+                set(MB200_SHARD_SUM, modesA[i], extentsA[i]);
+                return MB200_OK;
+            }
+        }
+    }
+    return MB200_OK;  // replicas only
+}
+
+int mb200_get_stats(mb200_handle_t h, mb200_stats_t *stats) {
+    MB200_CHECK_HANDLE(h);
+    if (!stats) return fail(MB200_INVALID_ARGUMENT, "stats is NULL");
+    std::lock_guard<std::mutex> lk(h->mu);
+    *stats = h->stats;
+    return MB200_OK;
+}
+
+int mb200_reset_stats(mb200_handle_t h) {
+    MB200_CHECK_HANDLE(h);
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->stats = mb200_stats_t{};
+    return MB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+// K5 — single-kernel direct contraction, plus the two tiny helper kernels (offset tables, dtype
+// promotion). sm_100a.
+//
+// The direct kernel is the launch-bound fast path: one launch, no workspace, no offset tables.
+// Every contraction in the reference's own test-suite (test/unit/operations/binary_einsum.jl) is
+// this size. It is also the general-shape path for outer products / scaling (K <= 2), where the
+// op is a pure streaming kernel, and for empty or zero-extent cases.
+//
+// One thread per output element (grid-stride): decode the element's digits over C's walk modes
+// (left, right, batch) to get base offsets in A, B and C, then run the summed modes with the
+// fastest one as a plain strided inner loop.
+#include "kernels.cuh"
+
+namespace mb200 {
+
+namespace {
+
+__device__ __forceinline__ void cfma(float &acc, float a, float b) { acc = fmaf(a, b, acc); }
+__device__ __forceinline__ void cfma(double &acc, double a, double b) { acc = fma(a, b, acc); }
+__device__ __forceinline__ void cfma(float2 &acc, float2 a, float2 b) {
+    acc.x = fmaf(a.x, b.x, acc.x);
+    acc.x = fmaf(-a.y, b.y, acc.x);
+    acc.y = fmaf(a.x, b.y, acc.y);
+    acc.y = fmaf(a.y, b.x, acc.y);
+}
+__device__ __forceinline__ void cfma(double2 &acc, double2 a, double2 b) {
+    acc.x = fma(a.x, b.x, acc.x);
+    acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y);
+    acc.y = fma(a.y, b.x, acc.y);
+}
+template <typename T> __device__ __forceinline__ T zero_of();
+template <> __device__ __forceinline__ float zero_of<float>() { return 0.f; }
+template <> __device__ __forceinline__ double zero_of<double>() { return 0.0; }
+template <> __device__ __forceinline__ float2 zero_of<float2>() { return make_float2(0.f, 0.f); }
+template <> __device__ __forceinline__ double2 zero_of<double2>() { return make_double2(0.0, 0.0); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) direct_kernel(const __grid_constant__ DirectParams p,
+                                                     const T *__restrict__ A, const T *__restrict__ B,
+                                                     T *__restrict__ C) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t k0 = p.nk > 0 ? p.k_ext[0] : 1;
+    const int64_t sa0 = p.nk > 0 ? p.k_sa[0] : 0;
+    const int64_t sb0 = p.nk > 0 ? p.k_sb[0] : 0;
+    const int64_t outer = p.nk > 0 ? (k0 > 0 ? p.total_k / k0 : 0) : 1;
+    for (int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; id < p.total_c; id += stride) {
+        int64_t r = id, oa = 0, ob = 0, oc = 0;
+        for (int i = 0; i < p.nc; i++) {
+            int64_t e = p.c_ext[i];
+            int64_t d = r % e;
+            r /= e;
+            oa += d * p.c_sa[i];
+            ob += d * p.c_sb[i];
+            oc += d * p.c_sc[i];
+        }
+        T acc = zero_of<T>();
+        if (p.total_k > 0) {
+            for (int64_t ko = 0; ko < outer; ko++) {
+                int64_t q = ko, ka = oa, kb = ob;
+                for (int i = 1; i < p.nk; i++) {
+                    int64_t e = p.k_ext[i];
+                    int64_t d = q % e;
+                    q /= e;
+                    ka += d * p.k_sa[i];
+                    kb += d * p.k_sb[i];
+                }
+                for (int64_t j = 0; j < k0; j++) cfma(acc, A[ka + j * sa0], B[kb + j * sb0]);
+            }
+        }
+        C[oc] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256) table_kernel(int64_t *__restrict__ out, int64_t size,
+                                                    const __grid_constant__ TableSpec spec) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < size; x += stride) {
+        int64_t r = x, off = 0;
+        for (int i = 0; i < spec.n; i++) {
+            int64_t e = spec.ext[i];
+            off += (r % e) * spec.stride[i];
+            r /= e;
+        }
+        out[x] = off;
+    }
+}
+
+template <typename TD, typename TS> __device__ __forceinline__ TD conv(TS v);
+template <> __device__ __forceinline__ double conv<double, float>(float v) { return (double)v; }
+template <> __device__ __forceinline__ float2 conv<float2, float>(float v) { return make_float2(v, 0.f); }
+template <> __device__ __forceinline__ double2 conv<double2, float>(float v) { return make_double2((double)v, 0.0); }
+template <> __device__ __forceinline__ double2 conv<double2, double>(double v) { return make_double2(v, 0.0); }
+template <> __device__ __forceinline__ double2 conv<double2, float2>(float2 v) { return make_double2((double)v.x, (double)v.y); }
+
+template <typename TD, typename TS>
+__global__ void __launch_bounds__(256) convert_kernel(TD *__restrict__ dst, const TS *__restrict__ src,
+                                                      int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        dst[i] = conv<TD, TS>(src[i]);
+}
+
+inline int grid_for(int64_t n, int threads, int cap = 148 * 16) {
+    int64_t g = (n + threads - 1) / threads;
+    if (g < 1) g = 1;
+    if (g > cap) g = cap;
+    return (int)g;
+}
+
+}  // namespace
+
+cudaError_t launch_build_table(int64_t *out, int64_t size, const TableSpec &spec, cudaStream_t s) {
+    table_kernel<<<grid_for(size, 256), 256, 0, s>>>(out, size, spec);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_direct(int dtype, const DirectParams &p, const void *A, const void *B, void *C,
+                          cudaStream_t s) {
+    if (p.total_c <= 0) return cudaSuccess;
+    int g = grid_for(p.total_c, 256);
+    switch (dtype) {
+        case MB200_F32: direct_kernel<float><<<g, 256, 0, s>>>(p, (const float *)A, (const float *)B, (float *)C); break;
+        case MB200_F64: direct_kernel<double><<<g, 256, 0, s>>>(p, (const double *)A, (const double *)B, (double *)C); break;
+        case MB200_C64: direct_kernel<float2><<<g, 256, 0, s>>>(p, (const float2 *)A, (const float2 *)B, (float2 *)C); break;
+        default: direct_kernel<double2><<<g, 256, 0, s>>>(p, (const double2 *)A, (const double2 *)B, (double2 *)C); break;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_convert(int dd, void *dst, int ds, const void *src, int64_t n, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    int g = grid_for(n, 256);
+#define MB200_CONV(TD, TS) convert_kernel<TD, TS><<<g, 256, 0, s>>>((TD *)dst, (const TS *)src, n)
+    if (dd == MB200_F64 && ds == MB200_F32) MB200_CONV(double, float);
+    else if (dd == MB200_C64 && ds == MB200_F32) MB200_CONV(float2, float);
+    else if (dd == MB200_C128 && ds == MB200_F32) MB200_CONV(double2, float);
+    else if (dd == MB200_C128 && ds == MB200_F64) MB200_CONV(double2, double);
+    else if (dd == MB200_C128 && ds == MB200_C64) MB200_CONV(double2, float2);
+    else return cudaErrorInvalidValue;
+#undef MB200_CONV
+    return cudaGetLastError();
+}
+
+}  // namespace mb200

@@ -1,0 +1,392 @@
+// K2 — gather-GEMM ("GETT": TTGT with the transposes fused into the GEMM's loads and stores).
+//
+//   C[rowC[m] + colC[n] + batC[l]] = sum_k A[rowA[m] + kA[k] + batA[l]] * B[colB[n] + kB[k] + batB[l]]
+//
+// The reference's BackendBase does TTGT as four passes (src/Operations/binary_einsum.jl:89-95:
+// permutedims(A), permutedims(B), gemm, permutedims(C)). Here the three permutes never touch HBM:
+// operand tiles are gathered straight from the tensors' native layouts with element-granular
+// cp.async (16 B per ComplexF64 element = half a 32 B sector, so a gather costs at most 2x sector
+// over-fetch from L2 and nothing extra from HBM), and the epilogue scatters C directly in the
+// requested index order. Offsets come from small per-plan int64 tables (rows / columns / k / batch).
+//
+// Compute cores
+//   CoreZ : ComplexF64, FP64 tensor cores  — mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4), complex product
+//           as the 4M real decomposition on interleaved (re,im) fragments: one LDS.128 yields both the
+//           real and the imaginary A (or B) fragment; -Im(A) is a sign-bit flip on the ALU pipe.
+//   CoreD : Float64, DMMA.
+//   CoreC / CoreS : ComplexF32 / Float32 on FFMA (used for shapes the tcgen05 path does not take).
+//
+// Pipeline: STAGES-deep cp.async ring over k-blocks of BK, one __syncthreads per k-block.
+#include "kernels.cuh"
+
+namespace mb200 {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async(void *smem, const void *gmem, int bytes_total, bool valid) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    int src = valid ? bytes_total : 0;
+    if (bytes_total == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem), "r"(src));
+    else if (bytes_total == 8)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(gmem), "r"(src));
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sa), "l"(gmem), "r"(src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double neg_bits(double x) {  // sign flip on the integer pipe
+    return __hiloint2double(__double2hiint(x) ^ 0x80000000, __double2loint(x));
+}
+
+// ------------------------------------------------------------------------------------------------
+// ComplexF64 on DMMA (4M). Warp tile WM x WN complex, m8n8k4 fragments.
+template <int BM_, int BN_, int WM_, int WN_, int BK_, int STAGES_>
+struct CoreZ {
+    using Elem = double2;
+    static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, BK = BK_, STAGES = STAGES_;
+    static constexpr int NWARPS = (BM / WM) * (BN / WN), NTHREADS = 32 * NWARPS;
+    static constexpr int LDA = BM + 2, LDB = BN + 2;  // == 2 (mod 8) in 16 B units: conflict-free LDS.128
+    static constexpr int MT = WM / 8, NT = WN / 8;
+    struct Acc { double re[MT][NT][2], im[MT][NT][2]; };
+    __device__ static void init(Acc &a) {
+#pragma unroll
+        for (int i = 0; i < MT; i++)
+#pragma unroll
+            for (int j = 0; j < NT; j++) a.re[i][j][0] = a.re[i][j][1] = a.im[i][j][0] = a.im[i][j][1] = 0.0;
+    }
+    __device__ static void compute(Acc &acc, const Elem *sa, const Elem *sb, int warp, int lane) {
+        const int wm = (warp % (BM / WM)) * WM, wn = (warp / (BM / WM)) * WN;
+        const int fr = lane >> 2, fk = lane & 3;
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; kk++) {
+            double2 af[MT], bf[NT];
+            double nai[MT];
+#pragma unroll
+            for (int i = 0; i < MT; i++) {
+                af[i] = sa[(kk * 4 + fk) * LDA + wm + i * 8 + fr];
+                nai[i] = neg_bits(af[i].y);
+            }
+#pragma unroll
+            for (int j = 0; j < NT; j++) bf[j] = sb[(kk * 4 + fk) * LDB + wn + j * 8 + fr];
+            // four passes of MT*NT independent DMMAs: consecutive DMMAs never share an accumulator
+#pragma unroll
+            for (int i = 0; i < MT; i++)
+#pragma unroll
+                for (int j = 0; j < NT; j++) dmma(acc.re[i][j][0], acc.re[i][j][1], af[i].x, bf[j].x);
+#pragma unroll
+            for (int i = 0; i < MT; i++)
+#pragma unroll
+                for (int j = 0; j < NT; j++) dmma(acc.im[i][j][0], acc.im[i][j][1], af[i].x, bf[j].y);
+#pragma unroll
+            for (int i = 0; i < MT; i++)
+#pragma unroll
+                for (int j = 0; j < NT; j++) dmma(acc.re[i][j][0], acc.re[i][j][1], nai[i], bf[j].y);
+#pragma unroll
+            for (int i = 0; i < MT; i++)
+#pragma unroll
+                for (int j = 0; j < NT; j++) dmma(acc.im[i][j][0], acc.im[i][j][1], af[i].y, bf[j].x);
+        }
+    }
+    __device__ static void store(const Acc &acc, Elem *C, const int64_t *sRowC, const int64_t *sColC,
+                                 int64_t cb, int mrem, int nrem, int warp, int lane) {
+        const int wm = (warp % (BM / WM)) * WM, wn = (warp / (BM / WM)) * WN;
+        const int fr = lane >> 2, fc = (lane & 3) * 2;
+#pragma unroll
+        for (int j = 0; j < NT; j++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                int c = wn + j * 8 + fc + h;
+                if (c >= nrem) continue;
+                int64_t co = sColC[c] + cb;
+#pragma unroll
+                for (int i = 0; i < MT; i++) {
+                    int r = wm + i * 8 + fr;
+                    if (r < mrem) C[sRowC[r] + co] = make_double2(acc.re[i][j][h], acc.im[i][j][h]);
+                }
+            }
+    }
+};
+
+// Float64 on DMMA.
+template <int BM_, int BN_, int WM_, int WN_, int BK_, int STAGES_>
+struct CoreD {
+    using Elem = double;
+    static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, BK = BK_, STAGES = STAGES_;
+    static constexpr int NWARPS = (BM / WM) * (BN / WN), NTHREADS = 32 * NWARPS;
+    static constexpr int LDA = BM + 4, LDB = BN + 4;  // == 4 (mod 16) in 8 B units: conflict-free LDS.64
+    static constexpr int MT = WM / 8, NT = WN / 8;
+    struct Acc { double c[MT][NT][2]; };
+    __device__ static void init(Acc &a) {
+#pragma unroll
+        for (int i = 0; i < MT; i++)
+#pragma unroll
+            for (int j = 0; j < NT; j++) a.c[i][j][0] = a.c[i][j][1] = 0.0;
+    }
+    __device__ static void compute(Acc &acc, const Elem *sa, const Elem *sb, int warp, int lane) {
+        const int wm = (warp % (BM / WM)) * WM, wn = (warp / (BM / WM)) * WN;
+        const int fr = lane >> 2, fk = lane & 3;
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; kk++) {
+            double af[MT], bf[NT];
+#pragma unroll
+            for (int i = 0; i < MT; i++) af[i] = sa[(kk * 4 + fk) * LDA + wm + i * 8 + fr];
+#pragma unroll
+            for (int j = 0; j < NT; j++) bf[j] = sb[(kk * 4 + fk) * LDB + wn + j * 8 + fr];
+#pragma unroll
+            for (int i = 0; i < MT; i++)
+#pragma unroll
+                for (int j = 0; j < NT; j++) dmma(acc.c[i][j][0], acc.c[i][j][1], af[i], bf[j]);
+        }
+    }
+    __device__ static void store(const Acc &acc, Elem *C, const int64_t *sRowC, const int64_t *sColC,
+                                 int64_t cb, int mrem, int nrem, int warp, int lane) {
+        const int wm = (warp % (BM / WM)) * WM, wn = (warp / (BM / WM)) * WN;
+        const int fr = lane >> 2, fc = (lane & 3) * 2;
+#pragma unroll
+        for (int j = 0; j < NT; j++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                int c = wn + j * 8 + fc + h;
+                if (c >= nrem) continue;
+                int64_t co = sColC[c] + cb;
+#pragma unroll
+                for (int i = 0; i < MT; i++) {
+                    int r = wm + i * 8 + fr;
+                    if (r < mrem) C[sRowC[r] + co] = acc.c[i][j][h];
+                }
+            }
+    }
+};
+
+// ComplexF32 / Float32 on FFMA. 256 threads as 16 x 16; thread (tx, ty) owns rows tx + 16 i and
+// columns ty + 16 j, so a warp's smem reads are 16 consecutive elements (A) or 2 broadcasts (B).
+template <typename E, int BM_, int BN_, int BK_, int STAGES_>
+struct CoreF {
+    using Elem = E;
+    static constexpr int BM = BM_, BN = BN_, BK = BK_, STAGES = STAGES_;
+    static constexpr int NTHREADS = 256;
+    static constexpr int LDA = BM, LDB = BN;
+    static constexpr int TM = BM / 16, TN = BN / 16;
+    struct Acc { E c[TM][TN]; };
+    __device__ static void zero(float &v) { v = 0.f; }
+    __device__ static void zero(float2 &v) { v = make_float2(0.f, 0.f); }
+    __device__ static void mac(float &c, float a, float b) { c = fmaf(a, b, c); }
+    __device__ static void mac(float2 &c, float2 a, float2 b) {
+        c.x = fmaf(a.x, b.x, c.x);
+        c.y = fmaf(a.x, b.y, c.y);
+        c.x = fmaf(-a.y, b.y, c.x);
+        c.y = fmaf(a.y, b.x, c.y);
+    }
+    __device__ static void init(Acc &a) {
+#pragma unroll
+        for (int i = 0; i < TM; i++)
+#pragma unroll
+            for (int j = 0; j < TN; j++) zero(a.c[i][j]);
+    }
+    __device__ static void compute(Acc &acc, const Elem *sa, const Elem *sb, int warp, int lane) {
+        const int tid = warp * 32 + lane, tx = tid & 15, ty = tid >> 4;
+#pragma unroll
+        for (int k = 0; k < BK; k++) {
+            E af[TM], bf[TN];
+#pragma unroll
+            for (int i = 0; i < TM; i++) af[i] = sa[k * LDA + tx + 16 * i];
+#pragma unroll
+            for (int j = 0; j < TN; j++) bf[j] = sb[k * LDB + ty + 16 * j];
+#pragma unroll
+            for (int i = 0; i < TM; i++)
+#pragma unroll
+                for (int j = 0; j < TN; j++) mac(acc.c[i][j], af[i], bf[j]);
+        }
+    }
+    __device__ static void store(const Acc &acc, Elem *C, const int64_t *sRowC, const int64_t *sColC,
+                                 int64_t cb, int mrem, int nrem, int warp, int lane) {
+        const int tid = warp * 32 + lane, tx = tid & 15, ty = tid >> 4;
+#pragma unroll
+        for (int j = 0; j < TN; j++) {
+            int c = ty + 16 * j;
+            if (c >= nrem) continue;
+            int64_t co = sColC[c] + cb;
+#pragma unroll
+            for (int i = 0; i < TM; i++) {
+                int r = tx + 16 * i;
+                if (r < mrem) C[sRowC[r] + co] = acc.c[i][j];
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+template <class Core>
+constexpr size_t gett_smem_bytes() {
+    return (size_t)Core::STAGES * Core::BK * (Core::LDA + Core::LDB) * sizeof(typename Core::Elem) +
+           (size_t)(Core::BM + Core::BN) * 2 * sizeof(int64_t);
+}
+
+// Tile order: groups of GROUP_M row tiles, walked column by column inside a group, so the CTAs of a
+// wave share a few A row-panels (kept in the 126 MB L2) while B column-panels stream through.
+constexpr int GROUP_M = 8;
+
+template <class Core>
+__global__ void __launch_bounds__(Core::NTHREADS, 1) gett_kernel(const __grid_constant__ GettParams p) {
+    using E = typename Core::Elem;
+    constexpr int BM = Core::BM, BN = Core::BN, BK = Core::BK, S = Core::STAGES;
+    constexpr int LDA = Core::LDA, LDB = Core::LDB, NT = Core::NTHREADS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    E *sA = reinterpret_cast<E *>(smem_raw);
+    E *sB = sA + (size_t)S * BK * LDA;
+    int64_t *sRowA = reinterpret_cast<int64_t *>(sB + (size_t)S * BK * LDB);
+    int64_t *sColB = sRowA + BM;
+    int64_t *sRowC = sColB + BN;
+    int64_t *sColC = sRowC + BM;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+    const int64_t tiles = tiles_m * tiles_n;
+    const int64_t l = blockIdx.x / tiles;
+    const int64_t t = blockIdx.x % tiles;
+    // grouped rasterisation
+    const int64_t per_group = GROUP_M * tiles_n;
+    const int64_t g = t / per_group;
+    const int64_t gm0 = g * GROUP_M;
+    const int64_t gsz = (tiles_m - gm0) < GROUP_M ? (tiles_m - gm0) : GROUP_M;
+    const int64_t tm = gm0 + (t % per_group) % gsz;
+    const int64_t tn = (t % per_group) / gsz;
+    const int64_t m0 = tm * BM, n0 = tn * BN;
+    const int mrem = (int)((p.M - m0) < BM ? (p.M - m0) : BM);
+    const int nrem = (int)((p.N - n0) < BN ? (p.N - n0) : BN);
+
+    for (int i = tid; i < BM; i += NT) {
+        bool v = i < mrem;
+        sRowA[i] = v ? p.rowA[m0 + i] : 0;
+        sRowC[i] = v ? p.rowC[m0 + i] : 0;
+    }
+    for (int i = tid; i < BN; i += NT) {
+        bool v = i < nrem;
+        sColB[i] = v ? p.colB[n0 + i] : 0;
+        sColC[i] = v ? p.colC[n0 + i] : 0;
+    }
+    const int64_t ab = p.batA[l], bb = p.batB[l], cb = p.batC[l];
+    __syncthreads();
+
+    const E *gA = reinterpret_cast<const E *>(p.A) + ab;
+    const E *gB = reinterpret_cast<const E *>(p.B) + bb;
+    const int64_t KB = (p.K + BK - 1) / BK;
+
+    auto load_tile = [&](int stage, int64_t kb) {
+        E *da = sA + (size_t)stage * BK * LDA;
+        E *db = sB + (size_t)stage * BK * LDB;
+        const int64_t kbase = kb * BK;
+#pragma unroll
+        for (int i = tid; i < BM * BK; i += NT) {
+            int m, k;
+            if (p.a_kmajor) { k = i % BK; m = i / BK; } else { m = i % BM; k = i / BM; }
+            bool v = (m < mrem) && (kbase + k < p.K);
+            int64_t off = v ? (sRowA[m] + p.kA[kbase + k]) : 0;
+            cp_async(da + k * LDA + m, gA + off, (int)sizeof(E), v);
+        }
+#pragma unroll
+        for (int i = tid; i < BN * BK; i += NT) {
+            int n, k;
+            if (p.b_kmajor) { k = i % BK; n = i / BK; } else { n = i % BN; k = i / BN; }
+            bool v = (n < nrem) && (kbase + k < p.K);
+            int64_t off = v ? (sColB[n] + p.kB[kbase + k]) : 0;
+            cp_async(db + k * LDB + n, gB + off, (int)sizeof(E), v);
+        }
+    };
+
+    typename Core::Acc acc;
+    Core::init(acc);
+
+#pragma unroll
+    for (int s = 0; s < S - 1; s++) {
+        if (s < KB) load_tile(s, s);
+        cp_async_commit();
+    }
+    for (int64_t kb = 0; kb < KB; kb++) {
+        cp_async_wait<S - 2>();
+        __syncthreads();
+        int64_t nk = kb + S - 1;
+        if (nk < KB) load_tile((int)(nk % S), nk);
+        cp_async_commit();
+        const int st = (int)(kb % S);
+        Core::compute(acc, sA + (size_t)st * BK * LDA, sB + (size_t)st * BK * LDB, warp, lane);
+    }
+    cp_async_wait<0>();
+    Core::store(acc, reinterpret_cast<E *>(p.C), sRowC, sColC, cb, mrem, nrem, warp, lane);
+}
+
+template <class Core>
+cudaError_t launch(const GettParams &p, cudaStream_t s) {
+    const int64_t tiles_m = (p.M + Core::BM - 1) / Core::BM, tiles_n = (p.N + Core::BN - 1) / Core::BN;
+    const int64_t grid = tiles_m * tiles_n * p.L;
+    if (grid <= 0) return cudaSuccess;
+    if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    gett_kernel<Core><<<(unsigned)grid, Core::NTHREADS, gett_smem_bytes<Core>(), s>>>(p);
+    return cudaGetLastError();
+}
+template <class Core>
+cudaError_t configure() {
+    return cudaFuncSetAttribute(gett_kernel<Core>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)gett_smem_bytes<Core>());
+}
+
+// tile menus ---------------------------------------------------------------------------------------
+using Z_128x64 = CoreZ<128, 64, 32, 32, 8, 4>;   // main ComplexF64 tile: 8 warps x (32 x 32)
+using Z_128x16 = CoreZ<128, 16, 16, 16, 8, 4>;   // skinny N (MPS-MPO middle step: N = K = 16)
+using Z_16x128 = CoreZ<16, 128, 16, 16, 8, 4>;   // skinny M
+using D_128x128 = CoreD<128, 128, 64, 32, 8, 4>; // Float64: 8 warps x (64 x 32)
+using D_128x16 = CoreD<128, 16, 16, 16, 8, 4>;
+using D_16x128 = CoreD<16, 128, 16, 16, 8, 4>;
+using C_128x64 = CoreF<float2, 128, 64, 8, 4>;   // ComplexF32 FFMA: thread tile 8 x 4
+using C_128x16 = CoreF<float2, 128, 16, 8, 4>;
+using C_16x128 = CoreF<float2, 16, 128, 8, 4>;
+using S_128x128 = CoreF<float, 128, 128, 8, 4>;  // Float32 FFMA: thread tile 8 x 8
+using S_128x16 = CoreF<float, 128, 16, 8, 4>;
+using S_16x128 = CoreF<float, 16, 128, 8, 4>;
+
+}  // namespace
+
+cudaError_t gett_configure() {
+    cudaError_t e;
+#define MB200_CFG(C) if ((e = configure<C>()) != cudaSuccess) return e
+    MB200_CFG(Z_128x64); MB200_CFG(Z_128x16); MB200_CFG(Z_16x128);
+    MB200_CFG(D_128x128); MB200_CFG(D_128x16); MB200_CFG(D_16x128);
+    MB200_CFG(C_128x64); MB200_CFG(C_128x16); MB200_CFG(C_16x128);
+    MB200_CFG(S_128x128); MB200_CFG(S_128x16); MB200_CFG(S_16x128);
+#undef MB200_CFG
+    return cudaSuccess;
+}
+
+cudaError_t launch_gett_f64(int dtype, const GettParams &p, cudaStream_t s) {
+    if (dtype == MB200_C128) {
+        if (p.N <= 16 && p.M > 16) return launch<Z_128x16>(p, s);
+        if (p.M <= 16 && p.N > 16) return launch<Z_16x128>(p, s);
+        return launch<Z_128x64>(p, s);
+    }
+    if (p.N <= 16 && p.M > 16) return launch<D_128x16>(p, s);
+    if (p.M <= 16 && p.N > 16) return launch<D_16x128>(p, s);
+    return launch<D_128x128>(p, s);
+}
+
+cudaError_t launch_simt_f32(int dtype, const GettParams &p, cudaStream_t s) {
+    if (dtype == MB200_C64) {
+        if (p.N <= 16 && p.M > 16) return launch<C_128x16>(p, s);
+        if (p.M <= 16 && p.N > 16) return launch<C_16x128>(p, s);
+        return launch<C_128x64>(p, s);
+    }
+    if (p.N <= 16 && p.M > 16) return launch<S_128x16>(p, s);
+    if (p.M <= 16 && p.N > 16) return launch<S_16x128>(p, s);
+    return launch<S_128x128>(p, s);
+}
+
+}  // namespace mb200

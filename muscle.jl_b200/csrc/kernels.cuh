@@ -1,0 +1,61 @@
+// Launch interfaces of the sm_100a kernels behind libmuscle_b200 (one translation unit each).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "common.hpp"
+
+namespace mb200 {
+
+// ---- offset tables -----------------------------------------------------------------------------
+// out[x] = sum_i digit_i(x) * stride[i], digits of x over `ext` (mode 0 fastest). n == 0 -> out[0]=0.
+struct TableSpec {
+    int n;
+    int64_t ext[MB200_MAX_MODES];
+    int64_t stride[MB200_MAX_MODES];
+};
+cudaError_t launch_build_table(int64_t *out, int64_t size, const TableSpec &spec, cudaStream_t s);
+
+// ---- K5: direct single-kernel contraction ----------------------------------------------------------
+struct DirectParams {
+    int nc;  // C-walk modes: left, right, batch (extent-1 removed)
+    int64_t c_ext[MB200_MAX_MODES], c_sc[MB200_MAX_MODES], c_sa[MB200_MAX_MODES], c_sb[MB200_MAX_MODES];
+    int nk;  // summed modes
+    int64_t k_ext[MB200_MAX_MODES], k_sa[MB200_MAX_MODES], k_sb[MB200_MAX_MODES];
+    int64_t total_c, total_k;
+};
+cudaError_t launch_direct(int dtype, const DirectParams &p, const void *A, const void *B, void *C,
+                          cudaStream_t s);
+
+// ---- K2 / FP32 SIMT: gather-GEMM ---------------------------------------------------------------------
+// C[rowC[m] + colC[n] + batC[l]] = sum_k A[rowA[m] + kA[k] + batA[l]] * B[colB[n] + kB[k] + batB[l]]
+// All offsets are in ELEMENTS of the compute dtype.
+struct GettParams {
+    const void *A, *B;
+    void *C;
+    const int64_t *rowA, *kA, *batA;
+    const int64_t *colB, *kB, *batB;
+    const int64_t *rowC, *colC, *batC;
+    int64_t M, N, K, L;
+    int a_kmajor, b_kmajor;
+};
+cudaError_t launch_gett_f64(int dtype, const GettParams &p, cudaStream_t s);   // F64 / C128, DMMA
+cudaError_t launch_simt_f32(int dtype, const GettParams &p, cudaStream_t s);   // F32 / C64, FFMA
+cudaError_t gett_configure();  // opt-in shared memory attributes; call once per device
+
+// ---- dtype promotion (mixed-eltype operands) -------------------------------------------------------
+cudaError_t launch_convert(int dtype_dst, void *dst, int dtype_src, const void *src, int64_t n,
+                           cudaStream_t s);
+
+// ---- K1: permute / matricise ---------------------------------------------------------------------------
+struct PermuteParams {
+    int n;                               // canonical modes (extent-1 dropped, adjacent merged)
+    int64_t ext[MB200_MAX_MODES];        // in SOURCE order (mode 0 = source unit stride)
+    int64_t dst_stride[MB200_MAX_MODES]; // stride of each source mode in the destination (elements)
+    int64_t total;
+    int64_t plane_stride;                // != 0: complex dst written planar, im plane at +plane_stride
+};
+cudaError_t launch_permute(int dtype, const PermuteParams &p, const void *src, void *dst, cudaStream_t s);
+
+}  // namespace mb200

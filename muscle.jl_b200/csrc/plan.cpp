@@ -1,0 +1,228 @@
+// Contraction planner (host only). See plan.hpp.
+#include "plan.hpp"
+
+#include <algorithm>
+#include <cstring>
+
+namespace mb200 {
+
+std::string &last_error() {
+    thread_local std::string e;
+    return e;
+}
+
+int fail(int status, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    last_error() = buf;
+    return status;
+}
+
+int make_desc(TensorDesc &d, int dtype, int nmode, const int32_t *modes, const int64_t *extents,
+              const int64_t *strides, const char *name) {
+    if (!dtype_valid(dtype)) return fail(MB200_INVALID_ARGUMENT, "%s: unknown dtype %d", name, dtype);
+    if (nmode < 0 || nmode > MB200_MAX_MODES)
+        return fail(MB200_INVALID_ARGUMENT, "%s: nmode %d outside [0, %d]", name, nmode, MB200_MAX_MODES);
+    if (nmode > 0 && (!modes || !extents))
+        return fail(MB200_INVALID_ARGUMENT, "%s: modes/extents must not be NULL when nmode > 0", name);
+    d.dtype = dtype;
+    d.n = nmode;
+    int64_t s = 1;
+    for (int i = 0; i < nmode; i++) {
+        d.modes[i] = modes[i];
+        d.ext[i] = extents[i];
+        if (extents[i] < 0) return fail(MB200_INVALID_ARGUMENT, "%s: negative extent", name);
+        for (int j = 0; j < i; j++)
+            if (modes[j] == modes[i])
+                return fail(MB200_INVALID_ARGUMENT,
+                            "%s: mode %d is repeated inside one tensor (traces/diagonals are unary_einsum, "
+                            "not binary_einsum)", name, (int)modes[i]);
+        d.stride[i] = strides ? strides[i] : s;
+        s *= extents[i];
+    }
+    return MB200_OK;
+}
+
+static int find_mode(const TensorDesc &t, int32_t m) {
+    for (int i = 0; i < t.n; i++)
+        if (t.modes[i] == m) return i;
+    return -1;
+}
+
+int make_plan(const TensorDesc &A, const TensorDesc &B, TensorDesc &C, const int64_t *stridesC,
+              int forced_path, Plan &plan) {
+    // ---- validation -------------------------------------------------------------------------
+    if (C.dtype != dtype_promote(A.dtype, B.dtype))
+        return fail(MB200_INVALID_ARGUMENT, "eltype of C (%s) must be promote_eltype(A, B) = %s",
+                    dtype_name(C.dtype), dtype_name(dtype_promote(A.dtype, B.dtype)));
+    for (int i = 0; i < C.n; i++)
+        for (int j = 0; j < i; j++)
+            if (C.modes[i] == C.modes[j])
+                return fail(MB200_INVALID_ARGUMENT, "C: mode %d is repeated", (int)C.modes[i]);
+    for (int i = 0; i < A.n; i++) {
+        int j = find_mode(B, A.modes[i]);
+        if (j >= 0 && A.ext[i] != B.ext[j])
+            return fail(MB200_DIMENSION_MISMATCH, "mode %d has extent %lld in A but %lld in B",
+                        (int)A.modes[i], (long long)A.ext[i], (long long)B.ext[j]);
+        if (j < 0 && find_mode(C, A.modes[i]) < 0)
+            return fail(MB200_INVALID_ARGUMENT,
+                        "mode %d appears only in A and not in the output (a free index missing from C is "
+                        "rejected, as by BackendBase)", (int)A.modes[i]);
+    }
+    for (int i = 0; i < B.n; i++)
+        if (find_mode(A, B.modes[i]) < 0 && find_mode(C, B.modes[i]) < 0)
+            return fail(MB200_INVALID_ARGUMENT,
+                        "mode %d appears only in B and not in the output (a free index missing from C is "
+                        "rejected, as by BackendBase)", (int)B.modes[i]);
+    // C extents are implied by A / B
+    {
+        int64_t s = 1;
+        for (int i = 0; i < C.n; i++) {
+            int ia = find_mode(A, C.modes[i]), ib = find_mode(B, C.modes[i]);
+            if (ia < 0 && ib < 0)
+                return fail(MB200_INVALID_ARGUMENT, "mode %d of the output is found in neither operand",
+                            (int)C.modes[i]);
+            C.ext[i] = ia >= 0 ? A.ext[ia] : B.ext[ib];
+            C.stride[i] = stridesC ? stridesC[i] : s;
+            s *= C.ext[i];
+        }
+    }
+
+    plan = Plan();
+    plan.dtype = C.dtype;
+
+    // ---- swap so that C's unit-stride mode is a row mode --------------------------------------
+    // The kernels store C with consecutive rows (m) in consecutive lanes.
+    int fastestC = -1;
+    {
+        int64_t best = INT64_MAX;
+        for (int i = 0; i < C.n; i++)
+            if (C.ext[i] > 1 && C.stride[i] < best) { best = C.stride[i]; fastestC = i; }
+    }
+    bool swap = false;
+    if (fastestC >= 0) {
+        int32_t m = C.modes[fastestC];
+        if (find_mode(A, m) < 0 && find_mode(B, m) >= 0) swap = true;
+    }
+    const TensorDesc &R = swap ? B : A;   // row operand
+    const TensorDesc &Q = swap ? A : B;   // column operand
+    plan.swapped = swap;
+    plan.dtype_row = R.dtype;
+    plan.dtype_col = Q.dtype;
+
+    // ---- classification -----------------------------------------------------------------------
+    for (int i = 0; i < R.n; i++) {
+        if (R.ext[i] == 1) continue;  // extent-1 modes never contribute to an address
+        int32_t m = R.modes[i];
+        int iq = find_mode(Q, m), ic = find_mode(C, m);
+        GroupMode g{m, R.ext[i], R.stride[i], iq >= 0 ? Q.stride[iq] : 0, ic >= 0 ? C.stride[ic] : 0};
+        if (iq >= 0 && ic >= 0) plan.batch.push_back(g);
+        else if (iq >= 0) plan.sum.push_back(g);
+        else plan.left.push_back(g);
+    }
+    for (int i = 0; i < Q.n; i++) {
+        if (Q.ext[i] == 1) continue;
+        int32_t m = Q.modes[i];
+        if (find_mode(R, m) >= 0) continue;
+        int ic = find_mode(C, m);
+        plan.right.push_back(GroupMode{m, Q.ext[i], 0, Q.stride[i], C.stride[ic]});
+    }
+    plan.empty_output = false;
+    for (int i = 0; i < C.n; i++)
+        if (C.ext[i] == 0) plan.empty_output = true;
+
+    // ---- walk order inside each group ----------------------------------------------------------
+    auto by_sc = [](const GroupMode &x, const GroupMode &y) { return x.sc < y.sc; };
+    auto by_sa = [](const GroupMode &x, const GroupMode &y) { return x.sa < y.sa; };
+    auto by_sb = [](const GroupMode &x, const GroupMode &y) { return x.sb < y.sb; };
+    std::stable_sort(plan.left.begin(), plan.left.end(), by_sc);
+    std::stable_sort(plan.right.begin(), plan.right.end(), by_sc);
+    std::stable_sort(plan.batch.begin(), plan.batch.end(), by_sc);
+    // unit-stride mode of each operand decides whether lanes should run along k when loading it
+    auto fastest_is_sum = [&](const TensorDesc &T) {
+        int64_t best = INT64_MAX;
+        int32_t m = -1;
+        for (int i = 0; i < T.n; i++)
+            if (T.ext[i] > 1 && T.stride[i] < best) { best = T.stride[i]; m = T.modes[i]; }
+        if (m < 0) return false;
+        for (auto &g : plan.sum)
+            if (g.label == m) return true;
+        return false;
+    };
+    plan.a_kmajor = fastest_is_sum(R);
+    plan.b_kmajor = fastest_is_sum(Q);
+    // summed modes follow the row operand's memory order (the reference uses A's label order,
+    // binary_einsum.jl:77; any common order is valid) unless only the column operand is K-major.
+    if (plan.b_kmajor && !plan.a_kmajor) std::stable_sort(plan.sum.begin(), plan.sum.end(), by_sb);
+    else std::stable_sort(plan.sum.begin(), plan.sum.end(), by_sa);
+
+    auto prod = [](const std::vector<GroupMode> &g) {
+        int64_t p = 1;
+        for (auto &x : g) p *= x.extent;
+        return p;
+    };
+    plan.M = prod(plan.left);
+    plan.N = prod(plan.right);
+    plan.K = prod(plan.sum);
+    plan.L = prod(plan.batch);
+    double macs = (double)plan.M * (double)plan.N * (double)plan.K * (double)plan.L;
+    plan.flops = (dtype_is_complex(plan.dtype) ? 8.0 : 2.0) * macs;
+    plan.bytes = (double)dtype_size(plan.dtype) *
+                 ((double)A.numel() + (double)B.numel() + (double)plan.M * plan.N * plan.L);
+
+    // ---- kernel family ---------------------------------------------------------------------------
+    const int64_t TABLE_LIMIT = (int64_t)1 << 26;
+    bool tables_ok = plan.M <= TABLE_LIMIT && plan.N <= TABLE_LIMIT && plan.K <= TABLE_LIMIT &&
+                     plan.L <= TABLE_LIMIT;
+    int path;
+    if (plan.empty_output || macs <= (double)(1 << 20) || plan.K <= 2 || !tables_ok)
+        path = MB200_PATH_DIRECT;
+    else
+        path = dtype_is_double(plan.dtype) ? MB200_PATH_GETT_F64 : MB200_PATH_SIMT_F32;
+    if (forced_path != MB200_PATH_AUTO) {
+        if (forced_path == MB200_PATH_DIRECT) path = MB200_PATH_DIRECT;
+        else if (!plan.empty_output && tables_ok) {
+            if (forced_path == MB200_PATH_GETT_F64 && dtype_is_double(plan.dtype)) path = forced_path;
+            if (forced_path == MB200_PATH_SIMT_F32 && !dtype_is_double(plan.dtype)) path = forced_path;
+            if (forced_path == MB200_PATH_TCGEN05_TF32 && !dtype_is_double(plan.dtype)) path = forced_path;
+        }
+    }
+    plan.path = path;
+
+    // ---- cache key ----------------------------------------------------------------------------------
+    std::string &k = plan.key;
+    k.clear();
+    auto put = [&k](int64_t v) { k.append(reinterpret_cast<const char *>(&v), sizeof v); };
+    put(forced_path);
+    for (const TensorDesc *t : {&A, &B, (const TensorDesc *)&C}) {
+        put(t->dtype);
+        put(t->n);
+        for (int i = 0; i < t->n; i++) { put(t->modes[i]); put(t->ext[i]); put(t->stride[i]); }
+    }
+    return MB200_OK;
+}
+
+void fill_info(const Plan &p, mb200_plan_info_t *info) {
+    std::memset(info, 0, sizeof *info);
+    info->M = p.M; info->N = p.N; info->K = p.K; info->L = p.L;
+    info->swapped = p.swapped;
+    info->path = p.path;
+    info->compute_dtype = p.dtype;
+    info->n_left = (int)p.left.size();
+    info->n_right = (int)p.right.size();
+    info->n_sum = (int)p.sum.size();
+    info->n_batch = (int)p.batch.size();
+    for (size_t i = 0; i < p.left.size(); i++) info->left[i] = p.left[i].label;
+    for (size_t i = 0; i < p.right.size(); i++) info->right[i] = p.right[i].label;
+    for (size_t i = 0; i < p.sum.size(); i++) info->sum[i] = p.sum[i].label;
+    for (size_t i = 0; i < p.batch.size(); i++) info->batch[i] = p.batch[i].label;
+    info->a_kmajor = p.a_kmajor;
+    info->b_kmajor = p.b_kmajor;
+    info->flops = p.flops;
+    info->bytes = p.bytes;
+}
+
+}  // namespace mb200

@@ -1,0 +1,331 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on the same seeded inputs,
+the reference's known-answer battery replayed on BackendB200, the committed golden vectors, and
+size-independent properties at the BASELINE.json sizes.
+
+Tolerances (north star): rel. Frobenius <= 1e-12 for Float64/ComplexF64, <= 1e-5 for Float32/ComplexF32;
+index bookkeeping / output placement bit-exact (integer-valued inputs, compared with ==).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import muscle_b200 as mb
+from muscle_b200 import B200Array, BackendB200, Index, Tensor, _lib, binary_einsum, binary_einsum_, with_backend
+from cases import PARITY_CASES, REFERENCE_BATTERY, build_case, integer_array, random_array
+from oracle import binary_einsum_general, rel_frobenius
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"float32": 1e-5, "complex64": 1e-5, "float64": 1e-12, "complex128": 1e-12}
+DTYPES = ["float32", "float64", "complex64", "complex128"]
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "binary_einsum_golden.npz")
+
+
+def I(s):
+    return [Index(c) for c in s]
+
+
+@pytest.fixture(autouse=True)
+def _auto_path():
+    yield
+    _lib.Handle.get().set_path(mb.PATH_AUTO)
+
+
+def contract(a, ia, b, ib, ic, device=True, path=mb.PATH_AUTO):
+    _lib.Handle.get().set_path(path)
+    ta, tb = Tensor(a, I(ia)), Tensor(b, I(ib))
+    if device:
+        ta, tb = ta.to_device(), tb.to_device()
+    c = binary_einsum(BackendB200(), I(ic), ta, tb)
+    assert c.inds == I(ic)
+    assert c.on_device == device
+    return c.to_host().data
+
+
+# ---- the reference's own battery on the new backend --------------------------------------------
+@pytest.mark.parametrize("device", [False, True], ids=["host_entry", "device_entry"])
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("case", REFERENCE_BATTERY, ids=[c[0] for c in REFERENCE_BATTERY])
+def test_reference_battery(case, dt, device):
+    """test/unit/operations/binary_einsum.jl:4-154 re-run per backend, the way
+    test/integration/{strided,omeinsum,cuda}.jl do; hyperindex cases succeed as on cuTENSOR/OMEinsum."""
+    name, sa, ia, sb, ib, kw, exp_inds, exp_shape, exp_val, hyper = case
+    A, B = Tensor(np.ones(sa, dt), I(ia)), Tensor(np.ones(sb, dt), I(ib))
+    if device:
+        A, B = A.to_device(), B.to_device()
+    kwargs = {k: I(v) for k, v in kw.items()}
+    Cc = with_backend(lambda: binary_einsum(A, B, **kwargs), BackendB200())
+    assert Cc.inds == I(exp_inds)
+    assert Cc.shape == exp_shape
+    got = Cc.to_host().data
+    assert got.dtype == np.dtype(dt)
+    assert np.array_equal(got, np.full(exp_shape, exp_val, dt))
+
+
+def test_reference_scale_and_mixed_eltypes():
+    """scale — binary_einsum.jl:96-119; mixed ComplexF64 × Float64 — omeinsum.jl:160-186, cuda.jl:100-124."""
+    for dt in (np.float64, np.complex128, np.float32, np.complex64):
+        A = Tensor(np.ones((2, 3), dt), I("ij"))
+        alpha = Tensor(np.array(2.0))
+        for dev in (False, True):
+            a, al = (A.to_device(), alpha.to_device()) if dev else (A, alpha)
+            for x, y in ((a, al), (al, a)):
+                Cc = with_backend(lambda: binary_einsum(x, y), BackendB200())
+                assert Cc.inds == I("ij")
+                exp_dt = np.result_type(dt, np.float64)
+                got = Cc.to_host().data
+                assert got.dtype == exp_dt and np.array_equal(got, 2.0 * np.ones((2, 3), exp_dt))
+                Cc = with_backend(lambda: binary_einsum(x, y, out=I("ji")), BackendB200())
+                assert Cc.shape == (3, 2) and np.array_equal(Cc.to_host().data, 2.0 * np.ones((3, 2), exp_dt))
+
+
+def test_auto_dispatch_on_device_arrays():
+    """Domain(B200Array) → BackendB200 without with_backend (pattern ext/MuscleCUDAExt.jl:7, binary_einsum.jl:21);
+    host/device "hybrid" operands (test/integration/reactant.jl:36-39)."""
+    A = Tensor(np.ones((2, 3)), I("ij"))
+    B = Tensor(np.ones((3, 4)), I("jk"))
+    for x, y in ((A.to_device(), B.to_device()), (A.to_device(), B), (A, B.to_device())):
+        Cc = binary_einsum(x, y)
+        assert Cc.on_device and np.array_equal(Cc.to_host().data, 3 * np.ones((2, 4)))
+
+
+def test_inplace():
+    """binary_einsum!(c, a, b) writes parent(c) in inds(c) order and returns c (binary_einsum.jl:57-70)."""
+    rng = np.random.default_rng(5)
+    a, b = random_array(rng, (6, 7, 5), "complex128"), random_array(rng, (5, 4, 7), "complex128")
+    ref = binary_einsum_general(list("li"), a, list("ijk"), b, list("klj"))
+    Cd = Tensor(B200Array((4, 6), "complex128"), I("li"))
+    out = binary_einsum_(Cd, Tensor(a, I("ijk")).to_device(), Tensor(b, I("klj")).to_device())
+    assert out is Cd and rel_frobenius(Cd.to_host().data, ref) <= 1e-12
+    Ch = Tensor(np.zeros((4, 6), np.complex128, order="F"), I("li"))
+    with_backend(lambda: binary_einsum_(Ch, Tensor(a, I("ijk")), Tensor(b, I("klj"))), BackendB200())
+    assert rel_frobenius(Ch.data, ref) <= 1e-12
+
+
+# ---- random-data parity against the oracle --------------------------------------------------------
+@pytest.mark.parametrize("path", ["auto", "direct", "tiled"])
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("case", PARITY_CASES, ids=[c[0] for c in PARITY_CASES])
+def test_parity_random(case, dt, path):
+    a, ia, b, ib, ic = build_case(case, dt, seed=11)
+    ref = binary_einsum_general(ic, a, ia, b, ib)
+    p = {"auto": mb.PATH_AUTO, "direct": mb.PATH_DIRECT,
+         "tiled": mb.PATH_GETT_F64 if np.dtype(dt).itemsize >= 8 and dt != "complex64" else mb.PATH_SIMT_F32}[path]
+    got = contract(a, ia, b, ib, ic, device=True, path=p)
+    assert got.shape == ref.shape and got.dtype == ref.dtype
+    assert rel_frobenius(got, ref) <= TOL[dt], (case[0], dt, path)
+
+
+@pytest.mark.parametrize("path", ["direct", "tiled"])
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("case", PARITY_CASES, ids=[c[0] for c in PARITY_CASES])
+def test_bookkeeping_bit_exact(case, dt, path):
+    """Integer-valued inputs: every product and sum is exact, so any misplaced element, wrong stride or
+    wrong classification shows up as inequality. Bit-exact (==) against the oracle."""
+    a, ia, b, ib, ic = build_case(case, dt, seed=23, integer=True)
+    ref = binary_einsum_general(ic, a, ia, b, ib)
+    p = {"direct": mb.PATH_DIRECT,
+         "tiled": mb.PATH_GETT_F64 if np.dtype(dt).itemsize >= 8 and dt != "complex64" else mb.PATH_SIMT_F32}[path]
+    got = contract(a, ia, b, ib, ic, device=True, path=p)
+    assert np.array_equal(got, ref), (case[0], dt, path)
+
+
+def test_golden_vectors():
+    g = np.load(GOLDEN)
+    by_name = {c[0]: c for c in PARITY_CASES}
+    keys = sorted({k.rsplit("__", 1)[0] for k in g.files})
+    for key in keys:
+        name, dt = key.split("__")
+        _, _, ia, ib, ic = by_name[name]
+        for device in (False, True):
+            got = contract(g[key + "__a"], ia, g[key + "__b"], ib, ic, device=device)
+            assert got.shape == g[key + "__c"].shape
+            assert rel_frobenius(got, g[key + "__c"]) <= TOL[dt], key
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_multi_tile_shapes(dt):
+    """Several CTA tiles, ragged edges, grouped rasterisation, K not a multiple of the k-block."""
+    rng = np.random.default_rng(2)
+    for (m, n, k, l) in [(1000, 520, 300, 1), (257, 129, 65, 3), (4100, 70, 33, 1), (70, 4100, 33, 1),
+                         (130, 18, 1030, 2), (18, 130, 1030, 2)]:
+        a = random_array(rng, (k, m, l), dt)
+        b = random_array(rng, (n, l, k), dt)
+        ref = np.einsum("kml,nlk->nml", a, b, optimize=True)
+        got = contract(a, "kml", b, "nlk", "nml")
+        assert rel_frobenius(got, ref) <= TOL[dt], (m, n, k, l, dt)
+        got = contract(a, "kml", b, "nlk", "mln")
+        assert rel_frobenius(got, np.transpose(ref, (1, 2, 0))) <= TOL[dt], (m, n, k, l, dt)
+
+
+def test_mixed_eltypes_promote():
+    rng = np.random.default_rng(9)
+    for da, db in [("float64", "complex128"), ("complex64", "float32"), ("float32", "float64"),
+                   ("complex64", "float64"), ("complex128", "complex64")]:
+        a, b = random_array(rng, (40, 30), da), random_array(rng, (30, 50), db)
+        ref = binary_einsum_general(list("ik"), a, list("ij"), b, list("jk"))
+        for path in (mb.PATH_DIRECT, mb.PATH_AUTO):
+            got = contract(a, "ij", b, "jk", "ik", path=path)
+            assert got.dtype == ref.dtype
+            assert rel_frobenius(got, ref) <= (1e-5 if ref.dtype.itemsize <= 8 and ref.dtype != np.float64 else 1e-12)
+
+
+def test_strided_operands_through_c_abi():
+    """A slab of a larger array (the free-index shard case: strides passed explicitly, no copy)."""
+    rng = np.random.default_rng(4)
+    a_full = random_array(rng, (12, 9, 10), "complex128")     # [i, k, s]
+    b = random_array(rng, (9, 7), "complex128")               # [k, j]
+    dA, dB = B200Array.from_host(a_full), B200Array.from_host(b)
+    dC = B200Array((12, 7, 4), "complex128")                  # [i, j, s] for s in 3:7
+    h = _lib.Handle.get()
+    s0 = 3
+    ptrA = dA.ptr + s0 * 12 * 9 * 16
+    _lib.check(mb.lib().mb200_binary_einsum(
+        h.ptr, C.c_void_p(dC.ptr), _lib.C128, 3, _lib.i32([0, 2, 3]), None,
+        C.c_void_p(ptrA), _lib.C128, 3, _lib.i32([0, 1, 3]), _lib.i64([12, 9, 4]), _lib.i64([1, 12, 108]),
+        C.c_void_p(dB.ptr), _lib.C128, 2, _lib.i32([1, 2]), _lib.i64([9, 7]), None))
+    ref = np.einsum("iks,kj->ijs", a_full[:, :, 3:7], b)
+    assert rel_frobenius(dC.to_host(), ref) <= 1e-12
+    # strided C: write every other column of a wider buffer
+    dC2 = B200Array((12, 14), "complex128")
+    _lib.check(mb.lib().mb200_memset(h.ptr, C.c_void_p(dC2.ptr), 0, dC2.nbytes))
+    a2 = random_array(rng, (12, 9), "complex128")
+    dA2 = B200Array.from_host(a2)
+    _lib.check(mb.lib().mb200_binary_einsum(
+        h.ptr, C.c_void_p(dC2.ptr), _lib.C128, 2, _lib.i32([0, 2]), _lib.i64([1, 24]),
+        C.c_void_p(dA2.ptr), _lib.C128, 2, _lib.i32([0, 1]), _lib.i64([12, 9]), None,
+        C.c_void_p(dB.ptr), _lib.C128, 2, _lib.i32([1, 2]), _lib.i64([9, 7]), None))
+    got = dC2.to_host()
+    assert rel_frobenius(got[:, 0::2], a2 @ b) <= 1e-12 and not got[:, 1::2].any()
+
+
+def test_empty_and_degenerate():
+    a = np.ones((3, 0), np.float64, order="F")
+    b = np.ones((0, 4), np.float64, order="F")
+    got = contract(a, "ij", b, "jk", "ik")          # empty contraction → zeros
+    assert got.shape == (3, 4) and not got.any()
+    got = contract(np.ones((0, 3)), "ij", np.ones((3, 4)), "jk", "ik")
+    assert got.shape == (0, 4)
+    x = np.array(3.0 + 1j)
+    y = np.array(2.0 - 1j)
+    got = contract(x, "", y, "", "")                # scalar × scalar
+    assert got.shape == () and got == x * y
+
+
+def test_error_behaviour_on_device():
+    A = Tensor(np.ones((2, 3)), I("ij")).to_device()
+    B = Tensor(np.ones((3, 4)), I("jk")).to_device()
+    with pytest.raises(mb.ArgumentError):           # free label missing from C
+        binary_einsum(BackendB200(), I("i"), A, B)
+    with pytest.raises(mb.ArgumentError):           # label of C in neither operand
+        binary_einsum(BackendB200(), I("iz"), A, B)
+    with pytest.raises(mb.DimensionMismatch):
+        binary_einsum(A, Tensor(np.ones((5, 4)), I("jk")).to_device())
+
+
+# ---- K1 permute kernel: bit-exact ----------------------------------------------------------------------
+PERMUTE_CASES = [
+    ((64, 48), (1, 0)), ((33, 17, 9), (2, 0, 1)), ((33, 17, 9), (1, 2, 0)), ((33, 17, 9), (0, 2, 1)),
+    ((2, 40, 3, 24), (3, 1, 0, 2)), ((2, 40, 3, 24), (1, 0, 3, 2)), ((16, 16, 16, 16), (1, 3, 0, 2)),
+    ((16, 16, 16, 16), (3, 2, 1, 0)), ((5, 1, 7, 1, 3), (4, 3, 2, 1, 0)), ((300, 2), (1, 0)), ((2, 300), (1, 0)),
+    ((2, 2, 2, 2, 2, 2, 2, 2, 2, 2), (9, 0, 8, 1, 7, 2, 6, 3, 5, 4)), ((12, 10, 8), (0, 1, 2)), ((1000,), (0,)),
+    ((7, 130, 5), (0, 2, 1)), ((200, 3, 50), (0, 2, 1)),
+]
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("shape,perm", PERMUTE_CASES)
+def test_permute_bit_exact(shape, perm, dt):
+    """`permutedims(t, perm)` (src/Tensor.jl:302-308 → Base.permutedims) is pure data movement: ==."""
+    rng = np.random.default_rng(1)
+    x = random_array(rng, shape, dt)
+    t = Tensor(x, [Index(i) for i in range(len(shape))]).to_device()
+    got = t.permutedims(list(perm))
+    assert got.inds == [Index(p) for p in perm]
+    assert np.array_equal(got.to_host().data, np.transpose(x, perm))
+
+
+def test_permute_planar_split():
+    """complex interleaved → planar (all re, then all im) in the same pass."""
+    rng = np.random.default_rng(1)
+    for dt, real in (("complex128", np.float64), ("complex64", np.float32)):
+        x = random_array(rng, (24, 10, 18), dt)
+        src = B200Array.from_host(x)
+        dst = B200Array((2, 18, 24, 10), real)   # planes slowest in memory → shape (18,24,10,2) col-major
+        dst = B200Array((18, 24, 10, 2), real)
+        h = _lib.Handle.get()
+        _lib.check(mb.lib().mb200_permute(h.ptr, C.c_void_p(dst.ptr), C.c_void_p(src.ptr), _lib.dtype_enum(dt), 3,
+                                          _lib.i64(x.shape), _lib.i32([2, 0, 1]), 1))
+        got = dst.to_host()
+        ref = np.transpose(x, (2, 0, 1))
+        assert np.array_equal(got[..., 0], ref.real) and np.array_equal(got[..., 1], ref.imag)
+
+
+# ---- BASELINE.json configs at full size ----------------------------------------------------------------
+def _chain_cfg2(E, A, W, Ab):
+    T = binary_einsum(E, A, out=I("awsc"))
+    T2 = binary_einsum(T, W, out=I("atvc"))
+    return binary_einsum(T2, Ab, out=I("evc"))
+
+
+def test_cfg2_mps_mpo_full_size_vs_oracle():
+    """configs[1]: MPS–MPO transfer contraction ComplexF64, χ=1024, d=2, MPO bond 8 — the bench workload.
+    Full-size result against the oracle (CPU BLAS), all three steps."""
+    chi, d, w = 1024, 2, 8
+    rng = np.random.default_rng(2000)
+    E = random_array(rng, (chi, w, chi), "complex128")
+    A = random_array(np.random.default_rng(2001), (chi, d, chi), "complex128")
+    W = random_array(np.random.default_rng(2002), (w, d, d, w), "complex128")
+    Ab = random_array(np.random.default_rng(2003), (chi, d, chi), "complex128")
+    tE, tA, tW, tAb = (Tensor(E, I("awb")).to_device(), Tensor(A, I("bsc")).to_device(),
+                       Tensor(W, I("wstv")).to_device(), Tensor(Ab, I("ate")).to_device())
+    got = _chain_cfg2(tE, tA, tW, tAb).to_host().data
+    T = np.tensordot(E, A, axes=([2], [0]))                         # a w s c
+    T2 = np.einsum("awsc,wstv->atvc", T, W, optimize=True)
+    ref = np.tensordot(Ab, T2, axes=([0, 1], [0, 1]))               # e v c
+    assert got.shape == (chi, w, chi)
+    assert rel_frobenius(got, ref) <= 1e-12
+
+
+def test_cfg1_full_size_properties():
+    """configs[0] at dim 64 (4096^3 GEMM-equivalent), scrambled layout A[k,i,l,j]·B[n,l,m,k] → C[m,j,n,i].
+    Size-independent checks: linearity in A, and a slab of C against the oracle."""
+    n = 64
+    rng = np.random.default_rng(1000)
+    A1 = random_array(rng, (n, n, n, n), "complex128")
+    A2 = random_array(rng, (n, n, n, n), "complex128")
+    B = random_array(np.random.default_rng(1001), (n, n, n, n), "complex128")
+    tB = Tensor(B, I("nlmk")).to_device()
+    c1 = binary_einsum(Tensor(A1, I("kilj")).to_device(), tB, out=I("mjni")).to_host().data
+    c2 = binary_einsum(Tensor(A2, I("kilj")).to_device(), tB, out=I("mjni")).to_host().data
+    c12 = binary_einsum(Tensor(A1 + 2.0 * A2, I("kilj")).to_device(), tB, out=I("mjni")).to_host().data
+    assert rel_frobenius(c12, c1 + 2.0 * c2) <= 1e-12
+    # slab i = 5: C[m,j,n,5] = sum_{k,l} A[k,5,l,j] B[n,l,m,k]
+    ref = np.einsum("klj,nlmk->mjn", A1[:, 5, :, :], B, optimize=True)
+    assert rel_frobenius(c1[:, :, :, 5], ref) <= 1e-12
+
+
+def test_cfg3_peps_batched_c64():
+    """configs[2]: PEPS double-layer ComplexF32, D=8, χ=256, batch hyperindex β=8 (reduced β/χ for the full
+    oracle compare here; the full-size run is a slab check)."""
+    rng = np.random.default_rng(3000)
+    chi, D, beta = 256, 8, 8
+    A = random_array(rng, (chi, D, D, chi, beta), "complex64")          # l k b m z
+    B = random_array(np.random.default_rng(3001), (chi, D, D, chi, beta), "complex64")  # m k q r z
+    got = binary_einsum(Tensor(A, I("lkbmz")).to_device(), Tensor(B, I("mkqrz")).to_device(),
+                        out=I("lbqrz")).to_host().data
+    assert got.shape == (chi, D, D, chi, beta)
+    z = 3
+    ref = np.einsum("lkbm,mkqr->lbqr", A[..., z].astype(np.complex128), B[..., z].astype(np.complex128), optimize=True)
+    assert rel_frobenius(got[..., z], ref.astype(np.complex64)) <= 1e-5
+
+
+def test_stats_count_launches():
+    h = _lib.Handle.get()
+    h.reset_stats()
+    a, ia, b, ib, ic = build_case(PARITY_CASES[3], "complex128", seed=1)
+    contract(a, ia, b, ib, ic, path=mb.PATH_GETT_F64)
+    s = h.stats()
+    assert s["launches_gett_f64"] == 1 and s["launches_total"] >= 1

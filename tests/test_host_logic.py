@@ -1,0 +1,208 @@
+"""CPU: the C-ABI library loads and exports every symbol of include/muscle_b200.h, the planner's
+index bookkeeping, the front-end kwargs semantics and the Backend/Domain dispatch mirror.
+No compute call is made here (there is no GPU and no CPU compute path in the product)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import muscle_b200 as mb
+from muscle_b200 import (ArgumentError, B200Error, BackendB200, BackendBase, DimensionMismatch, Index, Tensor,
+                         binary_einsum, binary_einsum_, with_backend)
+from muscle_b200 import _lib
+from cases import PARITY_CASES, REFERENCE_BATTERY
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    header = open(os.path.join(ROOT, "include", "muscle_b200.h")).read()
+    declared = set(re.findall(r"\b(mb200_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    L = mb.lib()
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/muscle_b200.h but not exported"
+    assert declared == set(_lib.PROTOTYPES), "ctypes prototypes out of sync with the header"
+    assert L.mb200_version() >= 100
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    A = Tensor(np.ones((2, 3)), "ij")
+    B = Tensor(np.ones((3, 4)), "jk")
+    with pytest.raises(B200Error):
+        binary_einsum(BackendB200(), [Index("i"), Index("k")], A, B)
+
+
+def test_frontend_matches_reference_battery():
+    """kwargs → inds_c (binary_einsum.jl:33-41), replaying the reference's test inputs."""
+    for name, sa, ia, sb, ib, kw, exp_inds, exp_shape, _, _ in REFERENCE_BATTERY:
+        kwargs = {k: [Index(c) for c in v] for k, v in kw.items()}
+        got = mb.frontend_inds_c([Index(c) for c in ia], [Index(c) for c in ib], **kwargs)
+        assert got == [Index(c) for c in exp_inds], name
+
+
+def test_frontend_matches_oracle_frontend():
+    from oracle import frontend_inds_c as oracle_frontend
+    rng = np.random.default_rng(0)
+    labels = list("abcdefgh")
+    for _ in range(200):
+        ia = list(rng.permutation(labels)[: rng.integers(0, 6)])
+        ib = list(rng.permutation(labels)[: rng.integers(0, 6)])
+        shared = [x for x in ia if x in ib]
+        dims = None if rng.random() < 0.3 else list(rng.permutation(labels)[: rng.integers(0, 4)])
+        exp = oracle_frontend(ia, ib, dims=dims)
+        got = mb.frontend_inds_c([Index(c) for c in ia], [Index(c) for c in ib],
+                                 dims=None if dims is None else [Index(c) for c in dims])
+        assert [g.tag for g in got] == exp, (ia, ib, dims, shared)
+
+
+def test_flatten_labels_like_cutensor_ext():
+    """indmap = enumerate(unique(inds_a ∪ inds_b)) — ext/MuscleCUDAExt.jl:24-27."""
+    ia = [Index(c) for c in "ijk"]
+    ib = [Index(c) for c in "klj"]
+    ma, mb_, mc = mb.flatten_labels(ia, ib, [Index("i"), Index("l")])
+    assert (ma, mb_, mc) == ([0, 1, 2], [2, 3, 1], [0, 3])
+    with pytest.raises(ArgumentError):
+        mb.flatten_labels(ia, ib, [Index("z")])
+    # tags may be any hashable (symbols, ints, named tuples — test/unit/operations/simple_update.jl:8)
+    assert Index(("site", 1)) == Index(("site", 1)) and Index(1) != Index("1")
+
+
+def test_backend_dispatch():
+    A = Tensor(np.ones((2, 3)), "ij")
+    B = Tensor(np.ones((3, 4)), "jk")
+    assert mb.choose_backend("binary_einsum", A.parent, B.parent) == BackendBase()   # binary_einsum.jl:20
+    assert with_backend(lambda: mb.choose_backend("binary_einsum", A.parent, B.parent), BackendB200()) == BackendB200()
+    # scoped: the override ends with the call (ScopedValue, src/Backend.jl:16-18)
+    assert mb.choose_backend("binary_einsum", A.parent, B.parent) == BackendBase()
+    # a backend without a method → ArgumentError (binary_einsum.jl:53-55,72-74)
+    with pytest.raises(ArgumentError):
+        binary_einsum(A, B)
+    with pytest.raises(ArgumentError):
+        binary_einsum_(Tensor(np.zeros((2, 4)), "ik"), A, B)
+    assert mb.domain(A) == mb.DomainHost()
+
+
+def test_tensor_ctor_checks():
+    with pytest.raises(ArgumentError):
+        Tensor(np.ones((2, 3)), "i")
+    with pytest.raises(DimensionMismatch):
+        Tensor(np.ones((2, 3)), "ii")
+    t = Tensor(np.ones((2, 3, 4)), "ijk")
+    assert t.inds == [Index("i"), Index("j"), Index("k")] and t.size(Index("k")) == 4 and t.dim("j") == 1
+    p = t.permutedims([Index("k"), Index("i"), Index("j")])
+    assert p.shape == (4, 2, 3) and p.inds == [Index("k"), Index("i"), Index("j")]
+    assert t.isequal(p) and t.isapprox(p)
+
+
+def _describe(ext, ia, ib, ic, dt=_lib.C128):
+    labels = {c: k for k, c in enumerate(dict.fromkeys(ia + ib))}
+    return mb.plan_describe(dt, [labels[c] for c in ic], dt, [labels[c] for c in ia], [ext[c] for c in ia],
+                            dt, [labels[c] for c in ib], [ext[c] for c in ib]), labels
+
+
+@pytest.mark.parametrize("case", PARITY_CASES, ids=[c[0] for c in PARITY_CASES])
+def test_planner_classification(case):
+    name, ext, ia, ib, ic = case
+    info, labels = _describe(ext, ia, ib, ic)
+    inv = {v: k for k, v in labels.items()}
+    left = [inv[info.left[i]] for i in range(info.n_left)]
+    right = [inv[info.right[i]] for i in range(info.n_right)]
+    summed = [inv[info.sum[i]] for i in range(info.n_sum)]
+    batch = [inv[info.batch[i]] for i in range(info.n_batch)]
+    row, col = (ib, ia) if info.swapped else (ia, ib)
+    live = lambda s: {c for c in s if ext[c] > 1}
+    assert set(batch) == live(set(ia) & set(ib) & set(ic))
+    assert set(summed) == live((set(ia) & set(ib)) - set(ic))
+    assert set(left) == live(set(row) - set(col))
+    assert set(right) == live(set(col) - set(row))
+    prod = lambda s: int(np.prod([ext[c] for c in s], dtype=np.int64)) if s else 1
+    assert (info.M, info.N, info.K, info.L) == (prod(left), prod(right), prod(summed), prod(batch))
+    assert info.flops == 8.0 * info.M * info.N * info.K * info.L
+    # C's unit-stride live mode is always a row (or batch) mode: that is what `swapped` guarantees
+    live_c = [c for c in ic if ext[c] > 1]
+    if live_c:
+        assert live_c[0] in left + batch
+    # walk order of the row/column/batch groups follows C's memory order
+    for grp in (left, right, batch):
+        pos = [ic.index(c) for c in grp]
+        assert pos == sorted(pos)
+
+
+def test_planner_sizes_of_baseline_configs():
+    """GEMM-equivalent sizes and paths of the north-star configs."""
+    cfg1, _ = _describe(dict(i=64, j=64, k=64, l=64, m=64, n=64), "kilj", "nlmk", "mjni")
+    assert (cfg1.M, cfg1.N, cfg1.K, cfg1.L) == (4096, 4096, 4096, 1) and cfg1.path == mb.PATH_GETT_F64
+    c2a, _ = _describe(dict(a=1024, w=8, b=1024, s=2, c=1024), "awb", "bsc", "awsc")
+    assert (c2a.M, c2a.N, c2a.K) == (8192, 2048, 1024) and c2a.flops == 8.0 * 8192 * 2048 * 1024
+    c2b, _ = _describe(dict(a=1024, w=8, s=2, c=1024, t=2, v=8), "awsc", "wstv", "atvc")
+    assert (c2b.M, c2b.N, c2b.K) == (1024 * 1024, 16, 16)
+    c2c, _ = _describe(dict(a=1024, t=2, v=8, c=1024, e=1024), "atvc", "ate", "evc")
+    assert sorted((c2c.M, c2c.N)) == [1024, 8192] and c2c.K == 2048
+    c3, _ = _describe(dict(l=256, k=8, b=8, m=256, q=8, r=256, z=8), "lkbmz", "mkqrz", "lbqrz", dt=_lib.C64)
+    assert (c3.M, c3.N, c3.K, c3.L) == (2048, 2048, 2048, 8) and c3.path in (mb.PATH_SIMT_F32, mb.PATH_TCGEN05_TF32)
+    tiny, _ = _describe(dict(i=2, j=3, k=4), "ij", "jk", "ik")
+    assert tiny.path == mb.PATH_DIRECT   # everything in the reference's own test-suite is launch-bound
+
+
+def test_planner_rejections():
+    d = _lib.F64
+    with pytest.raises(ArgumentError):      # repeated label inside one operand (ext/MuscleReactantExt.jl:88-89)
+        mb.plan_describe(d, [0], d, [0, 0], [2, 2], d, [1], [3])
+    with pytest.raises(ArgumentError):      # label of C in neither operand (ext/MuscleStridedExt.jl:53)
+        mb.plan_describe(d, [0, 5], d, [0, 1], [2, 3], d, [1], [3])
+    with pytest.raises(ArgumentError):      # free label missing from C (binary_einsum.jl:83)
+        mb.plan_describe(d, [0], d, [0, 1], [2, 3], d, [1, 2], [3, 4])
+    with pytest.raises(DimensionMismatch):  # shared label with different extents
+        mb.plan_describe(d, [0], d, [0, 1], [2, 3], d, [1], [4])
+    with pytest.raises(ArgumentError):      # eltype of C must be the promotion
+        mb.plan_describe(_lib.F32, [0], d, [0, 1], [2, 3], d, [1], [3])
+    with pytest.raises(ArgumentError):      # repeated label in C
+        mb.plan_describe(d, [0, 0], d, [0, 1], [2, 3], d, [1], [3])
+    ok = mb.plan_describe(_lib.C128, [0], _lib.F64, [0, 1], [2, 3], _lib.C128, [1], [3])
+    assert ok.compute_dtype == _lib.C128     # mixed eltypes promote (src/Muscle.jl:47 precompile workload)
+
+
+def test_errors_surface_before_any_device_work():
+    """Argument errors must not depend on a GPU: they are raised by the host-only planner."""
+    A = Tensor(np.ones((2, 3)), "ij")
+    B = Tensor(np.ones((4, 5)), "jk")
+    with pytest.raises(DimensionMismatch):
+        binary_einsum(BackendB200(), [Index("i"), Index("k")], A, B)
+    with pytest.raises(ArgumentError):
+        binary_einsum(BackendB200(), [Index("i")], A, Tensor(np.ones((3, 5)), "jk"))
+    with pytest.raises(ArgumentError):
+        binary_einsum(BackendB200(), [Index("i"), Index("k")], Tensor(np.ones((2, 3), np.int64), "ij"),
+                      Tensor(np.ones((3, 5)), "jk"))
+
+
+def test_shard_plan():
+    # cfg 4: free-index shard, no collective
+    labels = {c: k for k, c in enumerate("abcdefghi")}
+    ia, ib, ic = "adbecf", "fgdhei", "abcghi"
+    ext = {c: 16 for c in labels}
+    m = lambda s: [labels[c] for c in s]
+    e = lambda s: [ext[c] for c in s]
+    covered = []
+    for r in range(8):
+        s = mb.shard_plan(m(ic), m(ia), e(ia), m(ib), e(ib), 8, r)
+        assert s.kind == _lib.SHARD_FREE and s.mode == labels["i"] and not s.needs_allreduce
+        covered.append((s.begin, s.end))
+    assert covered == [(2 * r, 2 * r + 2) for r in range(8)]
+    # cfg 5: summed-index slice + allreduce
+    s = mb.shard_plan(m(ic), m(ia), e(ia), m(ib), e(ib), 8, 3, prefer_sum=True)
+    assert s.kind == _lib.SHARD_SUM and s.needs_allreduce and s.mode == labels["f"] and (s.begin, s.end) == (6, 8)
+    # batch mode
+    s = mb.shard_plan([0, 2, 3], [0, 1, 3], [4, 5, 8], [1, 2, 3], [5, 6, 8], 4, 1)
+    assert s.kind == _lib.SHARD_BATCH and s.mode == 3 and (s.begin, s.end) == (2, 4)
+    # uneven split covers the whole range without overlap
+    spans = [mb.shard_plan([0, 2], [0, 1], [7, 3], [1, 2], [3, 10], 4, r) for r in range(4)]
+    assert spans[0].begin == 0 and spans[-1].end == 10
+    assert all(spans[i].end == spans[i + 1].begin for i in range(3))
+    # nothing shardable → replicas only
+    s = mb.shard_plan([0], [0, 1], [2, 3], [1], [3], 8, 0)
+    assert s.kind == _lib.SHARD_NONE
