@@ -11,6 +11,7 @@ from .backend import (Backend, BackendB200, BackendBase, Domain, DomainB200, Dom
                       choose_backend_rule, domain, with_backend)
 from .einsum import binary_einsum, binary_einsum_, binary_einsum_inplace, flatten_labels, frontend_inds_c
 from .tensor import B200Array, Index, Tensor, findperm
+from . import dist
 
 __all__ = [
     "ArgumentError", "B200Error", "DimensionMismatch", "Handle", "LIB_PATH", "lib", "plan_describe", "shard_plan",

@@ -24,15 +24,27 @@ namespace mb200 {
 namespace {
 
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async(void *smem, const void *gmem, int bytes_total, bool valid) {
+// zero-fill form: copies BYTES when valid, writes BYTES of zeros otherwise (no branch)
+template <int BYTES>
+__device__ __forceinline__ void cp_async_zfill(void *smem, const void *gmem, bool valid) {
     unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    int src = valid ? bytes_total : 0;
-    if (bytes_total == 16)
+    int src = valid ? BYTES : 0;
+    if constexpr (BYTES == 16)
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem), "r"(src));
-    else if (bytes_total == 8)
+    else if constexpr (BYTES == 8)
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(gmem), "r"(src));
     else
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sa), "l"(gmem), "r"(src));
+}
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void *smem, const void *gmem) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    if constexpr (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem));
+    else if constexpr (BYTES == 8)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem));
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() {
@@ -40,7 +52,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
 }
 
 __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }
@@ -64,7 +76,10 @@ struct CoreZ {
 #pragma unroll
             for (int j = 0; j < NT; j++) a.re[i][j][0] = a.re[i][j][1] = a.im[i][j][0] = a.im[i][j][1] = 0.0;
     }
-    __device__ static void compute(Acc &acc, const Elem *sa, const Elem *sb, int warp, int lane) {
+    static constexpr int SLOTS = (BK / 4) * 4;  // hook calls per k-block
+    static constexpr bool ZFILL = false;
+    template <class Hook>
+    __device__ static void compute(Acc &acc, const Elem *sa, const Elem *sb, int warp, int lane, Hook &&hook) {
         const int wm = (warp % (BM / WM)) * WM, wn = (warp / (BM / WM)) * WN;
         const int fr = lane >> 2, fk = lane & 3;
 #pragma unroll
@@ -83,18 +98,22 @@ struct CoreZ {
             for (int i = 0; i < MT; i++)
 #pragma unroll
                 for (int j = 0; j < NT; j++) dmma(acc.re[i][j][0], acc.re[i][j][1], af[i].x, bf[j].x);
+            hook(kk * 4 + 0);
 #pragma unroll
             for (int i = 0; i < MT; i++)
 #pragma unroll
                 for (int j = 0; j < NT; j++) dmma(acc.im[i][j][0], acc.im[i][j][1], af[i].x, bf[j].y);
+            hook(kk * 4 + 1);
 #pragma unroll
             for (int i = 0; i < MT; i++)
 #pragma unroll
                 for (int j = 0; j < NT; j++) dmma(acc.re[i][j][0], acc.re[i][j][1], nai[i], bf[j].y);
+            hook(kk * 4 + 2);
 #pragma unroll
             for (int i = 0; i < MT; i++)
 #pragma unroll
                 for (int j = 0; j < NT; j++) dmma(acc.im[i][j][0], acc.im[i][j][1], af[i].y, bf[j].x);
+            hook(kk * 4 + 3);
         }
     }
     __device__ static void store(const Acc &acc, Elem *C, const int64_t *sRowC, const int64_t *sColC,
@@ -132,7 +151,10 @@ struct CoreD {
 #pragma unroll
             for (int j = 0; j < NT; j++) a.c[i][j][0] = a.c[i][j][1] = 0.0;
     }
-    __device__ static void compute(Acc &acc, const Elem *sa, const Elem *sb, int warp, int lane) {
+    static constexpr int SLOTS = (BK / 4) * MT;
+    static constexpr bool ZFILL = true;
+    template <class Hook>
+    __device__ static void compute(Acc &acc, const Elem *sa, const Elem *sb, int warp, int lane, Hook &&hook) {
         const int wm = (warp % (BM / WM)) * WM, wn = (warp / (BM / WM)) * WN;
         const int fr = lane >> 2, fk = lane & 3;
 #pragma unroll
@@ -143,9 +165,11 @@ struct CoreD {
 #pragma unroll
             for (int j = 0; j < NT; j++) bf[j] = sb[(kk * 4 + fk) * LDB + wn + j * 8 + fr];
 #pragma unroll
-            for (int i = 0; i < MT; i++)
+            for (int i = 0; i < MT; i++) {
 #pragma unroll
                 for (int j = 0; j < NT; j++) dmma(acc.c[i][j][0], acc.c[i][j][1], af[i], bf[j]);
+                hook(kk * MT + i);
+            }
         }
     }
     __device__ static void store(const Acc &acc, Elem *C, const int64_t *sRowC, const int64_t *sColC,
@@ -193,7 +217,10 @@ struct CoreF {
 #pragma unroll
             for (int j = 0; j < TN; j++) zero(a.c[i][j]);
     }
-    __device__ static void compute(Acc &acc, const Elem *sa, const Elem *sb, int warp, int lane) {
+    static constexpr int SLOTS = BK;
+    static constexpr bool ZFILL = true;
+    template <class Hook>
+    __device__ static void compute(Acc &acc, const Elem *sa, const Elem *sb, int warp, int lane, Hook &&hook) {
         const int tid = warp * 32 + lane, tx = tid & 15, ty = tid >> 4;
 #pragma unroll
         for (int k = 0; k < BK; k++) {
@@ -206,6 +233,7 @@ struct CoreF {
             for (int i = 0; i < TM; i++)
 #pragma unroll
                 for (int j = 0; j < TN; j++) mac(acc.c[i][j], af[i], bf[j]);
+            hook(k);
         }
     }
     __device__ static void store(const Acc &acc, Elem *C, const int64_t *sRowC, const int64_t *sColC,
@@ -282,25 +310,47 @@ __global__ void __launch_bounds__(Core::NTHREADS, 1) gett_kernel(const __grid_co
     const E *gB = reinterpret_cast<const E *>(p.B) + bb;
     const int64_t KB = (p.K + BK - 1) / BK;
 
-    auto load_tile = [&](int stage, int64_t kb) {
-        E *da = sA + (size_t)stage * BK * LDA;
-        E *db = sB + (size_t)stage * BK * LDB;
-        const int64_t kbase = kb * BK;
-#pragma unroll
-        for (int i = tid; i < BM * BK; i += NT) {
+    // One "unit" = one element-granular cp.async. Units [0, UA) belong to A, [UA, UA+UB) to B. A unit's
+    // (row, k) assignment is fixed per thread; rows past the tile edge are simply not loaded (their
+    // accumulators are never stored), the K tail is zero-filled with plain stores.
+    constexpr int UA = (BM * BK + NT - 1) / NT, UB = (BN * BK + NT - 1) / NT, UNITS = UA + UB;
+    auto issue_unit = [&](int stage, int64_t kbase, int u, bool more) {
+        if (u < UA) {
+            const int i = tid + u * NT;
             int m, k;
             if (p.a_kmajor) { k = i % BK; m = i / BK; } else { m = i % BM; k = i / BM; }
-            bool v = (m < mrem) && (kbase + k < p.K);
-            int64_t off = v ? (sRowA[m] + p.kA[kbase + k]) : 0;
-            cp_async(da + k * LDA + m, gA + off, (int)sizeof(E), v);
-        }
-#pragma unroll
-        for (int i = tid; i < BN * BK; i += NT) {
+            if ((BM * BK) % NT != 0 && i >= BM * BK) return;
+            E *dst = sA + (size_t)stage * BK * LDA + k * LDA + m;
+            if constexpr (Core::ZFILL) {   // branch-free: keeps the FFMA / real-DMMA loops in one basic block
+                const bool v = more && (m < mrem) && (kbase + k < p.K);
+                const int64_t off = v ? (sRowA[m] + p.kA[kbase + k]) : 0;
+                cp_async_zfill<(int)sizeof(E)>(dst, gA + off, v);
+            } else {
+                if (!more) return;
+                if (kbase + k < p.K) {
+                    if (m < mrem) cp_async<(int)sizeof(E)>(dst, gA + (sRowA[m] + p.kA[kbase + k]));
+                } else {
+                    *dst = E{};
+                }
+            }
+        } else {
+            const int i = tid + (u - UA) * NT;
             int n, k;
             if (p.b_kmajor) { k = i % BK; n = i / BK; } else { n = i % BN; k = i / BN; }
-            bool v = (n < nrem) && (kbase + k < p.K);
-            int64_t off = v ? (sColB[n] + p.kB[kbase + k]) : 0;
-            cp_async(db + k * LDB + n, gB + off, (int)sizeof(E), v);
+            if ((BN * BK) % NT != 0 && i >= BN * BK) return;
+            E *dst = sB + (size_t)stage * BK * LDB + k * LDB + n;
+            if constexpr (Core::ZFILL) {
+                const bool v = more && (n < nrem) && (kbase + k < p.K);
+                const int64_t off = v ? (sColB[n] + p.kB[kbase + k]) : 0;
+                cp_async_zfill<(int)sizeof(E)>(dst, gB + off, v);
+            } else {
+                if (!more) return;
+                if (kbase + k < p.K) {
+                    if (n < nrem) cp_async<(int)sizeof(E)>(dst, gB + (sColB[n] + p.kB[kbase + k]));
+                } else {
+                    *dst = E{};
+                }
+            }
         }
     };
 
@@ -309,17 +359,30 @@ __global__ void __launch_bounds__(Core::NTHREADS, 1) gett_kernel(const __grid_co
 
 #pragma unroll
     for (int s = 0; s < S - 1; s++) {
-        if (s < KB) load_tile(s, s);
+        if (s < KB) {
+#pragma unroll
+            for (int u = 0; u < UNITS; u++) issue_unit(s, (int64_t)s * BK, u, true);
+        }
         cp_async_commit();
     }
     for (int64_t kb = 0; kb < KB; kb++) {
         cp_async_wait<S - 2>();
         __syncthreads();
-        int64_t nk = kb + S - 1;
-        if (nk < KB) load_tile((int)(nk % S), nk);
-        cp_async_commit();
+        const int64_t nk = kb + S - 1;
+        const bool more = nk < KB;
+        const int nstage = (int)(nk % S);
         const int st = (int)(kb % S);
-        Core::compute(acc, sA + (size_t)st * BK * LDA, sB + (size_t)st * BK * LDB, warp, lane);
+        // the next stage's gather is spread over the MMA stream: slot s issues units [s*UNITS/SLOTS, ...)
+        Core::compute(acc, sA + (size_t)st * BK * LDA, sB + (size_t)st * BK * LDB, warp, lane, [&](int slot) {
+            constexpr int SLOTS = Core::SLOTS;
+            constexpr int PER = (UNITS + SLOTS - 1) / SLOTS;
+#pragma unroll
+            for (int q = 0; q < PER; q++) {
+                const int u = slot * PER + q;
+                if (u < UNITS) issue_unit(nstage, nk * BK, u, more);
+            }
+            if (slot == SLOTS - 1) cp_async_commit();
+        });
     }
     cp_async_wait<0>();
     Core::store(acc, reinterpret_cast<E *>(p.C), sRowC, sColC, cb, mrem, nrem, warp, lane);

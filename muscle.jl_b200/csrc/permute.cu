@@ -5,16 +5,18 @@
 // Canonical problem (built by the caller): modes in SOURCE order (mode 0 = source unit stride,
 // extent-1 modes dropped, modes adjacent in both layouts merged) + each mode's DESTINATION stride.
 // Let j be the mode with destination stride 1.
-//   * A tile is a product of three index ranges
+//   * A tile is a product of three index ranges, all with power-of-two tile extents
 //       v : a chunk of mode 0 when it is the unit-stride mode of BOTH layouts (j == 0), else absent
 //       x : a chunk of the "row space"    = leading source modes (contiguous in the source)
 //       y : a chunk of the "column space" = leading destination modes (contiguous in the destination)
 //     Every other mode is an outer mode decoded from blockIdx.
 //   * Reads walk (v,x) fastest → source-contiguous runs; writes walk (v,y) fastest → destination-
-//     contiguous runs. Offsets are separable, so each tile builds four small shared tables once
-//     (source/dest offset and smem slot per (v,x) and per (v,y)); the element loops are then
-//     shift/mask + two table reads + one LDG/STS or LDS/STG — no divisions.
-//   * smem pitch is odd, so the transposed tile read is bank-conflict free for 4/8/16 B elements.
+//     contiguous runs. Offsets are separable (off = v + tabX[x] + tabY[y]), so each tile builds four
+//     small shared tables once; the element loops are shift/mask + two table reads + one
+//     LDG/STS or LDS/STG — no divisions.
+//   * smem pitch per y is padded so the transposed read is bank-conflict free for 4/8/16 B elements.
+//   * When the tile needs no transposition (no x or no y range) elements go straight from global to
+//     global in one loop, no shared memory.
 #include <algorithm>
 #include <vector>
 
@@ -25,104 +27,114 @@ namespace mb200 {
 namespace {
 
 constexpr int PT_THREADS = 256;
-constexpr int PT_MAX_TAB = 512;   // entries per table
+constexpr int PT_MAX_TAB = 256;   // entries per table (TX, TY <= 256)
 
 struct PermK {
-    // outer modes
     int n_out;
-    int64_t o_ext[MB200_MAX_MODES], o_ss[MB200_MAX_MODES], o_ds[MB200_MAX_MODES];
-    // v (mode 0 chunk; v_ext == 1 means absent)
-    int64_t v_ext; int VT;
-    // x / y spaces
+    unsigned o_ext[MB200_MAX_MODES];
+    int64_t o_ss[MB200_MAX_MODES], o_ds[MB200_MAX_MODES];
+    int64_t v_ext;
     int nx, ny;
-    int64_t x_ext[MB200_MAX_MODES], x_ss[MB200_MAX_MODES], x_ds[MB200_MAX_MODES];
-    int64_t y_ext[MB200_MAX_MODES], y_ss[MB200_MAX_MODES], y_ds[MB200_MAX_MODES];
-    int64_t SX, SY; int TX, TY;
-    int64_t v_chunks, x_chunks, y_chunks;
-    int pitch;              // smem elements per y (>= VT*TX, odd)
-    int64_t plane_stride;   // planar: im plane offset in scalars
+    unsigned x_ext[MB200_MAX_MODES], y_ext[MB200_MAX_MODES];
+    int64_t x_ss[MB200_MAX_MODES], x_ds[MB200_MAX_MODES];
+    int64_t y_ss[MB200_MAX_MODES], y_ds[MB200_MAX_MODES];
+    int64_t SX, SY;
+    int lv, lx, ly;          // log2 of the tile extents VT, TX, TY
+    unsigned v_chunks, x_chunks, y_chunks;
+    int pitch;               // smem elements per y
+    int direct;              // 1: no transposition needed, global → global
+    int64_t plane_stride;    // planar: im plane offset in scalars
 };
 
-__device__ __forceinline__ void digits_off(int64_t idx, int n, const int64_t *ext, const int64_t *ss,
+// digits of idx over `ext` (32-bit divisions), accumulated into 64-bit offsets
+__device__ __forceinline__ void digits_off(unsigned idx, int n, const unsigned *ext, const int64_t *ss,
                                            const int64_t *ds, int64_t &so, int64_t &dof) {
     so = 0; dof = 0;
     for (int i = 0; i < n; i++) {
-        int64_t e = ext[i], d = idx % e;
-        idx /= e;
-        so += d * ss[i];
-        dof += d * ds[i];
+        unsigned e = ext[i], q = idx / e, d = idx - q * e;
+        idx = q;
+        so += (int64_t)d * ss[i];
+        dof += (int64_t)d * ds[i];
     }
 }
 
-__device__ __forceinline__ int ceil_log2(int v) { return v <= 1 ? 0 : 32 - __clz(v - 1); }
+template <typename E, typename S, bool PLANAR>
+__device__ __forceinline__ void put(void *dstv, int64_t off, const E &val, int64_t plane_stride) {
+    if constexpr (PLANAR) {
+        S *d = reinterpret_cast<S *>(dstv);
+        d[off] = val.x;
+        d[off + plane_stride] = val.y;
+    } else {
+        reinterpret_cast<E *>(dstv)[off] = val;
+    }
+}
 
 template <typename E, typename S, bool PLANAR>
 __global__ void __launch_bounds__(PT_THREADS) permute_kernel(const __grid_constant__ PermK p,
                                                              const E *__restrict__ src, void *__restrict__ dstv) {
-    // read-side tables indexed by rx = v + vt*x ; write-side tables indexed by cy = v + vt*y
-    __shared__ int64_t sSrcRX[PT_MAX_TAB], sDstCY[PT_MAX_TAB];
-    __shared__ int64_t sSrcY[PT_MAX_TAB], sDstX[PT_MAX_TAB];
-    __shared__ int sPosRX[PT_MAX_TAB], sPosCY[PT_MAX_TAB];
+    __shared__ int64_t sSrcX[PT_MAX_TAB], sDstX[PT_MAX_TAB], sSrcY[PT_MAX_TAB], sDstY[PT_MAX_TAB];
     extern __shared__ __align__(16) unsigned char tile_raw[];
     E *tile = reinterpret_cast<E *>(tile_raw);
 
-    int64_t b = blockIdx.x;
-    const int64_t vc = b % p.v_chunks; b /= p.v_chunks;
-    const int64_t xc = b % p.x_chunks; b /= p.x_chunks;
-    const int64_t yc = b % p.y_chunks; b /= p.y_chunks;
+    unsigned b = blockIdx.x;
+    const unsigned vc = b % p.v_chunks; b /= p.v_chunks;
+    const unsigned xc = b % p.x_chunks; b /= p.x_chunks;
+    const unsigned yc = b % p.y_chunks; b /= p.y_chunks;
     int64_t base_s, base_d;
     digits_off(b, p.n_out, p.o_ext, p.o_ss, p.o_ds, base_s, base_d);
-    const int64_t v0 = vc * p.VT, x0 = xc * p.TX, y0 = yc * p.TY;
-    const int vt = (int)min((int64_t)p.VT, p.v_ext - v0);
-    const int tx = (int)min((int64_t)p.TX, p.SX - x0);
-    const int ty = (int)min((int64_t)p.TY, p.SY - y0);
+    const int VT = 1 << p.lv, TX = 1 << p.lx, TY = 1 << p.ly;
+    const int64_t v0 = (int64_t)vc << p.lv, x0 = (int64_t)xc << p.lx, y0 = (int64_t)yc << p.ly;
+    const int vt = (int)min((int64_t)VT, p.v_ext - v0);
+    const int tx = (int)min((int64_t)TX, p.SX - x0);
+    const int ty = (int)min((int64_t)TY, p.SY - y0);
     base_s += v0; base_d += v0;  // v has stride 1 on both sides
     const int tid = threadIdx.x;
 
     for (int i = tid; i < tx; i += PT_THREADS) {
         int64_t so, dof;
-        digits_off(x0 + i, p.nx, p.x_ext, p.x_ss, p.x_ds, so, dof);
-        sDstX[i] = dof;
-        for (int v = 0; v < vt; v++) { sSrcRX[v + vt * i] = so + v; sPosRX[v + vt * i] = i * p.VT + v; }
+        digits_off((unsigned)(x0 + i), p.nx, p.x_ext, p.x_ss, p.x_ds, so, dof);
+        sSrcX[i] = so; sDstX[i] = dof;
     }
     for (int i = tid; i < ty; i += PT_THREADS) {
         int64_t so, dof;
-        digits_off(y0 + i, p.ny, p.y_ext, p.y_ss, p.y_ds, so, dof);
-        sSrcY[i] = so;
-        for (int v = 0; v < vt; v++) { sDstCY[v + vt * i] = dof + v; sPosCY[v + vt * i] = i * p.pitch + v; }
+        digits_off((unsigned)(y0 + i), p.ny, p.y_ext, p.y_ss, p.y_ds, so, dof);
+        sSrcY[i] = so; sDstY[i] = dof;
     }
     __syncthreads();
 
-    {   // gather: (v,x) fastest
-        const int inner = vt * tx, sh = ceil_log2(inner), mask = (1 << sh) - 1;
-        const int total = ty << sh;
+    const int total = 1 << (p.lv + p.lx + p.ly);
+    const int mv = VT - 1, mx = TX - 1, my = TY - 1;
+    if (p.direct) {   // read order == write order
 #pragma unroll 4
         for (int idx = tid; idx < total; idx += PT_THREADS) {
-            int rx = idx & mask, y = idx >> sh;
-            if (rx < inner) tile[y * p.pitch + sPosRX[rx]] = src[base_s + sSrcRX[rx] + sSrcY[y]];
+            const int v = idx & mv, x = (idx >> p.lv) & mx, y = idx >> (p.lv + p.lx);
+            if (v < vt && x < tx && y < ty) {
+                E val = src[base_s + v + sSrcX[x] + sSrcY[y]];
+                put<E, S, PLANAR>(dstv, base_d + v + sDstX[x] + sDstY[y], val, p.plane_stride);
+            }
         }
+        return;
+    }
+    // gather: (v,x) fastest; smem slot = y*pitch + x*VT + v
+#pragma unroll 4
+    for (int idx = tid; idx < total; idx += PT_THREADS) {
+        const int vx = idx & ((1 << (p.lv + p.lx)) - 1), v = idx & mv, x = vx >> p.lv, y = idx >> (p.lv + p.lx);
+        if (v < vt && x < tx && y < ty) tile[y * p.pitch + vx] = src[base_s + v + sSrcX[x] + sSrcY[y]];
     }
     __syncthreads();
-    {   // scatter: (v,y) fastest
-        const int inner = vt * ty, sh = ceil_log2(inner), mask = (1 << sh) - 1;
-        const int total = tx << sh;
-        S *dst = reinterpret_cast<S *>(dstv);
+    // scatter: (v,y) fastest
 #pragma unroll 4
-        for (int idx = tid; idx < total; idx += PT_THREADS) {
-            int cy = idx & mask, x = idx >> sh;
-            if (cy < inner) {
-                E val = tile[sPosCY[cy] + x * p.VT];
-                int64_t off = base_d + sDstCY[cy] + sDstX[x];
-                if constexpr (PLANAR) {
-                    dst[off] = val.x;
-                    dst[off + p.plane_stride] = val.y;
-                } else {
-                    reinterpret_cast<E *>(dst)[off] = val;
-                }
-            }
+    for (int idx = tid; idx < total; idx += PT_THREADS) {
+        const int v = idx & mv, y = (idx >> p.lv) & my, x = idx >> (p.lv + p.ly);
+        if (v < vt && x < tx && y < ty) {
+            E val = tile[y * p.pitch + (x << p.lv) + v];
+            put<E, S, PLANAR>(dstv, base_d + v + sDstX[x] + sDstY[y], val, p.plane_stride);
         }
     }
 }
+
+inline int floor_log2(int64_t v) { int l = 0; while ((int64_t)2 << l <= v) l++; return l; }
+inline int ceil_log2(int64_t v) { int l = 0; while (((int64_t)1 << l) < v) l++; return l; }
 
 }  // namespace
 
@@ -130,9 +142,11 @@ cudaError_t launch_permute(int dtype, const PermuteParams &q, const void *src, v
     if (q.total <= 0) return cudaSuccess;
     const int n = q.n;
     const size_t esz = dtype_size(dtype);
-    const int tile_elems = esz == 16 ? 1024 : (esz == 8 ? 2048 : 4096);
+    const int G = (int)(128 / esz);                                   // elements per 128 B smem phase
+    const int ltile = esz == 16 ? 11 : (esz == 8 ? 12 : 13);          // 32 KB tiles
+    for (int i = 0; i < n; i++)
+        if (q.ext[i] >= ((int64_t)1 << 31)) return cudaErrorInvalidValue;  // 32-bit digit math
 
-    // destination order of the source modes
     std::vector<int> dord(n);
     for (int i = 0; i < n; i++) dord[i] = i;
     std::stable_sort(dord.begin(), dord.end(), [&](int a, int b) { return q.dst_stride[a] < q.dst_stride[b]; });
@@ -145,64 +159,71 @@ cudaError_t launch_permute(int dtype, const PermuteParams &q, const void *src, v
     PermK k{};
     k.plane_stride = q.plane_stride;
     std::vector<int> role(n, 0);  // 0 outer, 1 v, 2 x, 3 y
-    k.v_ext = 1; k.VT = 1;
-    int xs = 0;       // next source-order candidate for x
-    size_t ys = 0;    // next destination-order candidate for y
+    k.v_ext = 1;
+    int xs = 0;
+    size_t ys = 0;
+    int lv = 0;
     if (n > 0 && dord[0] == 0) {  // shared unit-stride mode
         role[0] = 1;
         k.v_ext = q.ext[0];
-        k.VT = (int)std::min<int64_t>(q.ext[0], 128);
+        // short runs: one chunk covers the whole mode; long runs: power-of-two chunks up to the tile
+        lv = q.ext[0] <= 16 ? ceil_log2(q.ext[0]) : std::min(floor_log2(q.ext[0]), ltile);
         xs = 1; ys = 1;
     }
-    // target tile shape
-    int rem = std::max(1, tile_elems / k.VT);
-    int tx_target, ty_target;
-    if (k.VT >= 64) { tx_target = 1; ty_target = rem; }
-    else {
-        int r = 1;
-        while (r * r * 2 <= rem) r *= 2;       // ~sqrt, power of two
-        tx_target = r; ty_target = rem / r;
-        if (esz == 16 && k.VT == 1) { tx_target = 32; ty_target = 32; }
-    }
+    const int lrem = ltile - lv;
+    // if v-runs are already >= 128 B, no transposition is needed: spend the rest of the tile on y only
+    const bool long_runs = ((int64_t)1 << lv) * (int64_t)esz >= 128;
+    int lx_t = long_runs ? 0 : std::min(lrem / 2, 8);
+    int ly_t = std::min(lrem - lx_t, 8);
     int64_t SX = 1, SY = 1;
-    // the destination unit-stride mode always goes to y first (if it is not v)
-    if (ys < (size_t)n && role[dord[ys]] == 0 && ty_target > 1) { role[dord[ys]] = 3; SY *= q.ext[dord[ys]]; ys++; }
-    bool grow_x = tx_target > 1, grow_y = ty_target > 1;
+    if (ys < (size_t)n && role[dord[ys]] == 0 && ly_t > 0) { role[dord[ys]] = 3; SY *= q.ext[dord[ys]]; ys++; }
+    bool grow_x = lx_t > 0, grow_y = ly_t > 0;
     while (grow_x || grow_y) {
         if (grow_x) {
-            if (SX >= tx_target || xs >= n || role[xs] != 0) grow_x = false;
+            if (SX >= ((int64_t)1 << lx_t) || xs >= n || role[xs] != 0) grow_x = false;
             else { role[xs] = 2; SX *= q.ext[xs]; xs++; }
         }
         if (grow_y) {
-            if (SY >= ty_target || ys >= (size_t)n || role[dord[ys]] != 0) grow_y = false;
+            if (SY >= ((int64_t)1 << ly_t) || ys >= (size_t)n || role[dord[ys]] != 0) grow_y = false;
             else { role[dord[ys]] = 3; SY *= q.ext[dord[ys]]; ys++; }
         }
     }
     for (int i = 0; i < n; i++) {
-        if (role[i] == 2) { k.x_ext[k.nx] = q.ext[i]; k.x_ss[k.nx] = sstride[i]; k.x_ds[k.nx] = q.dst_stride[i]; k.nx++; }
-        if (role[i] == 0) { k.o_ext[k.n_out] = q.ext[i]; k.o_ss[k.n_out] = sstride[i]; k.o_ds[k.n_out] = q.dst_stride[i]; k.n_out++; }
+        if (role[i] == 2) { k.x_ext[k.nx] = (unsigned)q.ext[i]; k.x_ss[k.nx] = sstride[i]; k.x_ds[k.nx] = q.dst_stride[i]; k.nx++; }
+        if (role[i] == 0) { k.o_ext[k.n_out] = (unsigned)q.ext[i]; k.o_ss[k.n_out] = sstride[i]; k.o_ds[k.n_out] = q.dst_stride[i]; k.n_out++; }
     }
     for (int i : dord)
-        if (role[i] == 3) { k.y_ext[k.ny] = q.ext[i]; k.y_ss[k.ny] = sstride[i]; k.y_ds[k.ny] = q.dst_stride[i]; k.ny++; }
+        if (role[i] == 3) { k.y_ext[k.ny] = (unsigned)q.ext[i]; k.y_ss[k.ny] = sstride[i]; k.y_ds[k.ny] = q.dst_stride[i]; k.ny++; }
     k.SX = SX; k.SY = SY;
-    // tile extents: use what the other side leaves unused, bounded by the table size
-    k.TX = (int)std::min<int64_t>(SX, std::max(1, tx_target));
-    k.TY = (int)std::min<int64_t>(SY, std::max(1, rem / k.TX));
-    if ((int64_t)k.TX * k.TY * k.VT < rem * k.VT && SX > k.TX) k.TX = (int)std::min<int64_t>(SX, std::max(1, rem / k.TY));
-    while (k.VT * k.TX > PT_MAX_TAB) k.TX = std::max(1, k.TX / 2);
-    while (k.VT * k.TY > PT_MAX_TAB) k.TY = std::max(1, k.TY / 2);
-    k.pitch = (k.VT * k.TX) | 1;
-    k.v_chunks = (k.v_ext + k.VT - 1) / k.VT;
-    k.x_chunks = (SX + k.TX - 1) / k.TX;
-    k.y_chunks = (SY + k.TY - 1) / k.TY;
+    // tile extents (powers of two): shrink to the space, give the slack to the other side
+    int lx = std::min(lx_t, ceil_log2(SX));
+    int ly = std::min(std::min(lrem - lx, 8), ceil_log2(SY));
+    lx = std::min(std::min(lrem - ly, 8), ceil_log2(SX));
+    k.lv = lv; k.lx = lx; k.ly = ly;
+    const int VT = 1 << lv, TX = 1 << lx, TY = 1 << ly;
+    k.direct = (lx == 0 || ly == 0) ? 1 : 0;
+    const int row = VT * TX;
+    k.pitch = ((row + G - 1) / G) * G + std::min(VT, G);
+    k.v_chunks = (unsigned)((k.v_ext + VT - 1) / VT);
+    k.x_chunks = (unsigned)((SX + TX - 1) / TX);
+    k.y_chunks = (unsigned)((SY + TY - 1) / TY);
     int64_t outer = 1;
     for (int i = 0; i < k.n_out; i++) outer *= k.o_ext[i];
-    int64_t grid = k.v_chunks * k.x_chunks * k.y_chunks * outer;
+    if (SX >= ((int64_t)1 << 31) || SY >= ((int64_t)1 << 31) || outer >= ((int64_t)1 << 31)) return cudaErrorInvalidValue;
+    int64_t grid = (int64_t)k.v_chunks * k.x_chunks * k.y_chunks * outer;
     if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    size_t smem = (size_t)k.pitch * k.TY * esz;
+    size_t smem = k.direct ? 0 : (size_t)k.pitch * TY * esz;
 
     const bool planar = q.plane_stride != 0;
-#define MB200_PERM(E, S, P) permute_kernel<E, S, P><<<(unsigned)grid, PT_THREADS, smem, s>>>(k, (const E *)src, dst)
+#define MB200_PERM(E, S, P)                                                                               \
+    do {                                                                                                  \
+        static bool cfg = false;                                                                          \
+        if (!cfg) {                                                                                       \
+            cudaFuncSetAttribute(permute_kernel<E, S, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); \
+            cfg = true;                                                                                   \
+        }                                                                                                 \
+        permute_kernel<E, S, P><<<(unsigned)grid, PT_THREADS, smem, s>>>(k, (const E *)src, dst);         \
+    } while (0)
     switch (dtype) {
         case MB200_F32: MB200_PERM(float, float, false); break;
         case MB200_F64: MB200_PERM(double, double, false); break;

@@ -104,6 +104,18 @@ class B200Array:
         out.copy_from_host(a)
         return out
 
+    @classmethod
+    def from_torch(cls, t, shape, dtype):
+        """Alias a contiguous CUDA torch tensor as a column-major array of `shape`/`dtype` (no copy; the
+        torch tensor is kept alive as the owner). Used for device-generated synthetic data."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape, dtype=np.int64)) if len(shape) else 1
+        if not t.is_cuda or not t.is_contiguous() or t.numel() * t.element_size() < n * dtype.itemsize:
+            raise ArgumentError("from_torch needs a contiguous CUDA tensor at least as large as the array")
+        import torch
+        owner = t.view(torch.uint8).reshape(-1) if t.dtype != torch.uint8 else t.reshape(-1)
+        return cls(shape, dtype, t.device.index, _owner=owner, _ptr=t.data_ptr())
+
     def copy_from_host(self, a):
         a = _lib.fortran(a)
         if a.shape != self.shape or a.dtype != self.dtype:

@@ -1,0 +1,103 @@
+"""Per-kernel numbers for DESIGN.md / profiles/: K1 permute GB/s and binary_einsum TFLOP/s on the BASELINE
+configs (aligned and scrambled layouts). CUDA-event timed, device-resident, best-of and mean. Writes
+gpurun_out/kernels.json."""
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import muscle_b200 as mb  # noqa: E402
+from muscle_b200 import B200Array, Index, Tensor, _lib, binary_einsum  # noqa: E402
+
+I = lambda s: [Index(c) for c in s]
+
+
+def dev_rand(shape, dtype, seed=0):
+    g = torch.Generator(device="cuda:0"); g.manual_seed(seed)
+    n = int(np.prod(shape))
+    cplx = np.dtype(dtype).kind == "c"
+    real = torch.float64 if np.dtype(dtype).itemsize // (2 if cplx else 1) == 8 else torch.float32
+    t = torch.rand((2 if cplx else 1) * n, dtype=real, device="cuda:0", generator=g) * 2 - 1
+    return B200Array.from_torch(t, shape, dtype)
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.min(ts)), float(np.mean(ts))
+
+
+def permute_case(name, shape, perm, dtype, flags=0):
+    src = dev_rand(shape, dtype)
+    dst = B200Array([shape[p] for p in perm], dtype) if not flags else B200Array(list(shape) + [2], np.float64 if dtype == "complex128" else np.float32)
+    h = _lib.Handle.get()
+    fn = lambda: _lib.check(mb.lib().mb200_permute(h.ptr, C.c_void_p(dst.ptr), C.c_void_p(src.ptr), _lib.dtype_enum(dtype),
+                                                    len(shape), _lib.i64(shape), _lib.i32(perm), flags))
+    best, mean = timeit(fn)
+    nbytes = 2 * src.nbytes
+    return {"name": name, "shape": list(shape), "perm": list(perm), "dtype": dtype, "planar": bool(flags),
+            "bytes": nbytes, "ms_best": best, "ms_mean": mean, "gbs_best": nbytes / best / 1e6, "gbs_mean": nbytes / mean / 1e6}
+
+
+def einsum_case(name, ext, ia, ib, ic, dtype, iters=5):
+    A = Tensor(dev_rand([ext[c] for c in ia], dtype, 1), I(ia))
+    B = Tensor(dev_rand([ext[c] for c in ib], dtype, 2), I(ib))
+    labels = set(ia) | set(ib)
+    flops = (8.0 if np.dtype(dtype).kind == "c" else 2.0) * float(np.prod([ext[c] for c in labels], dtype=np.float64))
+    best, mean = timeit(lambda: binary_einsum(A, B, out=I(ic)), iters=iters, warm=2)
+    return {"name": name, "dtype": dtype, "a": ia, "b": ib, "c": ic, "flops": flops, "ms_best": best, "ms_mean": mean,
+            "tflops_best": flops / best / 1e9, "tflops_mean": flops / mean / 1e9}
+
+
+def main():
+    out = {"permute": [], "einsum": []}
+    P = out["permute"]
+    P.append(permute_case("cfg1_A_pack kilj->ijkl", (64, 64, 64, 64), (1, 3, 0, 2), "complex128"))
+    P.append(permute_case("cfg1_B_pack nlmk->klnm", (64, 64, 64, 64), (3, 1, 0, 2), "complex128"))
+    P.append(permute_case("transpose 4096x4096", (4096, 4096), (1, 0), "complex128"))
+    P.append(permute_case("transpose 8192x8192 f32", (8192, 8192), (1, 0), "float32"))
+    P.append(permute_case("transpose 8192x4096 c64", (8192, 4096), (1, 0), "complex64"))
+    P.append(permute_case("transpose 8192x4096 f64", (8192, 4096), (1, 0), "float64"))
+    P.append(permute_case("cfg2b_out awsc->atvc-like (1024,8,2,1024)->(0,2,1,3)", (1024, 8, 2, 1024), (0, 2, 1, 3), "complex128"))
+    P.append(permute_case("mps d=2 fastest (2,1024,1024,8)->(1,0,3,2)", (2, 1024, 1024, 8), (1, 0, 3, 2), "complex128"))
+    P.append(permute_case("rank6 dim16 reverse", (16,) * 6, (5, 4, 3, 2, 1, 0), "complex128"))
+    P.append(permute_case("rank8 dim8 c64 interleave", (8,) * 8, (4, 0, 5, 1, 6, 2, 7, 3), "complex64"))
+    P.append(permute_case("cfg3 pack+planar c64 (256,8,8,256,8)->(0,2,3,1,4)", (256, 8, 8, 256, 8), (0, 2, 3, 1, 4), "complex64", 1))
+    P.append(permute_case("copy (identity) c128 64^4", (64, 64, 64, 64), (0, 1, 2, 3), "complex128"))
+    E = out["einsum"]
+    e64 = dict(i=64, j=64, k=64, l=64, m=64, n=64)
+    E.append(einsum_case("cfg1 aligned  A[i,j,k,l] B[k,l,m,n] -> [i,j,m,n]", e64, "ijkl", "klmn", "ijmn", "complex128"))
+    E.append(einsum_case("cfg1 scrambled A[k,i,l,j] B[n,l,m,k] -> [m,j,n,i]", e64, "kilj", "nlmk", "mjni", "complex128"))
+    e2 = dict(a=1024, b=1024, c=1024, e=1024, w=8, v=8, s=2, t=2)
+    E.append(einsum_case("cfg2a", e2, "awb", "bsc", "awsc", "complex128"))
+    E.append(einsum_case("cfg2b", e2, "awsc", "wstv", "atvc", "complex128", iters=20))
+    E.append(einsum_case("cfg2c", e2, "atvc", "ate", "evc", "complex128"))
+    e3 = dict(l=256, k=8, b=8, m=256, q=8, r=256, z=8)
+    E.append(einsum_case("cfg3 PEPS batched c64", e3, "lkbmz", "mkqrz", "lbqrz", "complex64"))
+    e4 = {c: 16 for c in "abcdefghi"}
+    E.append(einsum_case("cfg4a rank6 dim16", e4, "adbecf", "fgdhei", "abcghi", "complex128"))
+    e5 = {c: 8 for c in "abcdefghpqrs"}
+    E.append(einsum_case("cfg5 rank8 dim8 c64 (unsliced)", e5, "aebfcgdh", "hpgqfres", "srqpdcba", "complex64"))
+    E.append(einsum_case("dgemm 8192^3 f64", dict(i=8192, j=8192, k=8192), "ik", "kj", "ij", "float64", iters=3))
+    E.append(einsum_case("sgemm 8192^3 f32", dict(i=8192, j=8192, k=8192), "ik", "kj", "ij", "float32", iters=3))
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(out, open("gpurun_out/kernels.json", "w"), indent=1)
+    for r in P:
+        print(f"PERMUTE {r['name']:<60s} {r['gbs_best']:8.0f} GB/s best {r['gbs_mean']:8.0f} mean")
+    for r in E:
+        print(f"EINSUM  {r['name']:<60s} {r['tflops_best']:8.2f} TF/s best {r['tflops_mean']:8.2f} mean  {r['ms_mean']:.3f} ms")
+
+
+if __name__ == "__main__":
+    main()
