@@ -1,0 +1,154 @@
+# MuscleB200.jl — the reference-side binding of libmuscle_b200.so (include/muscle_b200.h).
+#
+# UNEXECUTED IN THIS REPOSITORY'S BUILD IMAGE: Julia is not installed there (no network), so this file is
+# source-only. The Python/ctypes host in `muscle.jl_b200/` binds the very same entry points and is what
+# the tests and benchmarks run; this is the stub a Muscle.jl maintainer would add (INTEGRATION.md).
+#
+# It plugs into Muscle's existing dispatch exactly like the cuTENSOR extension does:
+#   * a new backend type next to src/Backend.jl:6-14,
+#   * `Muscle.Domain(::Type{<:B200Array}) = DomainB200()`            (pattern: ext/MuscleCUDAExt.jl:7),
+#   * `choose_backend_rule(binary_einsum, ::DomainB200, ::DomainB200)` (pattern: binary_einsum.jl:21),
+#   * the 4-argument backend methods invoked at src/Operations/binary_einsum.jl:50 and :68.
+module MuscleB200
+
+using Muscle
+using Muscle: Tensor, Index, inds, Backend, Domain
+using Libdl
+
+const libmuscle_b200 = Ref{String}(get(ENV, "MUSCLE_B200_LIB", "libmuscle_b200.so"))
+
+# ---- status → Julia exceptions (include/muscle_b200.h: mb200_status_t) -------------------------------
+const MB200_OK = Cint(0)
+last_error() = unsafe_string(ccall((:mb200_last_error_string, libmuscle_b200[]), Cstring, ()))
+function check(status::Cint)
+    status == MB200_OK && return nothing
+    msg = last_error()
+    if status == 1 || status == 2          # INVALID_ARGUMENT / NOT_SUPPORTED
+        throw(ArgumentError(msg))          # what @argcheck raises, binary_einsum.jl:82-83
+    elseif status == 3                     # DIMENSION_MISMATCH
+        throw(DimensionMismatch(msg))      # src/Tensor.jl:23
+    else
+        throw(ErrorException("libmuscle_b200 status $status: $msg"))
+    end
+end
+
+# ---- handle (one per device per task-thread; the library locks internally) ---------------------------
+mutable struct Handle
+    ptr::Ptr{Cvoid}
+    function Handle(device::Integer=0)
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:mb200_create, libmuscle_b200[]), Cint, (Ref{Ptr{Cvoid}}, Cint), r, device))
+        h = new(r[])
+        finalizer(h -> ccall((:mb200_destroy, libmuscle_b200[]), Cint, (Ptr{Cvoid},), h.ptr), h)
+        return h
+    end
+end
+const DEFAULT_HANDLE = Ref{Union{Nothing,Handle}}(nothing)
+handle() = something(DEFAULT_HANDLE[], (DEFAULT_HANDLE[] = Handle(0)))
+
+# ---- device array: dense, column-major, complex interleaved — a Julia Array that lives in HBM ---------
+mutable struct B200Array{T,N} <: AbstractArray{T,N}
+    ptr::Ptr{Cvoid}
+    dims::NTuple{N,Int}
+    function B200Array{T,N}(::UndefInitializer, dims::NTuple{N,Int}) where {T,N}
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:mb200_malloc, libmuscle_b200[]), Cint, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}, Csize_t),
+                    handle().ptr, r, max(1, prod(dims)) * sizeof(T)))
+        a = new{T,N}(r[], dims)
+        finalizer(a -> ccall((:mb200_free, libmuscle_b200[]), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), handle().ptr, a.ptr), a)
+        return a
+    end
+end
+Base.size(a::B200Array) = a.dims
+Base.similar(a::B200Array, ::Type{T}, dims::Dims{N}) where {T,N} = B200Array{T,N}(undef, dims)
+Base.unsafe_convert(::Type{Ptr{T}}, a::B200Array{T}) where {T} = Ptr{T}(a.ptr)
+Base.getindex(::B200Array, I...) = error("scalar indexing of a B200Array is not supported; use Array(a)")
+
+function B200Array(x::Array{T,N}) where {T,N}
+    a = B200Array{T,N}(undef, size(x))
+    GC.@preserve x check(ccall((:mb200_memcpy_h2d, libmuscle_b200[]), Cint,
+                               (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Csize_t), handle().ptr, a.ptr, pointer(x), sizeof(x)))
+    check(ccall((:mb200_stream_sync, libmuscle_b200[]), Cint, (Ptr{Cvoid},), handle().ptr))
+    return a
+end
+function Base.Array(a::B200Array{T,N}) where {T,N}
+    x = Array{T,N}(undef, size(a))
+    GC.@preserve x check(ccall((:mb200_memcpy_d2h, libmuscle_b200[]), Cint,
+                               (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Csize_t), handle().ptr, pointer(x), a.ptr, sizeof(x)))
+    check(ccall((:mb200_stream_sync, libmuscle_b200[]), Cint, (Ptr{Cvoid},), handle().ptr))
+    return x
+end
+
+# ---- Backend / Domain plumbing -------------------------------------------------------------------------
+struct BackendB200 <: Muscle.Backend end
+struct DomainB200 <: Muscle.Domain end
+Muscle.Domain(::Type{<:B200Array}) = DomainB200()
+Muscle.choose_backend_rule(::typeof(Muscle.binary_einsum), ::DomainB200, ::DomainB200) = BackendB200()
+Muscle.choose_backend_rule(::typeof(Muscle.binary_einsum!), ::DomainB200, ::DomainB200, ::DomainB200) = BackendB200()
+
+dtype_enum(::Type{Float32}) = Cint(0)
+dtype_enum(::Type{Float64}) = Cint(1)
+dtype_enum(::Type{ComplexF32}) = Cint(2)
+dtype_enum(::Type{ComplexF64}) = Cint(3)
+dtype_enum(::Type{T}) where {T} = throw(ArgumentError("eltype $T is not supported by BackendB200"))
+
+# Index → int mode ids, the reference's own convention (ext/MuscleCUDAExt.jl:24-27)
+function modes(inds_c, inds_a, inds_b)
+    indmap = Dict{Index,Int32}()
+    for ind in Iterators.flatten((inds_a, inds_b))
+        get!(indmap, ind, Int32(length(indmap)))
+    end
+    all(i -> haskey(indmap, i), inds_c) || throw(ArgumentError("an index of the output is found in neither operand"))
+    return Int32[indmap[i] for i in inds_c], Int32[indmap[i] for i in inds_a], Int32[indmap[i] for i in inds_b]
+end
+
+# binary_einsum(::BackendB200, inds_c, a, b) — the method called at src/Operations/binary_einsum.jl:50
+function Muscle.binary_einsum(::BackendB200, inds_c, a::Tensor, b::Tensor)
+    T = Base.promote_eltype(a, b)                                   # ext/MuscleCUDAExt.jl:16
+    dims = map(inds_c) do i
+        i ∈ inds(a) ? size(a, i) : i ∈ inds(b) ? size(b, i) : throw(ArgumentError("index $i not found in a nor b"))
+    end
+    c = Tensor(similar(parent(a), T, Tuple(dims)), collect(Index, inds_c))
+    Muscle.binary_einsum!(BackendB200(), c, a, b)
+    return c
+end
+
+# binary_einsum!(::BackendB200, c, a, b) — the method called at src/Operations/binary_einsum.jl:68
+function Muscle.binary_einsum!(::BackendB200, c::Tensor, a::Tensor, b::Tensor)
+    mc, ma, mb = modes(inds(c), inds(a), inds(b))
+    ea, eb = Int64[size(a)...], Int64[size(b)...]
+    pa, pb, pc = parent(a), parent(b), parent(c)
+    entry = pc isa B200Array ? :device : :host
+    GC.@preserve pa pb pc mc ma mb ea eb begin
+        if entry === :device
+            check(ccall((:mb200_binary_einsum, libmuscle_b200[]), Cint,
+                (Ptr{Cvoid},
+                 Ptr{Cvoid}, Cint, Cint, Ptr{Int32}, Ptr{Int64},
+                 Ptr{Cvoid}, Cint, Cint, Ptr{Int32}, Ptr{Int64}, Ptr{Int64},
+                 Ptr{Cvoid}, Cint, Cint, Ptr{Int32}, Ptr{Int64}, Ptr{Int64}),
+                handle().ptr,
+                pointer_of(pc), dtype_enum(eltype(c)), length(mc), mc, C_NULL,
+                pointer_of(pa), dtype_enum(eltype(a)), length(ma), ma, ea, C_NULL,
+                pointer_of(pb), dtype_enum(eltype(b)), length(mb), mb, eb, C_NULL))
+            # stream-ordered; the shim synchronises before handing the result back to Julia code
+            check(ccall((:mb200_stream_sync, libmuscle_b200[]), Cint, (Ptr{Cvoid},), handle().ptr))
+        else
+            # host Arrays (with_backend(BackendB200()) on DomainHost operands): the library stages through HBM
+            check(ccall((:mb200_binary_einsum_host, libmuscle_b200[]), Cint,
+                (Ptr{Cvoid},
+                 Ptr{Cvoid}, Cint, Cint, Ptr{Int32},
+                 Ptr{Cvoid}, Cint, Cint, Ptr{Int32}, Ptr{Int64},
+                 Ptr{Cvoid}, Cint, Cint, Ptr{Int32}, Ptr{Int64}),
+                handle().ptr,
+                pointer_of(pc), dtype_enum(eltype(c)), length(mc), mc,
+                pointer_of(pa), dtype_enum(eltype(a)), length(ma), ma, ea,
+                pointer_of(pb), dtype_enum(eltype(b)), length(mb), mb, eb))
+        end
+    end
+    return c
+end
+
+pointer_of(x::B200Array) = x.ptr
+pointer_of(x::Array) = Ptr{Cvoid}(pointer(x))
+
+end # module
