@@ -140,6 +140,54 @@ void evict_one(mb200_handle_t h) {
     }
 }
 
+// K1 pack of one operand into the tcgen05 kernel's operand format: [batch][rows][4*K] floats, K-major,
+// every 8-k group stored as re_hi | re_lo | im_hi | im_lo chunks of 8 floats (tf32.cu). Expressed as an
+// ordinary strided permutation: the fastest summed mode (extent % 8 == 0) is split into (8, e/8) with
+// destination strides (1, 32); the other summed modes get 4*kstride, row modes rows*4K, batch modes beyond.
+bool build_pack_params(const Plan &p, int which, PermuteParams &q, int64_t &rows) {
+    struct Md { int64_t ext, ss, ds; };
+    std::vector<Md> v;
+    const int64_t K = p.K;
+    int64_t kstride = 1;
+    for (size_t i = 0; i < p.sum.size(); i++) {
+        const GroupMode &g = p.sum[i];
+        const int64_t ss = which ? g.sb : g.sa;
+        if (i == 0) {
+            v.push_back({8, ss, 1});
+            if (g.extent / 8 > 1) v.push_back({g.extent / 8, ss * 8, 32});
+        } else {
+            v.push_back({g.extent, ss, 4 * kstride});
+        }
+        kstride *= g.extent;
+    }
+    int64_t rstride = 1;
+    for (const GroupMode &g : (which ? p.right : p.left)) {
+        v.push_back({g.extent, which ? g.sb : g.sa, rstride * 4 * K});
+        rstride *= g.extent;
+    }
+    rows = rstride;
+    int64_t bstride = 1;
+    for (const GroupMode &g : p.batch) {
+        v.push_back({g.extent, which ? g.sb : g.sa, bstride * rows * 4 * K});
+        bstride *= g.extent;
+    }
+    std::sort(v.begin(), v.end(), [](const Md &a, const Md &b) { return a.ss < b.ss; });
+    if (v.size() > (size_t)MB200_MAX_MODES) return false;
+    q = PermuteParams{};
+    q.n = (int)v.size();
+    q.total = 1;
+    int64_t expect = 1;
+    for (int i = 0; i < q.n; i++) {
+        if (v[i].ss != expect) return false;   // not dense: the planner should have caught it
+        expect *= v[i].ext;
+        q.ext[i] = v[i].ext;
+        q.dst_stride[i] = v[i].ds;
+        q.total *= v[i].ext;
+    }
+    q.split = 1;
+    return true;
+}
+
 // span (in elements) touched by a possibly strided tensor
 int64_t span_of(const TensorDesc &t) {
     int64_t s = 1;
@@ -208,9 +256,30 @@ int contract_device(mb200_handle_t h, void *C, TensorDesc &dC, const int64_t *st
     }
 
     cudaError_t e;
+    PermuteParams qa, qb;
+    int64_t rows_a = 0, rows_b = 0;
     if (p.path == MB200_PATH_DIRECT) {
         e = launch_direct(p.dtype, cp->dp, R, Q, C, s);
         h->stats.launches_direct++;
+    } else if (p.path == MB200_PATH_TCGEN05_TF32 && tf32_available() && build_pack_params(p, 0, qa, rows_a) &&
+               build_pack_params(p, 1, qb, rows_b)) {
+        // pack A, pack B (K1 with the tf32 hi/lo split writer), then the tcgen05 GEMM with the permuting epilogue
+        void *pa = nullptr, *pb = nullptr;
+        const size_t ba = (size_t)p.L * rows_a * 4 * p.K * sizeof(float), bb = (size_t)p.L * rows_b * 4 * p.K * sizeof(float);
+        MB200_CUDA(cudaMallocAsync(&pa, ba, s));
+        MB200_CUDA(cudaMallocAsync(&pb, bb, s));
+        e = launch_permute(MB200_C64, qa, R, pa, s);
+        if (e == cudaSuccess) e = launch_permute(MB200_C64, qb, Q, pb, s);
+        h->stats.launches_permute += 2;
+        h->stats.launches_total += 2;
+        if (e == cudaSuccess) {
+            GettParams g = cp->gp;
+            g.C = C;
+            e = launch_tf32_gemm(pa, pb, g, s);
+            h->stats.launches_tcgen05++;
+        }
+        cudaFreeAsync(pa, s);
+        cudaFreeAsync(pb, s);
     } else {
         GettParams g = cp->gp;
         g.A = R; g.B = Q; g.C = C;

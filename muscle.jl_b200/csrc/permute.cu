@@ -58,18 +58,28 @@ __device__ __forceinline__ void digits_off(unsigned idx, int n, const unsigned *
     }
 }
 
-template <typename E, typename S, bool PLANAR>
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// PLANAR: 0 = interleaved (plain), 1 = two planes, 2 = tf32 hi/lo split into four 8-float chunks
+template <typename E, typename S, int PLANAR>
 __device__ __forceinline__ void put(void *dstv, int64_t off, const E &val, int64_t plane_stride) {
-    if constexpr (PLANAR) {
+    if constexpr (PLANAR == 1) {
         S *d = reinterpret_cast<S *>(dstv);
         d[off] = val.x;
         d[off + plane_stride] = val.y;
+    } else if constexpr (PLANAR == 2) {
+        S *d = reinterpret_cast<S *>(dstv);
+        const float rh = tf32_hi(val.x), ih = tf32_hi(val.y);
+        d[off] = rh;
+        d[off + 8] = val.x - rh;
+        d[off + 16] = ih;
+        d[off + 24] = val.y - ih;
     } else {
         reinterpret_cast<E *>(dstv)[off] = val;
     }
 }
 
-template <typename E, typename S, bool PLANAR>
+template <typename E, typename S, int PLANAR>
 __global__ void __launch_bounds__(PT_THREADS) permute_kernel(const __grid_constant__ PermK p,
                                                              const E *__restrict__ src, void *__restrict__ dstv) {
     __shared__ int64_t sSrcX[PT_MAX_TAB], sDstX[PT_MAX_TAB], sSrcY[PT_MAX_TAB], sDstY[PT_MAX_TAB];
@@ -225,10 +235,14 @@ cudaError_t launch_permute(int dtype, const PermuteParams &q, const void *src, v
         permute_kernel<E, S, P><<<(unsigned)grid, PT_THREADS, smem, s>>>(k, (const E *)src, dst);         \
     } while (0)
     switch (dtype) {
-        case MB200_F32: MB200_PERM(float, float, false); break;
-        case MB200_F64: MB200_PERM(double, double, false); break;
-        case MB200_C64: if (planar) MB200_PERM(float2, float, true); else MB200_PERM(float2, float, false); break;
-        default: if (planar) MB200_PERM(double2, double, true); else MB200_PERM(double2, double, false); break;
+        case MB200_F32: MB200_PERM(float, float, 0); break;
+        case MB200_F64: MB200_PERM(double, double, 0); break;
+        case MB200_C64:
+            if (q.split) MB200_PERM(float2, float, 2);
+            else if (planar) MB200_PERM(float2, float, 1);
+            else MB200_PERM(float2, float, 0);
+            break;
+        default: if (planar) MB200_PERM(double2, double, 1); else MB200_PERM(double2, double, 0); break;
     }
 #undef MB200_PERM
     return cudaGetLastError();

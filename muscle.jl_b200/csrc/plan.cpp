@@ -173,6 +173,24 @@ int make_plan(const TensorDesc &A, const TensorDesc &B, TensorDesc &C, const int
     plan.bytes = (double)dtype_size(plan.dtype) *
                  ((double)A.numel() + (double)B.numel() + (double)plan.M * plan.N * plan.L);
 
+    // ---- tcgen05 eligibility: both operands dense in memory (the pack pass is a K1 permute of a dense
+    // tensor) and the fastest summed mode a multiple of 8 (one 8-k group = one 128 B TMA row)
+    auto dense = [](const TensorDesc &T) {
+        std::vector<std::pair<int64_t, int64_t>> v;
+        for (int i = 0; i < T.n; i++)
+            if (T.ext[i] != 1) v.push_back({T.stride[i], T.ext[i]});
+        std::sort(v.begin(), v.end());
+        int64_t expect = 1;
+        for (auto &x : v) {
+            if (x.first != expect) return false;
+            expect *= x.second;
+        }
+        return true;
+    };
+    plan.tc_ok = plan.dtype == MB200_C64 && !plan.sum.empty() && plan.sum[0].extent % 8 == 0 && dense(A) && dense(B) &&
+                 plan.M >= 64 && plan.N >= 32 && plan.K >= 64 && plan.M < ((int64_t)1 << 31) &&
+                 plan.N < ((int64_t)1 << 31) && plan.L < ((int64_t)1 << 31) && plan.K < ((int64_t)1 << 27);
+
     // ---- kernel family ---------------------------------------------------------------------------
     const int64_t TABLE_LIMIT = (int64_t)1 << 26;
     bool tables_ok = plan.M <= TABLE_LIMIT && plan.N <= TABLE_LIMIT && plan.K <= TABLE_LIMIT &&
@@ -180,14 +198,17 @@ int make_plan(const TensorDesc &A, const TensorDesc &B, TensorDesc &C, const int
     int path;
     if (plan.empty_output || macs <= (double)(1 << 20) || plan.K <= 2 || !tables_ok)
         path = MB200_PATH_DIRECT;
+    else if (dtype_is_double(plan.dtype))
+        path = MB200_PATH_GETT_F64;
     else
-        path = dtype_is_double(plan.dtype) ? MB200_PATH_GETT_F64 : MB200_PATH_SIMT_F32;
+        path = (plan.tc_ok && macs >= (double)((int64_t)1 << 27)) ? MB200_PATH_TCGEN05_TF32 : MB200_PATH_SIMT_F32;
     if (forced_path != MB200_PATH_AUTO) {
         if (forced_path == MB200_PATH_DIRECT) path = MB200_PATH_DIRECT;
         else if (!plan.empty_output && tables_ok) {
             if (forced_path == MB200_PATH_GETT_F64 && dtype_is_double(plan.dtype)) path = forced_path;
             if (forced_path == MB200_PATH_SIMT_F32 && !dtype_is_double(plan.dtype)) path = forced_path;
-            if (forced_path == MB200_PATH_TCGEN05_TF32 && !dtype_is_double(plan.dtype)) path = forced_path;
+            if (forced_path == MB200_PATH_TCGEN05_TF32 && plan.tc_ok) path = forced_path;
+            if (forced_path == MB200_PATH_TCGEN05_TF32 && !plan.tc_ok && !dtype_is_double(plan.dtype)) path = MB200_PATH_SIMT_F32;
         }
     }
     plan.path = path;

@@ -47,6 +47,7 @@ struct Plan {
     bool a_kmajor = false, b_kmajor = false;
     int path = MB200_PATH_DIRECT;
     bool empty_output = false;  // some C extent is 0
+    bool tc_ok = false;         // eligible for the tcgen05 3xTF32 path (dense ComplexF32 operands, first summed extent % 8 == 0)
     double flops = 0, bytes = 0;
     std::string key;  // cache key (all integers of the three descriptors + dtypes + forced path)
 };

@@ -1,0 +1,342 @@
+// K3 — ComplexF32 GEMM on 5th-gen tensor cores: tcgen05.mma kind::tf32, accumulators in TMEM, operands
+// fed by TMA, 3xTF32 error compensation, 4M complex decomposition, fused permuting epilogue.
+//
+// Operand format (written by the K1 pack pass with the SPLIT4 writer, permute.cu): a K-major matrix
+// [rows][4*K] of float where every group of 8 k-values is stored as four consecutive 32 B chunks
+//     | re_hi(k0..k7) | re_lo(k0..k7) | im_hi(k0..k7) | im_lo(k0..k7) |        (128 B per row per group)
+// with x_hi = x & 0xFFFFE000 (exact tf32) and x_lo = x - x_hi (exact in fp32). One TMA box row is one
+// 128 B swizzle-128B line; each 32 B chunk is exactly one K=8 tf32 MMA operand, so the MMA descriptor
+// for chunk p is the tile descriptor advanced by 32*p bytes.
+//
+// Per group of 8 k the MMA warp issues 12 MMAs (3xTF32 x 4M) into two TMEM accumulators:
+//     D_re += rh*rh' + rh*rl' + rl*rh' - (ih*ih' + ih*il' + il*ih')      (minus = a_negate in the idesc)
+//     D_im += rh*ih' + rh*il' + rl*ih' +  ih*rh' + ih*rl' + il*rh'
+// Effective ceiling: TF32 dense peak / 3 in complex-flop terms (8 flops per complex MAC = 12 tf32 MACs).
+//
+// Roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..9 = epilogue (tcgen05.ld 32 lanes x BN/2 columns each -> running sums in registers ->
+// C[rowC[m] + colC[n] + batC[l]]). Pipelines: full/empty mbarriers over a 6-stage smem ring (TMA <-> MMA),
+// tmem_full/tmem_empty over two TMEM chunk buffers (MMA <-> epilogue). One output tile (128 x BN) per CTA.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <mutex>
+
+#include "kernels.cuh"
+
+namespace mb200 {
+
+namespace {
+
+constexpr int TBM = 128;          // tile rows = TMEM lanes
+constexpr int TSTAGES = 6;
+constexpr int TTHREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int GROUP_BYTES = 128;  // bytes per row per 8-k group
+constexpr int CHUNK_GROUPS = 16;  // 128 k per TMEM accumulation chunk (two-level accumulation)
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug must surface as a trapped kernel, never as a hung GPU
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4, [16,30) leading byte offset >> 4 (= 1, unused for swizzled K-major),
+//   [32,46) stride byte offset >> 4 (= 1024 B between 8-row groups), [46,48) version = 1 (Blackwell),
+//   [61,64) layout type = 2 (SWIZZLE_128B). Tiles are 1024 B aligned, so base_offset = 0.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @4, a/b_format TF32 = 2 @7/@10,
+// a_negate @13, a/b K-major (0) @15/@16, N >> 3 @17, M >> 4 @24
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool neg_a) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((neg_a ? 1u : 0u) << 13) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct Tf32Params {
+    float2 *C;
+    const int64_t *rowC, *colC, *batC;
+    int64_t M, N, L;
+    int KG;   // number of 8-k groups
+};
+
+template <int BN>
+struct Tf32Smem {
+    static constexpr int A_BYTES = TBM * GROUP_BYTES;   // 16 KB
+    static constexpr int B_BYTES = BN * GROUP_BYTES;
+    static constexpr int STAGE = A_BYTES + B_BYTES;
+    static constexpr int TOTAL = TSTAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/ + BN * 8 /*colC*/;
+};
+
+// Two-level accumulation. The tensor core adds into TMEM with truncation, so a long accumulation chain
+// drifts linearly (measured: rel. error 1.45e-8 * K, i.e. 5.9e-5 at K = 4096). TMEM therefore only ever
+// holds a chunk of CHUNK_GROUPS*8 = 128 k (double-buffered: the MMA warp fills buffer c&1 while the
+// epilogue warps drain the other one); the running sums live in the epilogue warps' registers and are
+// added with ordinary round-to-nearest FADDs.
+template <int BN>
+__global__ void __launch_bounds__(TTHREADS, 1)
+tf32_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                 const __grid_constant__ Tf32Params p) {
+    using SM = Tf32Smem<BN>;
+    constexpr int HALF = BN / 2;                  // columns per epilogue thread
+    constexpr uint32_t BUF_COLS = 2 * BN;         // D_re | D_im
+    constexpr uint32_t TMEM_COLS = 2 * BUF_COLS;  // two chunk buffers (256 or 512: powers of two)
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *full = reinterpret_cast<uint64_t *>(tiles + TSTAGES * SM::STAGE);
+    uint64_t *empty = full + TSTAGES;
+    uint64_t *tmem_full = empty + TSTAGES;        // [2]
+    uint64_t *tmem_empty = tmem_full + 2;         // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    int64_t *sColC = reinterpret_cast<int64_t *>(tiles + TSTAGES * SM::STAGE + 256);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t tiles_m = (p.M + TBM - 1) / TBM, tiles_n = (p.N + BN - 1) / BN;
+    const int64_t per = tiles_m * tiles_n;
+    const int64_t l = blockIdx.x / per;
+    const int64_t t = blockIdx.x % per;
+    // grouped rasterisation: 8 row-tiles share a B column panel in L2
+    const int64_t gsz_full = 8, pg = gsz_full * tiles_n, g = t / pg, gm0 = g * gsz_full;
+    const int64_t gsz = (tiles_m - gm0) < gsz_full ? (tiles_m - gm0) : gsz_full;
+    const int64_t tm = gm0 + (t % pg) % gsz, tn = (t % pg) / gsz;
+    const int m0 = (int)(tm * TBM), n0 = (int)(tn * BN);
+    const int nchunks = (p.KG + CHUNK_GROUPS - 1) / CHUNK_GROUPS;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+        for (int s = 0; s < TSTAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp >= 2) {
+        for (int i = threadIdx.x - 64; i < BN; i += TTHREADS - 64) sColC[i] = (n0 + i < p.N) ? p.colC[n0 + i] : 0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {   // ---- TMA producer
+            for (int kg = 0; kg < p.KG; kg++) {
+                const int s = kg % TSTAGES;
+                const uint32_t ph = (kg / TSTAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_expect_tx(&full[s], SM::STAGE);
+                unsigned char *a = tiles + s * SM::STAGE;
+                tma_load_3d(a, &mapA, &full[s], kg * 32, m0, (int)l);
+                tma_load_3d(a + SM::A_BYTES, &mapB, &full[s], kg * 32, n0, (int)l);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {   // ---- MMA issuer
+            constexpr uint32_t IDESC = make_idesc(TBM, BN, false), IDESC_NEG = make_idesc(TBM, BN, true);
+            int kg = 0;
+            for (int c = 0; c < nchunks; c++) {
+                const int buf = c & 1;
+                mbar_wait(&tmem_empty[buf], ((c >> 1) & 1) ^ 1);   // epilogue has drained this buffer
+                tc_fence_after();
+                const uint32_t d_re = tmem_base + buf * BUF_COLS, d_im = d_re + BN;
+                const int kend = min(p.KG, (c + 1) * CHUNK_GROUPS);
+                for (bool first = true; kg < kend; kg++, first = false) {
+                    const int s = kg % TSTAGES;
+                    mbar_wait(&full[s], (kg / TSTAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(tiles + s * SM::STAGE);
+                    const uint64_t da = make_desc(sa), db = make_desc(sa + SM::A_BYTES);
+                    // chunk c of a row is +32*c bytes: descriptor start-address field += 2*c
+                    const uint64_t a_rh = da, a_rl = da + 2, a_ih = da + 4, a_il = da + 6;
+                    const uint64_t b_rh = db, b_rl = db + 2, b_ih = db + 4, b_il = db + 6;
+                    const uint32_t acc = first ? 0u : 1u;
+                    umma_tf32(d_re, a_rh, b_rh, IDESC, acc);
+                    umma_tf32(d_im, a_rh, b_ih, IDESC, acc);
+                    umma_tf32(d_re, a_rh, b_rl, IDESC, 1u);
+                    umma_tf32(d_im, a_rh, b_il, IDESC, 1u);
+                    umma_tf32(d_re, a_rl, b_rh, IDESC, 1u);
+                    umma_tf32(d_im, a_rl, b_ih, IDESC, 1u);
+                    umma_tf32(d_re, a_ih, b_ih, IDESC_NEG, 1u);
+                    umma_tf32(d_im, a_ih, b_rh, IDESC, 1u);
+                    umma_tf32(d_re, a_ih, b_il, IDESC_NEG, 1u);
+                    umma_tf32(d_im, a_ih, b_rl, IDESC, 1u);
+                    umma_tf32(d_re, a_il, b_ih, IDESC_NEG, 1u);
+                    umma_tf32(d_im, a_il, b_rh, IDESC, 1u);
+                    umma_commit(&empty[s]);          // frees the smem stage when these MMAs have read it
+                }
+                umma_commit(&tmem_full[buf]);        // this chunk's accumulators are complete
+            }
+        }
+    } else {               // ---- epilogue: warps 2..9; TMEM lane quarter = warp % 4, column half = (warp-2)/4
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        const int row = q * 32 + lane;
+        const int64_t m = (int64_t)m0 + row;
+        const bool row_ok = m < p.M;
+        const int64_t crow = (row_ok ? p.rowC[m] : 0) + p.batC[l];
+        float accr[HALF], acci[HALF];
+#pragma unroll
+        for (int j = 0; j < HALF; j++) accr[j] = acci[j] = 0.f;
+        for (int c = 0; c < nchunks; c++) {
+            const int buf = c & 1;
+            mbar_wait(&tmem_full[buf], (c >> 1) & 1);
+            tc_fence_after();
+            const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BUF_COLS + half * HALF;
+#pragma unroll
+            for (int sub = 0; sub < HALF / 32; sub++) {
+                uint32_t v[32];
+                tmem_ld32(tq + sub * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j++) accr[sub * 32 + j] += __uint_as_float(v[j]);
+                tmem_ld32(tq + BN + sub * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j++) acci[sub * 32 + j] += __uint_as_float(v[j]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+        }
+        if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < HALF; j++) {
+                const int cidx = half * HALF + j;
+                if (n0 + cidx < p.N) p.C[crow + sColC[cidx]] = make_float2(accr[j], acci[j]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---- host side ----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// packed operand: [L][rows][4*K] floats, K-major, rows of KG*128 bytes
+bool make_map(CUtensorMap *map, const void *base, int64_t K, int64_t rows, int64_t L, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)(4 * K), (cuuint64_t)rows, (cuuint64_t)L};
+    cuuint64_t strides[2] = {(cuuint64_t)(16 * K), (cuuint64_t)(16 * K) * (cuuint64_t)rows};
+    cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <int BN>
+cudaError_t launch_bn(const void *packA, const void *packB, const GettParams &g, cudaStream_t s) {
+    CUtensorMap mapA, mapB;
+    if (!make_map(&mapA, packA, g.K, g.M, g.L, TBM) || !make_map(&mapB, packB, g.K, g.N, g.L, BN))
+        return cudaErrorInvalidValue;
+    Tf32Params p{};
+    p.C = reinterpret_cast<float2 *>(g.C);
+    p.rowC = g.rowC; p.colC = g.colC; p.batC = g.batC;
+    p.M = g.M; p.N = g.N; p.L = g.L;
+    p.KG = (int)(g.K / 8);
+    const int64_t grid = ((g.M + TBM - 1) / TBM) * ((g.N + BN - 1) / BN) * g.L;
+    if (grid <= 0) return cudaSuccess;
+    if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    static bool cfg = false;
+    if (!cfg) {
+        cudaError_t e = cudaFuncSetAttribute(tf32_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tf32Smem<BN>::TOTAL);
+        if (e != cudaSuccess) return e;
+        cfg = true;
+    }
+    tf32_gemm_kernel<BN><<<(unsigned)grid, TTHREADS, Tf32Smem<BN>::TOTAL, s>>>(mapA, mapB, p);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+bool tf32_available() { return encode_fn() != nullptr; }
+
+// C (ComplexF32, scattered through rowC/colC/batC) = packA [L][M][4K] x packB [L][N][4K]^T, K % 8 == 0
+cudaError_t launch_tf32_gemm(const void *packA, const void *packB, const GettParams &g, cudaStream_t s) {
+    if (g.K % 8 != 0 || g.K < 8) return cudaErrorInvalidValue;
+    if (g.N > 64) return launch_bn<128>(packA, packB, g, s);
+    return launch_bn<64>(packA, packB, g, s);
+}
+
+}  // namespace mb200

@@ -329,3 +329,63 @@ def test_stats_count_launches():
     contract(a, ia, b, ib, ic, path=mb.PATH_GETT_F64)
     s = h.stats()
     assert s["launches_gett_f64"] == 1 and s["launches_total"] >= 1
+
+
+# ---- K3: tcgen05 / TMEM 3xTF32 path ------------------------------------------------------------------------
+TC_CASES = [
+    ("tc_matmul_kmajor", dict(i=200, j=72, k=128), "ki", "kj", "ij"),
+    ("tc_matmul_mmajor", dict(i=200, j=72, k=128), "ik", "jk", "ji"),
+    ("tc_rank4", dict(a=16, b=12, c=8, d=24, e=10, f=16), "acbd", "dfce", "feab"),
+    ("tc_batch_peps", dict(l=64, k=8, b=4, m=32, q=4, r=48, z=3), "lkbmz", "mkqrz", "lbqrz"),
+    ("tc_multitile", dict(m=300, n=520, k=264, l=2), "kml", "nlk", "nml"),
+    ("tc_multitile_T", dict(m=300, n=520, k=264, l=2), "kml", "nlk", "mln"),
+    ("tc_rank8", dict(a=4, b=4, c=4, d=2, e=8, f=4, g=2, h=8, p=4, q=4, r=2, s=4), "aebfcgdh", "hpgqfres", "srqpdcba"),
+    ("tc_skinny_n", dict(a=512, w=8, s=8, t=4, v=8), "aws", "wstv", "atv"),
+]
+
+
+def _tc_planned(case):
+    name, ext, ia, ib, ic = case
+    labels = {c: k for k, c in enumerate(dict.fromkeys(ia + ib))}
+    h = _lib.Handle.get()
+    return labels
+
+
+@pytest.mark.parametrize("integer", [False, True], ids=["random", "integer_exact"])
+@pytest.mark.parametrize("case", TC_CASES, ids=[c[0] for c in TC_CASES])
+def test_tcgen05_tf32x3_parity(case, integer):
+    """ComplexF32 through pack (K1 split writer) + tcgen05 GEMM, forced; <= 1e-5 rel. Frobenius against the
+    oracle, and bit-exact on integer-valued inputs (hi parts exact, lo parts zero, fp32 accumulation exact)."""
+    a, ia, b, ib, ic = build_case(case, "complex64", seed=31, integer=integer)
+    ref = binary_einsum_general(ic, a.astype(np.complex128), ia, b.astype(np.complex128), ib).astype(np.complex64)
+    h = _lib.Handle.get()
+    h.reset_stats()
+    got = contract(a, ia, b, ib, ic, device=True, path=mb.PATH_TCGEN05_TF32)
+    s = h.stats()
+    assert s["launches_tcgen05"] == 1 and s["launches_permute"] == 2, s   # the tcgen05 kernel really ran
+    assert got.shape == ref.shape
+    if integer:
+        assert np.array_equal(got, ref), case[0]
+    else:
+        assert rel_frobenius(got, ref) <= 1e-5, (case[0], rel_frobenius(got, ref))
+
+
+def test_tcgen05_accuracy_beats_plain_tf32():
+    """3xTF32 + two-level accumulation must recover ~fp32 accuracy at long K (single-pass TF32 gives ~1e-3, a
+    single TMEM accumulation chain drifts to 5.9e-5 at K = 4096)."""
+    rng = np.random.default_rng(77)
+    a = random_array(rng, (4096, 256), "complex64")
+    b = random_array(rng, (4096, 192), "complex64")
+    ref = (a.astype(np.complex128).T @ b.astype(np.complex128))
+    got = contract(a, "ki", b, "kj", "ij", path=mb.PATH_TCGEN05_TF32)
+    err = rel_frobenius(got.astype(np.complex128), ref)
+    assert err <= 5e-6, err   # measured 2.4e-6, flat in K thanks to the two-level accumulation
+
+
+def test_tcgen05_auto_selected_for_large_c64():
+    info = mb.plan_describe(_lib.C64, [0, 2, 4, 5, 6], _lib.C64, [0, 1, 2, 3, 6], [256, 8, 8, 256, 8],
+                            _lib.C64, [3, 1, 4, 5, 6], [256, 8, 8, 256, 8])
+    assert info.path == mb.PATH_TCGEN05_TF32
+    # strided operand or first summed extent not a multiple of 8 -> FFMA path
+    info = mb.plan_describe(_lib.C64, [0, 2], _lib.C64, [1, 0], [100, 512], _lib.C64, [1, 2], [100, 512])
+    assert info.path == mb.PATH_SIMT_F32
