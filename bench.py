@@ -35,6 +35,7 @@ CHI, D, W = 1024, 2, 8
 # figure and B200_PROFILING.md states no FP64 fallback; cuBLAS ZGEMM measured on this pool reaches 36.8 TF/s
 # (profiles/peaks_r01.json), so the nominal number is a tight ceiling.
 FP64_TENSOR_PEAK_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12
+TF32_DENSE_PEAK_TFLOPS = 148 * 2048 * 2 * 1.965e9 / 1e12   # 128x256x8 tf32 MMA per 128 clk per SM -> 1191 TFLOP/s nominal
 FP64_PEAK_SOURCE = ("nominal FP64 DMMA peak 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2 TFLOP/s (MEASURED_PEAKS.json has "
                     "no FP64 entry, B200_PROFILING.md no FP64 fallback); cuBLAS ZGEMM 4096^3 measured on this pool: "
                     "36.8 TFLOP/s (profiles/peaks_r01.json)")
@@ -434,10 +435,30 @@ def run_sharded_configs(args, world, rank, local):
 
     ms = timed(step5, 5)
     ms_gemm = timed(lambda: binary_einsum(A5, B5, out=I(ic)), 5)
+    h5 = mb.Handle.get(local).stats()
     out["config5_summed_slice_allreduce"] = {
         "workload": f"rank-8 ComplexF32 dim 8, 4 summed; summed index h sliced {min(world, n)}x, partial C (134 MB) all_reduce(SUM) over NCCL",
         "scaling": "strong", "tflops": flops5 / (ms * 1e-3) / 1e12, "ms": ms, "ms_contraction_only": ms_gemm,
-        "flops": flops5, "allreduce_bytes": 8 * n ** 8 if world > 1 else 0}
+        "flops": flops5, "allreduce_bytes": 8 * n ** 8 if world > 1 else 0,
+        "kernel": "pack x2 (K1 split writer) + tcgen05 3xTF32 GEMM" if h5["launches_tcgen05"] else "FFMA gather-GEMM"}
+    del A5, B5
+    torch.cuda.empty_cache()
+
+    # config 3: PEPS double-layer environment contraction ComplexF32, D=8, chi=256, batch hyperindex beta=8; sharded
+    # over the batch index (no collective)
+    chi, Dd, beta = 256, 8, 8
+    bl = max(1, beta // world) if world <= beta else 1
+    A3 = Tensor(dev_rand([chi, Dd, Dd, chi, bl], "complex64", 3000 + rank), I("lkbmz"))
+    B3 = Tensor(dev_rand([chi, Dd, Dd, chi, bl], "complex64", 3100 + rank), I("mkqrz"))
+    flops3 = 8.0 * float(chi * Dd) ** 3 * (bl * min(world, beta))
+    ms = timed(lambda: binary_einsum(A3, B3, out=I("lbqrz")), 5)
+    tf3 = flops3 / (ms * 1e-3) / 1e12
+    out["config3_peps_batched_c64"] = {
+        "workload": f"PEPS double-layer ComplexF32 D=8 chi=256 beta=8 (2048^3 x 8 GEMM-equivalent), batch index sharded {min(world, beta)}x, no collective",
+        "scaling": "strong", "tflops": tf3, "ms": ms, "flops": flops3,
+        "pct_of_tf32x3_ceiling_per_gpu": 100.0 * tf3 / world / (TF32_DENSE_PEAK_TFLOPS / 3.0),
+        "ceiling_note": "3xTF32 x 4M = 12 tf32 MACs per complex MAC (8 flops): ceiling = TF32 dense peak / 3; "
+                        f"TF32 dense peak taken as nominal {TF32_DENSE_PEAK_TFLOPS:.0f} TFLOP/s (cuBLAS TF32 SGEMM measured 694)"}
     return out
 
 
