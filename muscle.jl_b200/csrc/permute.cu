@@ -18,6 +18,7 @@
 //   * When the tile needs no transposition (no x or no y range) elements go straight from global to
 //     global in one loop, no shared memory.
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 #include "kernels.cuh"
@@ -27,7 +28,8 @@ namespace mb200 {
 namespace {
 
 constexpr int PT_THREADS = 256;
-constexpr int PT_MAX_TAB = 256;   // entries per table (TX, TY <= 256)
+constexpr int PT_MAX_TAB = 128;   // entries per table of the persistent kernel (TX, TY <= 128)
+constexpr int PT_BIG_TAB = 256;   // entries per table of the one-tile-per-CTA kernels (TX, TY <= 256)
 
 struct PermK {
     int n_out;
@@ -79,67 +81,193 @@ __device__ __forceinline__ void put(void *dstv, int64_t off, const E &val, int64
     }
 }
 
-template <typename E, typename S, int PLANAR>
-__global__ void __launch_bounds__(PT_THREADS) permute_kernel(const __grid_constant__ PermK p,
-                                                             const E *__restrict__ src, void *__restrict__ dstv) {
-    __shared__ int64_t sSrcX[PT_MAX_TAB], sDstX[PT_MAX_TAB], sSrcY[PT_MAX_TAB], sDstY[PT_MAX_TAB];
-    extern __shared__ __align__(16) unsigned char tile_raw[];
-    E *tile = reinterpret_cast<E *>(tile_raw);
+// per-tile scalars (uniform across the CTA)
+struct TileCtx {
+    int64_t base_s, base_d;
+    int vt, tx, ty;
+    unsigned x0, y0;
+};
 
-    unsigned b = blockIdx.x;
+__device__ __forceinline__ TileCtx decode_tile(const PermK &p, unsigned b) {
+    TileCtx t;
     const unsigned vc = b % p.v_chunks; b /= p.v_chunks;
     const unsigned xc = b % p.x_chunks; b /= p.x_chunks;
     const unsigned yc = b % p.y_chunks; b /= p.y_chunks;
-    int64_t base_s, base_d;
-    digits_off(b, p.n_out, p.o_ext, p.o_ss, p.o_ds, base_s, base_d);
-    const int VT = 1 << p.lv, TX = 1 << p.lx, TY = 1 << p.ly;
+    digits_off(b, p.n_out, p.o_ext, p.o_ss, p.o_ds, t.base_s, t.base_d);
     const int64_t v0 = (int64_t)vc << p.lv, x0 = (int64_t)xc << p.lx, y0 = (int64_t)yc << p.ly;
-    const int vt = (int)min((int64_t)VT, p.v_ext - v0);
-    const int tx = (int)min((int64_t)TX, p.SX - x0);
-    const int ty = (int)min((int64_t)TY, p.SY - y0);
-    base_s += v0; base_d += v0;  // v has stride 1 on both sides
-    const int tid = threadIdx.x;
+    t.vt = (int)min((int64_t)1 << p.lv, p.v_ext - v0);
+    t.tx = (int)min((int64_t)1 << p.lx, p.SX - x0);
+    t.ty = (int)min((int64_t)1 << p.ly, p.SY - y0);
+    t.base_s += v0; t.base_d += v0;  // v has stride 1 on both sides
+    t.x0 = (unsigned)x0; t.y0 = (unsigned)y0;
+    return t;
+}
 
-    for (int i = tid; i < tx; i += PT_THREADS) {
+template <int N> struct TileTabsT { int64_t srcX[N], dstX[N], srcY[N], dstY[N]; };
+using TileTabs = TileTabsT<PT_MAX_TAB>;
+using TileTabsBig = TileTabsT<PT_BIG_TAB>;
+
+template <class Tabs>
+__device__ __forceinline__ void build_tabs(const PermK &p, const TileCtx &t, Tabs &tab, int tid) {
+    for (int i = tid; i < t.tx; i += PT_THREADS) {
         int64_t so, dof;
-        digits_off((unsigned)(x0 + i), p.nx, p.x_ext, p.x_ss, p.x_ds, so, dof);
-        sSrcX[i] = so; sDstX[i] = dof;
+        digits_off(t.x0 + i, p.nx, p.x_ext, p.x_ss, p.x_ds, so, dof);
+        tab.srcX[i] = so; tab.dstX[i] = dof;
     }
-    for (int i = tid; i < ty; i += PT_THREADS) {
+    for (int i = tid; i < t.ty; i += PT_THREADS) {
         int64_t so, dof;
-        digits_off((unsigned)(y0 + i), p.ny, p.y_ext, p.y_ss, p.y_ds, so, dof);
-        sSrcY[i] = so; sDstY[i] = dof;
+        digits_off(t.y0 + i, p.ny, p.y_ext, p.y_ss, p.y_ds, so, dof);
+        tab.srcY[i] = so; tab.dstY[i] = dof;
+    }
+}
+
+// No transposition needed (no x range or no y range): read order == write order, global -> global.
+template <typename E, typename S, int PLANAR>
+__global__ void __launch_bounds__(PT_THREADS) permute_direct_kernel(const __grid_constant__ PermK p,
+                                                                    const E *__restrict__ src, void *__restrict__ dstv) {
+    __shared__ TileTabsBig tab;
+    const int tid = threadIdx.x;
+    const TileCtx t = decode_tile(p, blockIdx.x);
+    build_tabs(p, t, tab, tid);
+    __syncthreads();
+    const int total = 1 << (p.lv + p.lx + p.ly);
+    const int mv = (1 << p.lv) - 1, mx = (1 << p.lx) - 1;
+#pragma unroll 4
+    for (int idx = tid; idx < total; idx += PT_THREADS) {
+        const int v = idx & mv, x = (idx >> p.lv) & mx, y = idx >> (p.lv + p.lx);
+        if (v < t.vt && x < t.tx && y < t.ty) {
+            E val = src[t.base_s + v + tab.srcX[x] + tab.srcY[y]];
+            put<E, S, PLANAR>(dstv, t.base_d + v + tab.dstX[x] + tab.dstY[y], val, p.plane_stride);
+        }
+    }
+}
+
+// Transposing tile, one tile per CTA (partial tiles, 4-byte and Float64 elements).
+template <typename E, typename S, int PLANAR>
+__global__ void __launch_bounds__(PT_THREADS) permute_simple_kernel(const __grid_constant__ PermK p,
+                                                                    const E *__restrict__ src, void *__restrict__ dstv) {
+    __shared__ TileTabsBig tab;
+    extern __shared__ __align__(16) unsigned char tile_raw[];
+    E *tile = reinterpret_cast<E *>(tile_raw);
+    const int tid = threadIdx.x;
+    const TileCtx t = decode_tile(p, blockIdx.x);
+    build_tabs(p, t, tab, tid);
+    __syncthreads();
+    const int total = 1 << (p.lv + p.lx + p.ly);
+    const int lvx = p.lv + p.lx, mv = (1 << p.lv) - 1, mvx = (1 << lvx) - 1, my = (1 << p.ly) - 1;
+#pragma unroll 4
+    for (int idx = tid; idx < total; idx += PT_THREADS) {   // gather: (v,x) fastest
+        const int vx = idx & mvx, v = idx & mv, x = vx >> p.lv, y = idx >> lvx;
+        if (v < t.vt && x < t.tx && y < t.ty) tile[y * p.pitch + vx] = src[t.base_s + v + tab.srcX[x] + tab.srcY[y]];
     }
     __syncthreads();
-
-    const int total = 1 << (p.lv + p.lx + p.ly);
-    const int mv = VT - 1, mx = TX - 1, my = TY - 1;
-    if (p.direct) {   // read order == write order
 #pragma unroll 4
-        for (int idx = tid; idx < total; idx += PT_THREADS) {
-            const int v = idx & mv, x = (idx >> p.lv) & mx, y = idx >> (p.lv + p.lx);
-            if (v < vt && x < tx && y < ty) {
-                E val = src[base_s + v + sSrcX[x] + sSrcY[y]];
-                put<E, S, PLANAR>(dstv, base_d + v + sDstX[x] + sDstY[y], val, p.plane_stride);
+    for (int idx = tid; idx < total; idx += PT_THREADS) {   // scatter: (v,y) fastest
+        const int v = idx & mv, y = (idx >> p.lv) & my, x = idx >> (p.lv + p.ly);
+        if (v < t.vt && x < t.tx && y < t.ty) {
+            E val = tile[y * p.pitch + (x << p.lv) + v];
+            put<E, S, PLANAR>(dstv, t.base_d + v + tab.dstX[x] + tab.dstY[y], val, p.plane_stride);
+        }
+    }
+}
+
+// Transposing tiles. Persistent CTAs walk tiles blockIdx.x, +gridDim.x, ...; the next tile's elements are
+// already in flight into registers while the current tile is scattered from shared memory (two tile buffers,
+// three table sets, one __syncthreads per tile).
+template <typename E, typename S, int PLANAR, int NE>
+__global__ void __launch_bounds__(PT_THREADS) permute_tiled_kernel(const __grid_constant__ PermK p, unsigned ntiles,
+                                                                   const E *__restrict__ src, void *__restrict__ dstv) {
+    __shared__ TileTabs tabs[3];
+    extern __shared__ __align__(16) unsigned char tile_raw[];
+    E *tile0 = reinterpret_cast<E *>(tile_raw);
+    const int tile_stride = p.pitch << p.ly;   // elements per tile buffer
+    const int tid = threadIdx.x;
+    const int lvx = p.lv + p.lx, mv = (1 << p.lv) - 1, mvx = (1 << lvx) - 1, my = (1 << p.ly) - 1;
+    const int total = 1 << (lvx + p.ly);
+
+    // With power-of-two tile extents and 256 threads, a thread's (v,x) slot on the gather side and its (v,y) slot
+    // on the scatter side do not change from element to element (idx = tid + 256*i): only y (resp. x) advances by a
+    // fixed step. That removes most of the per-element index arithmetic and half of the table reads.
+    const int lvy = p.lv + p.ly;
+    const bool hoist = lvx <= 8 && lvy <= 8;
+    const int g_vx = tid & mvx, g_v = tid & mv, g_x = g_vx >> p.lv, g_y0 = tid >> lvx, g_ystep = PT_THREADS >> lvx;
+    const int s_v = tid & mv, s_y = (tid >> p.lv) & my, s_x0 = tid >> lvy, s_xstep = PT_THREADS >> lvy;
+
+    E regs[NE];
+    auto gather = [&](const TileCtx &t, const TileTabs &tab) {
+        if (hoist) {
+            const bool ok = g_v < t.vt && g_x < t.tx;
+            const E *base = src + (t.base_s + g_v + tab.srcX[g_x]);
+#pragma unroll
+            for (int i = 0; i < NE; i++) {
+                const int y = g_y0 + i * g_ystep;
+                if (ok && y < t.ty) regs[i] = base[tab.srcY[y]];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NE; i++) {
+                const int idx = tid + i * PT_THREADS;
+                const int vx = idx & mvx, v = idx & mv, x = vx >> p.lv, y = idx >> lvx;
+                if (v < t.vt && x < t.tx && y < t.ty) regs[i] = src[t.base_s + v + tab.srcX[x] + tab.srcY[y]];
             }
         }
-        return;
-    }
-    // gather: (v,x) fastest; smem slot = y*pitch + x*VT + v
-#pragma unroll 4
-    for (int idx = tid; idx < total; idx += PT_THREADS) {
-        const int vx = idx & ((1 << (p.lv + p.lx)) - 1), v = idx & mv, x = vx >> p.lv, y = idx >> (p.lv + p.lx);
-        if (v < vt && x < tx && y < ty) tile[y * p.pitch + vx] = src[base_s + v + sSrcX[x] + sSrcY[y]];
-    }
+    };
+
+    unsigned cur_id = blockIdx.x;
+    if (cur_id >= ntiles) return;
+    TileCtx cur = decode_tile(p, cur_id);
+    build_tabs(p, cur, tabs[0], tid);
     __syncthreads();
-    // scatter: (v,y) fastest
-#pragma unroll 4
-    for (int idx = tid; idx < total; idx += PT_THREADS) {
-        const int v = idx & mv, y = (idx >> p.lv) & my, x = idx >> (p.lv + p.ly);
-        if (v < vt && x < tx && y < ty) {
-            E val = tile[y * p.pitch + (x << p.lv) + v];
-            put<E, S, PLANAR>(dstv, base_d + v + sDstX[x] + sDstY[y], val, p.plane_stride);
+    gather(cur, tabs[0]);
+    for (int it = 0;; it++) {
+        E *tile = tile0 + (size_t)(it & 1) * tile_stride;
+        // registers -> smem slot y*pitch + (x*VT + v)   (conflict-free: consecutive lanes, consecutive slots)
+        if (hoist) {
+#pragma unroll
+            for (int i = 0; i < NE; i++) {
+                const int y = g_y0 + i * g_ystep;
+                if (y <= my) tile[y * p.pitch + g_vx] = regs[i];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NE; i++) {
+                const int idx = tid + i * PT_THREADS;
+                if (idx < total) tile[(idx >> lvx) * p.pitch + (idx & mvx)] = regs[i];   // small tiles use fewer slots
+            }
         }
+        const unsigned next_id = cur_id + gridDim.x;
+        const bool has_next = next_id < ntiles;
+        TileCtx nxt = cur;
+        if (has_next) {
+            nxt = decode_tile(p, next_id);
+            build_tabs(p, nxt, tabs[(it + 1) % 3], tid);
+        }
+        __syncthreads();
+        if (has_next) gather(nxt, tabs[(it + 1) % 3]);          // in flight during the scatter below
+        const TileTabs &tab = tabs[it % 3];
+        if (hoist) {                                            // scatter: (v,y) fastest
+            const bool ok = s_v < cur.vt && s_y < cur.ty;
+            const int64_t dbase = cur.base_d + s_v + tab.dstY[s_y];
+            const E *trow = tile + s_y * p.pitch + s_v;
+#pragma unroll
+            for (int i = 0; i < NE; i++) {
+                const int x = s_x0 + i * s_xstep;
+                if (ok && x < cur.tx) put<E, S, PLANAR>(dstv, dbase + tab.dstX[x], trow[x << p.lv], p.plane_stride);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NE; i++) {
+                const int idx = tid + i * PT_THREADS;
+                const int v = idx & mv, y = (idx >> p.lv) & my, x = idx >> (p.lv + p.ly);
+                if (v < cur.vt && x < cur.tx && y < cur.ty) {
+                    E val = tile[y * p.pitch + (x << p.lv) + v];
+                    put<E, S, PLANAR>(dstv, cur.base_d + v + tab.dstX[x] + tab.dstY[y], val, p.plane_stride);
+                }
+            }
+        }
+        if (!has_next) break;
+        cur = nxt;
+        cur_id = next_id;
     }
 }
 
@@ -222,17 +350,35 @@ cudaError_t launch_permute(int dtype, const PermuteParams &q, const void *src, v
     if (SX >= ((int64_t)1 << 31) || SY >= ((int64_t)1 << 31) || outer >= ((int64_t)1 << 31)) return cudaErrorInvalidValue;
     int64_t grid = (int64_t)k.v_chunks * k.x_chunks * k.y_chunks * outer;
     if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    size_t smem = k.direct ? 0 : (size_t)k.pitch * TY * esz;
+    size_t smem = k.direct ? 0 : (size_t)k.pitch * TY * esz;   // one tile buffer
 
     const bool planar = q.plane_stride != 0;
-#define MB200_PERM(E, S, P)                                                                               \
-    do {                                                                                                  \
-        static bool cfg = false;                                                                          \
-        if (!cfg) {                                                                                       \
-            cudaFuncSetAttribute(permute_kernel<E, S, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); \
-            cfg = true;                                                                                   \
-        }                                                                                                 \
-        permute_kernel<E, S, P><<<(unsigned)grid, PT_THREADS, smem, s>>>(k, (const E *)src, dst);         \
+    const unsigned ntiles = (unsigned)grid;
+    // persistent grid for the transposing kernel: 2 CTAs per SM (two 33 KB tile buffers + 3 table sets each)
+    const unsigned pgrid = std::min<unsigned>(ntiles, 148u * 2u);
+    // the persistent kernel takes full-size tiles of 16-byte / ComplexF32 elements; everything else one tile per CTA
+    const bool full_tile = (lv + lx + ly) == ltile && lx <= 7 && ly <= 7;
+#define MB200_PERM(E, S, P)                                                                                   \
+    do {                                                                                                      \
+        constexpr int NE = (int)((32 * 1024 / sizeof(E)) / PT_THREADS);                                       \
+        constexpr bool PERSIST_OK = sizeof(E) == 16 || (sizeof(E) == 8 && (P) != 0) || std::is_same<E, float2>::value; \
+        if (k.direct) {                                                                                       \
+            permute_direct_kernel<E, S, P><<<ntiles, PT_THREADS, 0, s>>>(k, (const E *)src, dst);             \
+        } else if (PERSIST_OK && full_tile) {                                                                 \
+            static bool cfg = false;                                                                          \
+            if (!cfg) {                                                                                       \
+                cudaFuncSetAttribute(permute_tiled_kernel<E, S, P, NE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); \
+                cfg = true;                                                                                   \
+            }                                                                                                 \
+            permute_tiled_kernel<E, S, P, NE><<<pgrid, PT_THREADS, 2 * smem, s>>>(k, ntiles, (const E *)src, dst); \
+        } else {                                                                                              \
+            static bool cfg2 = false;                                                                         \
+            if (!cfg2) {                                                                                      \
+                cudaFuncSetAttribute(permute_simple_kernel<E, S, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); \
+                cfg2 = true;                                                                                  \
+            }                                                                                                 \
+            permute_simple_kernel<E, S, P><<<ntiles, PT_THREADS, smem, s>>>(k, (const E *)src, dst);          \
+        }                                                                                                     \
     } while (0)
     switch (dtype) {
         case MB200_F32: MB200_PERM(float, float, 0); break;
