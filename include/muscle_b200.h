@@ -157,11 +157,36 @@ int mb200_shard_plan(int nmodeC, const int32_t *modesC,
                      int nmodeB, const int32_t *modesB, const int64_t *extentsB,
                      int nranks, int rank, int prefer_sum, mb200_shard_info_t *info);
 
+/* ---- fused contraction + reduce-scatter over peer memory (summed-index slice) ---------------
+ * One process per GPU. Every rank contracts its K-slice; instead of writing a full-size partial C and
+ * all-reducing it (Dagger's treereduce(AddComputeOp), ext/MuscleDaggerExt/binary_einsum.jl:107-115), the GEMM
+ * epilogue stores each output element straight into the staging buffer of the rank that OWNS it
+ * (owner = flat offset in the dense column-major C >> slab_shift), slot `rank`, over NVLink peer mappings.
+ * After a cross-rank barrier every rank sums its nranks slots (mb200_reduce_slots) and holds its slab of C.
+ * staging[r] must point to nranks * (1 << slab_shift) elements on rank r (own buffer for r == rank,
+ * mb200_ipc_import mappings for the others). Supported for the tensor-core paths (ComplexF64 DMMA,
+ * ComplexF32 tcgen05); NOT_SUPPORTED otherwise (use an all-reduce). */
+#define MB200_IPC_HANDLE_BYTES 64
+#define MB200_MAX_PEERS 8
+int mb200_ipc_export(mb200_handle_t handle, void *dptr, unsigned char *handle_out /* 64 bytes */);
+int mb200_ipc_import(mb200_handle_t handle, const unsigned char *handle_in /* 64 bytes */, void **peer_ptr);
+int mb200_ipc_release(mb200_handle_t handle, void *peer_ptr);
+int mb200_binary_einsum_scatter(mb200_handle_t handle,
+                                int dtypeC, int nmodeC, const int32_t *modesC,
+                                const void *A, int dtypeA, int nmodeA, const int32_t *modesA,
+                                const int64_t *extentsA, const int64_t *stridesA,
+                                const void *B, int dtypeB, int nmodeB, const int32_t *modesB,
+                                const int64_t *extentsB, const int64_t *stridesB,
+                                void *const *staging, int nranks, int rank, int slab_shift);
+/* out[e] = sum over s < nslots of staging_local[s * slab_elems + e]   (e < slab_elems) */
+int mb200_reduce_slots(mb200_handle_t handle, void *out, const void *staging_local, int dtype,
+                       int64_t slab_elems, int nslots);
+
 /* ---- counters (bench.py's gpu_launches claim) ----------------------------------------------- */
 typedef struct {
     uint64_t launches_total;
     uint64_t launches_direct, launches_gett_f64, launches_simt_f32, launches_tcgen05;
-    uint64_t launches_permute, launches_table, launches_convert;
+    uint64_t launches_permute, launches_table, launches_convert, launches_reduce;
     uint64_t plans_built, plans_hit;
 } mb200_stats_t;
 int mb200_get_stats(mb200_handle_t handle, mb200_stats_t *stats);

@@ -63,7 +63,7 @@ class ShardInfo(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "launches_total", "launches_direct", "launches_gett_f64", "launches_simt_f32", "launches_tcgen05",
-        "launches_permute", "launches_table", "launches_convert", "plans_built", "plans_hit")]
+        "launches_permute", "launches_table", "launches_convert", "launches_reduce", "plans_built", "plans_hit")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -103,6 +103,15 @@ PROTOTYPES = {
     "mb200_permute": ([_vp, _vp, _vp, _i, _i, _i64p, _i32p, C.c_uint32], C.c_int),
     "mb200_shard_plan": ([_i, _i32p, _i, _i32p, _i64p, _i, _i32p, _i64p, _i, _i, _i,
                           C.POINTER(ShardInfo)], C.c_int),
+    "mb200_ipc_export": ([_vp, _vp, C.c_char_p], C.c_int),
+    "mb200_ipc_import": ([_vp, C.c_char_p, C.POINTER(_vp)], C.c_int),
+    "mb200_ipc_release": ([_vp, _vp], C.c_int),
+    "mb200_binary_einsum_scatter": ([_vp,
+                                     _i, _i, _i32p,
+                                     _vp, _i, _i, _i32p, _i64p, _i64p,
+                                     _vp, _i, _i, _i32p, _i64p, _i64p,
+                                     C.POINTER(_vp), _i, _i, _i], C.c_int),
+    "mb200_reduce_slots": ([_vp, _vp, _vp, _i, C.c_int64, _i], C.c_int),
     "mb200_get_stats": ([_vp, C.POINTER(Stats)], C.c_int),
     "mb200_reset_stats": ([_vp], C.c_int),
 }

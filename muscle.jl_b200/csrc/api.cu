@@ -199,13 +199,23 @@ int64_t span_of(const TensorDesc &t) {
 }
 
 int contract_device(mb200_handle_t h, void *C, TensorDesc &dC, const int64_t *stridesC, const void *A,
-                    const TensorDesc &dA, const void *B, const TensorDesc &dB) {
+                    const TensorDesc &dA, const void *B, const TensorDesc &dB, const ScatterDesc *sc = nullptr) {
     Plan plan;
     int st = make_plan(dA, dB, dC, stridesC, h->forced_path, plan);
     if (st != MB200_OK) return st;
     if (plan.empty_output) return MB200_OK;
-    if (!C || (!A && dA.numel() > 0) || (!B && dB.numel() > 0))
+    if ((!C && !sc) || (!A && dA.numel() > 0) || (!B && dB.numel() > 0))
         return fail(MB200_INVALID_ARGUMENT, "NULL data pointer");
+    if (sc) {
+        const bool tensor_path = (plan.path == MB200_PATH_GETT_F64 && plan.dtype == MB200_C128) ||
+                                 (plan.path == MB200_PATH_TCGEN05_TF32 && tf32_available());
+        if (!tensor_path)
+            return fail(MB200_NOT_SUPPORTED, "fused reduce-scatter needs the ComplexF64 DMMA or ComplexF32 tcgen05 path "
+                                             "(this contraction is planned on path %d); use an all-reduce", plan.path);
+        if (dC.numel() != ((int64_t)sc->nranks << sc->shift))
+            return fail(MB200_INVALID_ARGUMENT, "C has %lld elements, expected nranks << slab_shift = %lld",
+                        (long long)dC.numel(), (long long)((int64_t)sc->nranks << sc->shift));
+    }
     MB200_CUDA(cudaSetDevice(h->device));
 
     CachedPlan *cp;
@@ -275,6 +285,7 @@ int contract_device(mb200_handle_t h, void *C, TensorDesc &dC, const int64_t *st
         if (e == cudaSuccess) {
             GettParams g = cp->gp;
             g.C = C;
+            if (sc) g.sc = *sc;
             e = launch_tf32_gemm(pa, pb, g, s);
             h->stats.launches_tcgen05++;
         }
@@ -283,6 +294,7 @@ int contract_device(mb200_handle_t h, void *C, TensorDesc &dC, const int64_t *st
     } else {
         GettParams g = cp->gp;
         g.A = R; g.B = Q; g.C = C;
+        if (sc) g.sc = *sc;
         if (dtype_is_double(p.dtype)) {
             e = launch_gett_f64(p.dtype, g, s);
             h->stats.launches_gett_f64++;
@@ -605,6 +617,69 @@ int mb200_shard_plan(int nmodeC, const int32_t *modesC, int nmodeA, const int32_
         }
     }
     return MB200_OK;  // replicas only
+}
+
+int mb200_ipc_export(mb200_handle_t h, void *dptr, unsigned char *handle_out) {
+    MB200_CHECK_HANDLE(h);
+    if (!dptr || !handle_out) return fail(MB200_INVALID_ARGUMENT, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == MB200_IPC_HANDLE_BYTES, "IPC handle size");
+    MB200_CUDA(cudaSetDevice(h->device));
+    cudaIpcMemHandle_t ih;
+    MB200_CUDA(cudaIpcGetMemHandle(&ih, dptr));
+    std::memcpy(handle_out, &ih, sizeof ih);
+    return MB200_OK;
+}
+
+int mb200_ipc_import(mb200_handle_t h, const unsigned char *handle_in, void **peer_ptr) {
+    MB200_CHECK_HANDLE(h);
+    if (!handle_in || !peer_ptr) return fail(MB200_INVALID_ARGUMENT, "NULL argument");
+    MB200_CUDA(cudaSetDevice(h->device));
+    cudaIpcMemHandle_t ih;
+    std::memcpy(&ih, handle_in, sizeof ih);
+    MB200_CUDA(cudaIpcOpenMemHandle(peer_ptr, ih, cudaIpcMemLazyEnablePeerAccess));
+    return MB200_OK;
+}
+
+int mb200_ipc_release(mb200_handle_t h, void *peer_ptr) {
+    MB200_CHECK_HANDLE(h);
+    MB200_CUDA(cudaSetDevice(h->device));
+    MB200_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+    return MB200_OK;
+}
+
+int mb200_binary_einsum_scatter(mb200_handle_t h, int dtypeC, int nmodeC, const int32_t *modesC, const void *A,
+                                int dtypeA, int nmodeA, const int32_t *modesA, const int64_t *extentsA,
+                                const int64_t *stridesA, const void *B, int dtypeB, int nmodeB, const int32_t *modesB,
+                                const int64_t *extentsB, const int64_t *stridesB, void *const *staging, int nranks,
+                                int rank, int slab_shift) {
+    MB200_CHECK_HANDLE(h);
+    if (!staging || nranks < 1 || nranks > MB200_MAX_PEERS || rank < 0 || rank >= nranks || slab_shift < 0 || slab_shift > 40)
+        return fail(MB200_INVALID_ARGUMENT, "bad staging / nranks %d / rank %d / slab_shift %d", nranks, rank, slab_shift);
+    ScatterDesc sc{};
+    for (int r = 0; r < nranks; r++) {
+        if (!staging[r]) return fail(MB200_INVALID_ARGUMENT, "staging[%d] is NULL", r);
+        sc.peer[r] = staging[r];
+    }
+    sc.nranks = nranks; sc.rank = rank; sc.shift = slab_shift;
+    TensorDesc dA, dB, dC;
+    int st;
+    if ((st = make_desc(dA, dtypeA, nmodeA, modesA, extentsA, stridesA, "A")) != MB200_OK) return st;
+    if ((st = make_desc(dB, dtypeB, nmodeB, modesB, extentsB, stridesB, "B")) != MB200_OK) return st;
+    if ((st = make_c_desc(dC, dtypeC, nmodeC, modesC)) != MB200_OK) return st;
+    std::lock_guard<std::mutex> lk(h->mu);
+    return contract_device(h, nullptr, dC, nullptr, A, dA, B, dB, &sc);
+}
+
+int mb200_reduce_slots(mb200_handle_t h, void *out, const void *staging_local, int dtype, int64_t slab_elems, int nslots) {
+    MB200_CHECK_HANDLE(h);
+    if (!dtype_valid(dtype) || !out || !staging_local || slab_elems < 0 || nslots < 1)
+        return fail(MB200_INVALID_ARGUMENT, "bad arguments to mb200_reduce_slots");
+    std::lock_guard<std::mutex> lk(h->mu);
+    MB200_CUDA(cudaSetDevice(h->device));
+    MB200_CUDA(launch_reduce_slots(dtype, out, staging_local, slab_elems, nslots, h->stream));
+    h->stats.launches_reduce++;
+    h->stats.launches_total++;
+    return MB200_OK;
 }
 
 int mb200_get_stats(mb200_handle_t h, mb200_stats_t *stats) {

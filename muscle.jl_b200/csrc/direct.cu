@@ -101,6 +101,20 @@ __global__ void __launch_bounds__(256) convert_kernel(TD *__restrict__ dst, cons
         dst[i] = conv<TD, TS>(src[i]);
 }
 
+// out[i] = sum_s in[s * n + i] over plain reals (a sum does not care about re/im interleaving)
+template <typename T>
+__global__ void __launch_bounds__(256) reduce_slots_kernel(T *__restrict__ out, const T *__restrict__ in, int64_t n, int nslots) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        T acc = in[i];
+        for (int s = 1; s < nslots; s++) {
+            T v = in[(int64_t)s * n + i];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        out[i] = acc;
+    }
+}
+
 inline int grid_for(int64_t n, int threads, int cap = 148 * 16) {
     int64_t g = (n + threads - 1) / threads;
     if (g < 1) g = 1;
@@ -124,6 +138,20 @@ cudaError_t launch_direct(int dtype, const DirectParams &p, const void *A, const
         case MB200_F64: direct_kernel<double><<<g, 256, 0, s>>>(p, (const double *)A, (const double *)B, (double *)C); break;
         case MB200_C64: direct_kernel<float2><<<g, 256, 0, s>>>(p, (const float2 *)A, (const float2 *)B, (float2 *)C); break;
         default: direct_kernel<double2><<<g, 256, 0, s>>>(p, (const double2 *)A, (const double2 *)B, (double2 *)C); break;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_reduce_slots(int dtype, void *out, const void *staging, int64_t slab_elems, int nslots, cudaStream_t s) {
+    const int64_t bytes = slab_elems * (int64_t)dtype_size(dtype);
+    if (bytes <= 0) return cudaSuccess;
+    if (bytes % 32 != 0) return cudaErrorInvalidValue;
+    if (dtype_is_double(dtype)) {
+        const int64_t n = bytes / 32;   // double4
+        reduce_slots_kernel<double4><<<grid_for(n, 256), 256, 0, s>>>((double4 *)out, (const double4 *)staging, n, nslots);
+    } else {
+        const int64_t n = bytes / 16;   // float4
+        reduce_slots_kernel<float4><<<grid_for(n, 256), 256, 0, s>>>((float4 *)out, (const float4 *)staging, n, nslots);
     }
     return cudaGetLastError();
 }

@@ -117,7 +117,7 @@ struct CoreZ {
         }
     }
     __device__ static void store(const Acc &acc, Elem *C, const int64_t *sRowC, const int64_t *sColC,
-                                 int64_t cb, int mrem, int nrem, int warp, int lane) {
+                                 int64_t cb, int mrem, int nrem, int warp, int lane, const ScatterDesc &sc) {
         const int wm = (warp % (BM / WM)) * WM, wn = (warp / (BM / WM)) * WN;
         const int fr = lane >> 2, fc = (lane & 3) * 2;
 #pragma unroll
@@ -130,9 +130,10 @@ struct CoreZ {
 #pragma unroll
                 for (int i = 0; i < MT; i++) {
                     int r = wm + i * 8 + fr;
-                    if (r < mrem) C[sRowC[r] + co] = make_double2(acc.re[i][j][h], acc.im[i][j][h]);
+                    if (r < mrem) *scatter_ptr(sc, C, sRowC[r] + co) = make_double2(acc.re[i][j][h], acc.im[i][j][h]);
                 }
             }
+        if (sc.nranks) __threadfence_system();   // peer stores must be visible before the cross-rank barrier
     }
 };
 
@@ -173,7 +174,7 @@ struct CoreD {
         }
     }
     __device__ static void store(const Acc &acc, Elem *C, const int64_t *sRowC, const int64_t *sColC,
-                                 int64_t cb, int mrem, int nrem, int warp, int lane) {
+                                 int64_t cb, int mrem, int nrem, int warp, int lane, const ScatterDesc &) {
         const int wm = (warp % (BM / WM)) * WM, wn = (warp / (BM / WM)) * WN;
         const int fr = lane >> 2, fc = (lane & 3) * 2;
 #pragma unroll
@@ -237,7 +238,7 @@ struct CoreF {
         }
     }
     __device__ static void store(const Acc &acc, Elem *C, const int64_t *sRowC, const int64_t *sColC,
-                                 int64_t cb, int mrem, int nrem, int warp, int lane) {
+                                 int64_t cb, int mrem, int nrem, int warp, int lane, const ScatterDesc &) {
         const int tid = warp * 32 + lane, tx = tid & 15, ty = tid >> 4;
 #pragma unroll
         for (int j = 0; j < TN; j++) {
@@ -385,7 +386,7 @@ __global__ void __launch_bounds__(Core::NTHREADS, 1) gett_kernel(const __grid_co
         });
     }
     cp_async_wait<0>();
-    Core::store(acc, reinterpret_cast<E *>(p.C), sRowC, sColC, cb, mrem, nrem, warp, lane);
+    Core::store(acc, reinterpret_cast<E *>(p.C), sRowC, sColC, cb, mrem, nrem, warp, lane, p.sc);
 }
 
 template <class Core>

@@ -31,9 +31,23 @@ cudaError_t launch_direct(int dtype, const DirectParams &p, const void *A, const
 // ---- K2 / FP32 SIMT: gather-GEMM ---------------------------------------------------------------------
 // C[rowC[m] + colC[n] + batC[l]] = sum_k A[rowA[m] + kA[k] + batA[l]] * B[colB[n] + kB[k] + batB[l]]
 // All offsets are in ELEMENTS of the compute dtype.
+// Epilogue redirection for the fused reduce-scatter: element at flat offset e of C goes to
+// peer[e >> shift] + (rank << shift) + (e & mask). nranks == 0: plain store to C.
+struct ScatterDesc {
+    void *peer[MB200_MAX_PEERS];
+    int nranks, rank, shift;
+};
+template <typename E>
+__device__ __forceinline__ E *scatter_ptr(const ScatterDesc &sc, E *C, int64_t off) {
+    if (sc.nranks == 0) return C + off;
+    const int owner = (int)(off >> sc.shift);
+    return reinterpret_cast<E *>(sc.peer[owner]) + (((int64_t)sc.rank << sc.shift) + (off & (((int64_t)1 << sc.shift) - 1)));
+}
+
 struct GettParams {
     const void *A, *B;
     void *C;
+    ScatterDesc sc;
     const int64_t *rowA, *kA, *batA;
     const int64_t *colB, *kB, *batB;
     const int64_t *rowC, *colC, *batC;
@@ -43,6 +57,8 @@ struct GettParams {
 cudaError_t launch_gett_f64(int dtype, const GettParams &p, cudaStream_t s);   // F64 / C128, DMMA
 cudaError_t launch_simt_f32(int dtype, const GettParams &p, cudaStream_t s);   // F32 / C64, FFMA
 cudaError_t gett_configure();  // opt-in shared memory attributes; call once per device
+
+cudaError_t launch_reduce_slots(int dtype, void *out, const void *staging, int64_t slab_elems, int nslots, cudaStream_t s);
 
 // ---- dtype promotion (mixed-eltype operands) -------------------------------------------------------
 cudaError_t launch_convert(int dtype_dst, void *dst, int dtype_src, const void *src, int64_t n,

@@ -159,6 +159,16 @@ int make_plan(const TensorDesc &A, const TensorDesc &B, TensorDesc &C, const int
     if (plan.b_kmajor && !plan.a_kmajor) std::stable_sort(plan.sum.begin(), plan.sum.end(), by_sb);
     else std::stable_sort(plan.sum.begin(), plan.sum.end(), by_sa);
 
+    // ComplexF32: the tcgen05 operand format needs the fastest summed mode to be a multiple of 8 (one 8-k group =
+    // one 128 B TMA row). Any common order of the summed modes is valid, so rotate a suitable mode to the front.
+    if (plan.dtype == MB200_C64 && !plan.sum.empty() && plan.sum[0].extent % 8 != 0) {
+        for (size_t i = 1; i < plan.sum.size(); i++)
+            if (plan.sum[i].extent % 8 == 0) {
+                std::rotate(plan.sum.begin(), plan.sum.begin() + i, plan.sum.begin() + i + 1);
+                break;
+            }
+    }
+
     auto prod = [](const std::vector<GroupMode> &g) {
         int64_t p = 1;
         for (auto &x : g) p *= x.extent;

@@ -117,6 +117,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool neg_a) {
 }
 
 struct Tf32Params {
+    ScatterDesc sc;
     float2 *C;
     const int64_t *rowC, *colC, *batC;
     int64_t M, N, L;
@@ -264,9 +265,10 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
             for (int j = 0; j < HALF; j++) {
                 const int cidx = half * HALF + j;
-                if (n0 + cidx < p.N) p.C[crow + sColC[cidx]] = make_float2(accr[j], acci[j]);
+                if (n0 + cidx < p.N) *scatter_ptr(p.sc, p.C, crow + sColC[cidx]) = make_float2(accr[j], acci[j]);
             }
         }
+        if (p.sc.nranks) __threadfence_system();   // peer stores must be visible before the cross-rank barrier
     }
     tc_fence_before();
     __syncthreads();
@@ -311,6 +313,7 @@ cudaError_t launch_bn(const void *packA, const void *packB, const GettParams &g,
     if (!make_map(&mapA, packA, g.K, g.M, g.L, TBM) || !make_map(&mapB, packB, g.K, g.N, g.L, BN))
         return cudaErrorInvalidValue;
     Tf32Params p{};
+    p.sc = g.sc;
     p.C = reinterpret_cast<float2 *>(g.C);
     p.rowC = g.rowC; p.colC = g.colC; p.batC = g.batC;
     p.M = g.M; p.N = g.N; p.L = g.L;

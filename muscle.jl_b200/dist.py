@@ -118,3 +118,107 @@ def all_gather_along(c: Tensor, index, group=None) -> Tensor:
     dist.all_gather_object(parts, host.data, group=group)
     full = np.concatenate(parts, axis=host.dim(index))
     return Tensor(_lib.fortran(full), host.inds)
+
+
+# ---- fused contraction + reduce-scatter over peer memory (summed-index slice) -------------------------------
+class _PeerStaging:
+    """Two symmetric staging buffers per rank (cudaMalloc'd, exported through CUDA IPC) and the peer mappings of
+    every other rank's buffers. Buffers alternate between calls so a fast rank can never overwrite slots an owner
+    is still reducing (the next call's barrier orders them)."""
+
+    def __init__(self, device, nbytes, group):
+        import ctypes as C
+        import torch.distributed as dist
+        self.handle = _lib.Handle.get(device)
+        L = _lib.lib()
+        self.nranks = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.own, exported = [], []
+        for _ in range(2):
+            p = C.c_void_p()
+            _lib.check(L.mb200_malloc(self.handle.ptr, C.byref(p), nbytes))
+            self.own.append(int(p.value))
+            buf = C.create_string_buffer(64)
+            if self.nranks > 1:
+                _lib.check(L.mb200_ipc_export(self.handle.ptr, p, buf))
+            exported.append(buf.raw)
+        gathered = [exported]
+        if self.nranks > 1:
+            gathered = [None] * self.nranks
+            dist.all_gather_object(gathered, exported, group=group)
+        self.peers = []
+        for b in range(2):
+            ptrs = []
+            for r in range(self.nranks):
+                if r == self.rank:
+                    ptrs.append(self.own[b])
+                else:
+                    q = C.c_void_p()
+                    _lib.check(L.mb200_ipc_import(self.handle.ptr, gathered[r][b], C.byref(q)))
+                    ptrs.append(int(q.value))
+            self.peers.append(ptrs)
+        self.turn = 0
+
+
+_STAGING: dict = {}
+
+
+def sum_slice_reduce_scatter(a_loc: Tensor, b_loc: Tensor, inds_c, group=None) -> Tensor:
+    """Summed-index slice with the reduction fused into the GEMM epilogue: this rank contracts its K-slice and
+    the epilogue stores every output element into the owner rank's staging slot over NVLink peer memory
+    (mb200_binary_einsum_scatter); after a stream-ordered cross-rank barrier each rank sums its slots
+    (mb200_reduce_slots). Returns this rank's slab of C — the flat column-major range
+    [rank*slab, (rank+1)*slab), i.e. reduce-scatter semantics (C stays sharded).
+    Raises ArgumentError when the contraction is not on a tensor-core path or C does not split into
+    power-of-two slabs; callers then use `all_reduce_sum`."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+
+    inds_c = _as_index_list(inds_c)
+    if not (a_loc.on_device and b_loc.on_device):
+        raise _lib.ArgumentError("sum_slice_reduce_scatter needs device-resident slices")
+    nranks = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    ma, mb, mc = flatten_labels(a_loc.inds, b_loc.inds, inds_c)
+    T = np.result_type(a_loc.dtype, b_loc.dtype)
+    ext = {}
+    for t in (a_loc, b_loc):
+        for i, e in zip(t.inds, t.shape):
+            ext[i] = e
+    shape_c = tuple(ext[i] for i in inds_c)
+    numel = int(np.prod(shape_c, dtype=np.int64)) if shape_c else 1
+    slab = numel // nranks
+    if nranks > _MAX_PEERS or slab * nranks != numel or slab & (slab - 1) or slab == 0:
+        raise _lib.ArgumentError("C does not split into power-of-two slabs over the ranks")
+    dev = a_loc.data.device
+    nbytes = numel * T.itemsize
+    key = (dev, nranks, nbytes, id(group))
+    st = _STAGING.get(key)
+    if st is None:
+        st = _STAGING[key] = _PeerStaging(dev, nbytes, group)
+    b = st.turn
+    st.turn ^= 1
+    h = _lib.Handle.get(dev)
+    L = _lib.lib()
+    arr = (C.c_void_p * nranks)(*st.peers[b])
+    _lib.check(L.mb200_binary_einsum_scatter(
+        h.ptr, _lib.dtype_enum(T), len(mc), _lib.i32(mc),
+        C.c_void_p(a_loc.data.ptr), _lib.dtype_enum(a_loc.dtype), len(ma), _lib.i32(ma), _lib.i64(a_loc.shape), None,
+        C.c_void_p(b_loc.data.ptr), _lib.dtype_enum(b_loc.dtype), len(mb), _lib.i32(mb), _lib.i64(b_loc.shape), None,
+        arr, nranks, rank, slab.bit_length() - 1))
+    if nranks > 1:
+        # stream-ordered cross-rank barrier: every rank's GEMM (and its peer stores) precedes its all_reduce
+        flag = torch.zeros(1, device=f"cuda:{dev}")
+        dist.all_reduce(flag, group=group)
+    # slab as an array: split C's slowest mode when it divides evenly, else a flat vector
+    shaped = bool(shape_c) and shape_c[-1] % nranks == 0
+    out = B200Array(shape_c[:-1] + (shape_c[-1] // nranks,) if shaped else (slab,), T, dev)
+    _lib.check(L.mb200_reduce_slots(h.ptr, C.c_void_p(out.ptr), C.c_void_p(st.own[b]), _lib.dtype_enum(T), slab, nranks))
+    if shaped:
+        return Tensor(out, inds_c)
+    from .tensor import Index
+    return Tensor(out, [Index(("flat", tuple(i.tag for i in inds_c)))])
+
+
+_MAX_PEERS = 8

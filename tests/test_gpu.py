@@ -389,3 +389,54 @@ def test_tcgen05_auto_selected_for_large_c64():
     # strided operand or first summed extent not a multiple of 8 -> FFMA path
     info = mb.plan_describe(_lib.C64, [0, 2], _lib.C64, [1, 0], [100, 512], _lib.C64, [1, 2], [100, 512])
     assert info.path == mb.PATH_SIMT_F32
+
+
+# ---- fused contraction + reduce-scatter epilogue (single GPU: the "peers" are local buffers) -----------------
+@pytest.mark.parametrize("dt,path,tol", [("complex128", "gett", 1e-12), ("complex64", "tcgen05", 1e-5)])
+def test_fused_scatter_epilogue_and_slot_reduce(dt, path, tol):
+    """mb200_binary_einsum_scatter + mb200_reduce_slots with 4 emulated ranks on one GPU: every rank contracts its
+    K-slice, the epilogue routes each element to the owner's staging slot, the owners sum their slots. The union
+    of the slabs must equal the unsliced contraction (what all_reduce(SUM) of the partials would give)."""
+    nranks, Mx, Nx, Kx = 4, 256, 128, 1024
+    rng = np.random.default_rng(17)
+    a = random_array(rng, (Kx, Mx), dt)          # [k, i]
+    b = random_array(rng, (Kx, Nx), dt)          # [k, j]
+    ref = a.T @ b                                 # C[i, j]
+    numel = Mx * Nx
+    slab = numel // nranks
+    assert slab & (slab - 1) == 0
+    h = _lib.Handle.get()
+    h.set_path(mb.PATH_TCGEN05_TF32 if path == "tcgen05" else mb.PATH_AUTO)
+    L = mb.lib()
+    staging = [B200Array((nranks * slab,), dt) for _ in range(nranks)]
+    for s in staging:
+        _lib.check(L.mb200_memset(h.ptr, C.c_void_p(s.ptr), 0xFF, s.nbytes))   # NaN-fill: every slot must be written
+    arr = (C.c_void_p * nranks)(*[s.ptr for s in staging])
+    kc = Kx // nranks
+    h.reset_stats()
+    for r in range(nranks):
+        da = B200Array.from_host(a[r * kc:(r + 1) * kc, :])
+        db = B200Array.from_host(b[r * kc:(r + 1) * kc, :])
+        _lib.check(L.mb200_binary_einsum_scatter(
+            h.ptr, _lib.dtype_enum(dt), 2, _lib.i32([1, 2]),
+            C.c_void_p(da.ptr), _lib.dtype_enum(dt), 2, _lib.i32([0, 1]), _lib.i64(da.shape), None,
+            C.c_void_p(db.ptr), _lib.dtype_enum(dt), 2, _lib.i32([0, 2]), _lib.i64(db.shape), None,
+            arr, nranks, r, slab.bit_length() - 1))
+    st = h.stats()
+    assert (st["launches_tcgen05"] if path == "tcgen05" else st["launches_gett_f64"]) == nranks, st
+    out = np.empty(numel, dtype=dt)
+    for o in range(nranks):
+        d = B200Array((slab,), dt)
+        _lib.check(L.mb200_reduce_slots(h.ptr, C.c_void_p(d.ptr), C.c_void_p(staging[o].ptr), _lib.dtype_enum(dt), slab, nranks))
+        out[o * slab:(o + 1) * slab] = d.to_host()
+    got = out.reshape((Mx, Nx), order="F")
+    assert rel_frobenius(got, ref.astype(dt)) <= tol
+    # a contraction that is not on a tensor-core path is refused (callers fall back to all_reduce)
+    h.set_path(mb.PATH_AUTO)
+    tiny_a, tiny_b = B200Array.from_host(a[:8, :16].copy(order="F")), B200Array.from_host(b[:8, :16].copy(order="F"))
+    with pytest.raises(mb.ArgumentError):
+        _lib.check(L.mb200_binary_einsum_scatter(
+            h.ptr, _lib.dtype_enum(dt), 2, _lib.i32([1, 2]),
+            C.c_void_p(tiny_a.ptr), _lib.dtype_enum(dt), 2, _lib.i32([0, 1]), _lib.i64((8, 16)), None,
+            C.c_void_p(tiny_b.ptr), _lib.dtype_enum(dt), 2, _lib.i32([0, 2]), _lib.i64((8, 16)), None,
+            arr, nranks, 0, 6))
