@@ -77,7 +77,6 @@ struct CoreZ {
             for (int j = 0; j < NT; j++) a.re[i][j][0] = a.re[i][j][1] = a.im[i][j][0] = a.im[i][j][1] = 0.0;
     }
     static constexpr int SLOTS = (BK / 4) * 4;  // hook calls per k-block
-    static constexpr bool ZFILL = false;
     template <class Hook>
     __device__ static void compute(Acc &acc, const Elem *sa, const Elem *sb, int warp, int lane, Hook &&hook) {
         const int wm = (warp % (BM / WM)) * WM, wn = (warp / (BM / WM)) * WN;
@@ -153,7 +152,6 @@ struct CoreD {
             for (int j = 0; j < NT; j++) a.c[i][j][0] = a.c[i][j][1] = 0.0;
     }
     static constexpr int SLOTS = (BK / 4) * MT;
-    static constexpr bool ZFILL = true;
     template <class Hook>
     __device__ static void compute(Acc &acc, const Elem *sa, const Elem *sb, int warp, int lane, Hook &&hook) {
         const int wm = (warp % (BM / WM)) * WM, wn = (warp / (BM / WM)) * WN;
@@ -219,7 +217,6 @@ struct CoreF {
             for (int j = 0; j < TN; j++) zero(a.c[i][j]);
     }
     static constexpr int SLOTS = BK;
-    static constexpr bool ZFILL = true;
     template <class Hook>
     __device__ static void compute(Acc &acc, const Elem *sa, const Elem *sb, int warp, int lane, Hook &&hook) {
         const int tid = warp * 32 + lane, tx = tid & 15, ty = tid >> 4;
@@ -258,7 +255,7 @@ struct CoreF {
 template <class Core>
 constexpr size_t gett_smem_bytes() {
     return (size_t)Core::STAGES * Core::BK * (Core::LDA + Core::LDB) * sizeof(typename Core::Elem) +
-           (size_t)(Core::BM + Core::BN) * 2 * sizeof(int64_t);
+           (size_t)(Core::BM + Core::BN) * 2 * sizeof(int64_t) + (size_t)4 * Core::BK * sizeof(int64_t);
 }
 
 // Tile order: groups of GROUP_M row tiles, walked column by column inside a group, so the CTAs of a
@@ -277,6 +274,7 @@ __global__ void __launch_bounds__(Core::NTHREADS, 1) gett_kernel(const __grid_co
     int64_t *sColB = sRowA + BM;
     int64_t *sRowC = sColB + BN;
     int64_t *sColC = sRowC + BM;
+    int64_t *sK = sColC + BN;   // [2][2][BK]: k-offsets of A and B for the k-block whose gather is issued next
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
@@ -311,68 +309,83 @@ __global__ void __launch_bounds__(Core::NTHREADS, 1) gett_kernel(const __grid_co
     const E *gB = reinterpret_cast<const E *>(p.B) + bb;
     const int64_t KB = (p.K + BK - 1) / BK;
 
-    // One "unit" = one element-granular cp.async. Units [0, UA) belong to A, [UA, UA+UB) to B. A unit's
-    // (row, k) assignment is fixed per thread; rows past the tile edge are simply not loaded (their
-    // accumulators are never stored), the K tail is zero-filled with plain stores.
+    // One "unit" = one element-granular cp.async. Units [0, UA) belong to A, [UA, UA+UB) to B. A unit's (row, k)
+    // assignment is fixed per thread, so its global row pointer and smem slot are hoisted out of the k loop; the
+    // only per-k-block input is the k-offset, read from shared memory (staged one block ahead, pre-scaled to
+    // bytes, -1 = past the end of K). Invalid elements are zero-filled by the cp.async itself: no branches.
     constexpr int UA = (BM * BK + NT - 1) / NT, UB = (BN * BK + NT - 1) / NT, UNITS = UA + UB;
-    auto issue_unit = [&](int stage, int64_t kbase, int u, bool more) {
+    const char *u_ptr[UNITS];   // global row base (bytes); nullptr = row outside the tile / unit unused
+    int u_dst[UNITS];           // smem byte offset inside a stage (A and B share one stage block)
+    int u_k[UNITS];             // index into the staged k-offsets: k for A, BK + k for B
+    constexpr int STAGE_A = BK * LDA * (int)sizeof(E), STAGE_B = BK * LDB * (int)sizeof(E);
+#pragma unroll
+    for (int u = 0; u < UNITS; u++) {
         if (u < UA) {
             const int i = tid + u * NT;
             int m, k;
             if (p.a_kmajor) { k = i % BK; m = i / BK; } else { m = i % BM; k = i / BM; }
-            if ((BM * BK) % NT != 0 && i >= BM * BK) return;
-            E *dst = sA + (size_t)stage * BK * LDA + k * LDA + m;
-            if constexpr (Core::ZFILL) {   // branch-free: keeps the FFMA / real-DMMA loops in one basic block
-                const bool v = more && (m < mrem) && (kbase + k < p.K);
-                const int64_t off = v ? (sRowA[m] + p.kA[kbase + k]) : 0;
-                cp_async_zfill<(int)sizeof(E)>(dst, gA + off, v);
-            } else {
-                if (!more) return;
-                if (kbase + k < p.K) {
-                    if (m < mrem) cp_async<(int)sizeof(E)>(dst, gA + (sRowA[m] + p.kA[kbase + k]));
-                } else {
-                    *dst = E{};
-                }
-            }
+            const bool ok = i < BM * BK && m < mrem;
+            u_ptr[u] = ok ? reinterpret_cast<const char *>(gA + sRowA[m]) : nullptr;
+            u_dst[u] = (i < BM * BK) ? (k * LDA + m) * (int)sizeof(E) : -1;
+            u_k[u] = k;
         } else {
             const int i = tid + (u - UA) * NT;
             int n, k;
             if (p.b_kmajor) { k = i % BK; n = i / BK; } else { n = i % BN; k = i / BN; }
-            if ((BN * BK) % NT != 0 && i >= BN * BK) return;
-            E *dst = sB + (size_t)stage * BK * LDB + k * LDB + n;
-            if constexpr (Core::ZFILL) {
-                const bool v = more && (n < nrem) && (kbase + k < p.K);
-                const int64_t off = v ? (sColB[n] + p.kB[kbase + k]) : 0;
-                cp_async_zfill<(int)sizeof(E)>(dst, gB + off, v);
-            } else {
-                if (!more) return;
-                if (kbase + k < p.K) {
-                    if (n < nrem) cp_async<(int)sizeof(E)>(dst, gB + (sColB[n] + p.kB[kbase + k]));
-                } else {
-                    *dst = E{};
-                }
-            }
+            const bool ok = i < BN * BK && n < nrem;
+            u_ptr[u] = ok ? reinterpret_cast<const char *>(gB + sColB[n]) : nullptr;
+            u_dst[u] = (i < BN * BK) ? (k * LDB + n) * (int)sizeof(E) : -1;
+            u_k[u] = BK + k;
         }
+    }
+    const unsigned sA_u32 = (unsigned)__cvta_generic_to_shared(sA), sB_u32 = (unsigned)__cvta_generic_to_shared(sB);
+    auto issue_unit = [&](int stage, int u, const int64_t *koff) {
+        if ((u < UA ? (BM * BK) % NT : (BN * BK) % NT) != 0 && u_dst[u] < 0) return;   // only partial-tile variants
+        const int64_t ko = koff[u_k[u]];
+        const bool v = u_ptr[u] != nullptr && ko >= 0;
+        const char *src = v ? u_ptr[u] + ko : reinterpret_cast<const char *>(p.A);
+        const unsigned dst = (u < UA ? sA_u32 + stage * STAGE_A : sB_u32 + stage * STAGE_B) + u_dst[u];
+        const int bytes = v ? (int)sizeof(E) : 0;
+        if constexpr (sizeof(E) == 16)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes));
+        else if constexpr (sizeof(E) == 8)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(bytes));
+        else
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(bytes));
     };
 
     typename Core::Acc acc;
     Core::init(acc);
 
-#pragma unroll
-    for (int s = 0; s < S - 1; s++) {
-        if (s < KB) {
-#pragma unroll
-            for (int u = 0; u < UNITS; u++) issue_unit(s, (int64_t)s * BK, u, true);
+    // k-offsets are staged through shared memory one k-block ahead of their use (pre-scaled to bytes, -1 past K):
+    // the gather units read them with a short LDS instead of stalling the in-order MMA warps on a global load.
+    auto stage_koff = [&](int64_t kblock, int slot) {
+        if (tid < 2 * BK) {
+            const int k = tid % BK;
+            const int64_t kg = kblock * BK + k;
+            int64_t v = -1;
+            if (kg < p.K) v = ((tid < BK) ? p.kA[kg] : p.kB[kg]) * (int64_t)sizeof(E);
+            sK[slot * 2 * BK + tid] = v;
         }
+    };
+    // prologue: stages 0..S-2
+    for (int s = 0; s < S - 1; s++) {
+        stage_koff(s, 0);
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < UNITS; u++) issue_unit(s, u, sK);
         cp_async_commit();
+        __syncthreads();
     }
+    stage_koff(S - 1, 0);   // offsets of the first k-block gathered inside the main loop
     for (int64_t kb = 0; kb < KB; kb++) {
         cp_async_wait<S - 2>();
-        __syncthreads();
+        __syncthreads();     // stage kb landed; sK[kb & 1] (written one iteration ago / in the prologue) visible
         const int64_t nk = kb + S - 1;
-        const bool more = nk < KB;
         const int nstage = (int)(nk % S);
         const int st = (int)(kb % S);
+        const int64_t *koff = sK + (kb & 1) * 2 * BK;
+        stage_koff(nk + 1, (int)((kb + 1) & 1));   // for the next iteration's gather
         // the next stage's gather is spread over the MMA stream: slot s issues units [s*UNITS/SLOTS, ...)
         Core::compute(acc, sA + (size_t)st * BK * LDA, sB + (size_t)st * BK * LDB, warp, lane, [&](int slot) {
             constexpr int SLOTS = Core::SLOTS;
@@ -380,7 +393,7 @@ __global__ void __launch_bounds__(Core::NTHREADS, 1) gett_kernel(const __grid_co
 #pragma unroll
             for (int q = 0; q < PER; q++) {
                 const int u = slot * PER + q;
-                if (u < UNITS) issue_unit(nstage, nk * BK, u, more);
+                if (u < UNITS) issue_unit(nstage, u, koff);
             }
             if (slot == SLOTS - 1) cp_async_commit();
         });
