@@ -263,7 +263,7 @@ constexpr size_t gett_smem_bytes() {
 constexpr int GROUP_M = 8;
 
 template <class Core>
-__global__ void __launch_bounds__(Core::NTHREADS, 1) gett_kernel(const __grid_constant__ GettParams p) {
+__global__ void __launch_bounds__(Core::NTHREADS, Core::NTHREADS <= 128 ? 4 : 1) gett_kernel(const __grid_constant__ GettParams p) {
     using E = typename Core::Elem;
     constexpr int BM = Core::BM, BN = Core::BN, BK = Core::BK, S = Core::STAGES;
     constexpr int LDA = Core::LDA, LDB = Core::LDB, NT = Core::NTHREADS;
@@ -419,7 +419,8 @@ cudaError_t configure() {
 
 // tile menus ---------------------------------------------------------------------------------------
 using Z_128x64 = CoreZ<128, 64, 32, 32, 8, 4>;   // main ComplexF64 tile: 8 warps x (32 x 32)
-using Z_128x16 = CoreZ<128, 16, 16, 16, 8, 4>;   // skinny N (MPS-MPO middle step: N = K = 16)
+using Z_128x16 = CoreZ<128, 16, 16, 16, 8, 4>;   // skinny N
+using Z_128x16s = CoreZ<128, 16, 32, 16, 8, 2>;  // skinny N and short K (MPS-MPO middle step: N = K = 16): 4 warps, 2 stages -> 4-5 CTAs/SM
 using Z_16x128 = CoreZ<16, 128, 16, 16, 8, 4>;   // skinny M
 using D_128x128 = CoreD<128, 128, 64, 32, 8, 4>; // Float64: 8 warps x (64 x 32)
 using D_128x16 = CoreD<128, 16, 16, 16, 8, 4>;
@@ -436,7 +437,7 @@ using S_16x128 = CoreF<float, 16, 128, 8, 4>;
 cudaError_t gett_configure() {
     cudaError_t e;
 #define MB200_CFG(C) if ((e = configure<C>()) != cudaSuccess) return e
-    MB200_CFG(Z_128x64); MB200_CFG(Z_128x16); MB200_CFG(Z_16x128);
+    MB200_CFG(Z_128x64); MB200_CFG(Z_128x16); MB200_CFG(Z_128x16s); MB200_CFG(Z_16x128);
     MB200_CFG(D_128x128); MB200_CFG(D_128x16); MB200_CFG(D_16x128);
     MB200_CFG(C_128x64); MB200_CFG(C_128x16); MB200_CFG(C_16x128);
     MB200_CFG(S_128x128); MB200_CFG(S_128x16); MB200_CFG(S_16x128);
@@ -446,7 +447,7 @@ cudaError_t gett_configure() {
 
 cudaError_t launch_gett_f64(int dtype, const GettParams &p, cudaStream_t s) {
     if (dtype == MB200_C128) {
-        if (p.N <= 16 && p.M > 16) return launch<Z_128x16>(p, s);
+        if (p.N <= 16 && p.M > 16) return p.K <= 32 ? launch<Z_128x16s>(p, s) : launch<Z_128x16>(p, s);
         if (p.M <= 16 && p.N > 16) return launch<Z_16x128>(p, s);
         return launch<Z_128x64>(p, s);
     }

@@ -91,6 +91,33 @@ def main():
     E.append(einsum_case("cfg5 rank8 dim8 c64 (unsliced)", e5, "aebfcgdh", "hpgqfres", "srqpdcba", "complex64"))
     E.append(einsum_case("dgemm 8192^3 f64", dict(i=8192, j=8192, k=8192), "ik", "kj", "ij", "float64", iters=3))
     E.append(einsum_case("sgemm 8192^3 f32", dict(i=8192, j=8192, k=8192), "ik", "kj", "ij", "float32", iters=3))
+    # launch-bound tiny contraction (everything in the reference's own test-suite is this size): per-call latency
+    # of the C ABI alone (ctypes, cached plan, one direct-kernel launch) and of the Python front-end
+    import time
+    h = _lib.Handle.get()
+    a = Tensor(dev_rand((2, 3), "complex128"), I("ij")); b = Tensor(dev_rand((3, 4), "complex128"), I("jk"))
+    c = B200Array((2, 4), "complex128")
+    args = (h.ptr, C.c_void_p(c.ptr), _lib.C128, 2, _lib.i32([0, 2]), None,
+            C.c_void_p(a.data.ptr), _lib.C128, 2, _lib.i32([0, 1]), _lib.i64((2, 3)), None,
+            C.c_void_p(b.data.ptr), _lib.C128, 2, _lib.i32([1, 2]), _lib.i64((3, 4)), None)
+    fn = mb.lib().mb200_binary_einsum
+    for _ in range(100):
+        fn(*args)
+    torch.cuda.synchronize()
+    n = 5000
+    t0 = time.perf_counter()
+    for _ in range(n):
+        fn(*args)
+    torch.cuda.synchronize()
+    abi_us = (time.perf_counter() - t0) / n * 1e6
+    t0 = time.perf_counter()
+    for _ in range(1000):
+        binary_einsum(a, b)
+    torch.cuda.synchronize()
+    py_us = (time.perf_counter() - t0) / 1000 * 1e6
+    out["tiny_contraction_latency_us"] = {"c_abi_call": abi_us, "python_front_end": py_us,
+                                          "what": "2x3 . 3x4 ComplexF64 matmul, device-resident, one direct_kernel launch per call"}
+    print(f"TINY    2x3.3x4 c128: {abi_us:.2f} us per C-ABI call, {py_us:.1f} us through the Python front-end")
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(out, open("gpurun_out/kernels.json", "w"), indent=1)
     for r in P:
