@@ -298,31 +298,64 @@ def run_ours(args):
                    "frac": bytes_2b / (t2b * 1e-3) / 1e9 / hbm_peak, "bytes_per_launch": bytes_2b, "ms_per_launch": t2b,
                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}
 
-    # ---- e2e: public API with HOST (pinned) buffers, H2D + chain + D2H inside the timed region -------
+    # ---- e2e: public API with HOST (pinned) buffers; every step uploads its inputs and downloads its result -----
+    # Steps are pipelined over three streams (upload / contract / download) so the PCIe copies of neighbouring
+    # steps overlap the contraction; all copies of all timed steps are inside the timed region.
     Ke = max(3, min(K, 10))
     h2d = sum(v[0].nbytes for v in pinned.values())
     d2h = res_view.nbytes
+    res_pins = [torch.empty(CHI * W * CHI * 2, dtype=torch.float64).pin_memory() for _ in range(2)]
+    res_views = [t.numpy().view(np.complex128).reshape((CHI, W, CHI), order="F") for t in res_pins]
+    s_in, s_comp, s_out = torch.cuda.Stream(local), torch.cuda.Stream(local), torch.cuda.Stream(local)
 
-    def e2e_step():
+    def e2e_run(nsteps):
+        keep = []                                    # keep device buffers alive until every stream is done
+        for k in range(nsteps):
+            with torch.cuda.stream(s_in):
+                t = {name: Tensor(view, I(inds)).to_device(local, non_blocking=True) for name, (view, inds, _) in pinned.items()}
+                ev_in = torch.cuda.Event(); ev_in.record(s_in)
+            with torch.cuda.stream(s_comp):
+                s_comp.wait_event(ev_in)
+                z = chain(t)
+                ev_c = torch.cuda.Event(); ev_c.record(s_comp)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_c)
+                z.data.to_host(out=res_views[k & 1], non_blocking=True)
+            keep.append((t, z))
+        for st in (s_in, s_comp, s_out):
+            st.synchronize()
+        return keep
+
+    def e2e_serial_step():
         t = {name: Tensor(B200Array.from_host(view, local), I(inds)) for name, (view, inds, _) in pinned.items()}
         chain(t).data.to_host(out=res_view)
 
-    e2e_step()
+    e2e_run(2)
+    check = float(np.abs(res_views[1] - chain(dev).to_host().data).max())
+    e2e_serial_step()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(Ke):
-        e2e_step()
+    for _ in range(3):
+        e2e_serial_step()
     e1.record()
     torch.cuda.synchronize()
-    e2e_ms = e0.elapsed_time(e1) / Ke
+    serial_ms = e0.elapsed_time(e1) / 3
+    barrier()
+    t0 = time.perf_counter()
+    e2e_run(Ke)
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / Ke
     if world > 1:
         tmax = torch.tensor([e2e_ms], device=f"cuda:{local}", dtype=torch.float64)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         e2e_ms = float(tmax.item())
     e2e = {"value": world * step_flops / (e2e_ms * 1e-3) / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": Ke,
-           "api": "Tensor(pinned numpy).to_device → 3× binary_einsum → .to_host (per rank)"}
+           "serial_ms_per_step": serial_ms, "serial_value": world * step_flops / (serial_ms * 1e-3) / 1e12,
+           "max_abs_diff_vs_device_resident_result": check,
+           "timing": "host wall clock around Ke pipelined steps, all streams synchronised on both sides",
+           "api": "Tensor(pinned numpy).to_device(non_blocking) -> 3x binary_einsum -> .to_host(non_blocking); steps "
+                  "pipelined over upload/contract/download streams (serial_* = the same without pipelining)"}
 
     # ---- the north star's sharded configs ----------------------------------------------------------------
     sharded = None

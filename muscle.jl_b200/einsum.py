@@ -78,10 +78,10 @@ def _b200_out_of_place(inds_c, a: Tensor, b: Tensor) -> Tensor:
     ma, mb, mc = flatten_labels(a.inds, b.inds, inds_c)
     T = _promote(a, b)
     L = _lib.lib()
-    # host-only validation first: argument errors must not depend on a GPU being present
-    _lib.plan_describe(_lib.dtype_enum(T), mc, _lib.dtype_enum(a.dtype), ma, a.shape,
-                       _lib.dtype_enum(b.dtype), mb, b.shape)
     if not a.on_device and not b.on_device:
+        # host-only validation first: argument errors must not depend on a GPU being present
+        _lib.plan_describe(_lib.dtype_enum(T), mc, _lib.dtype_enum(a.dtype), ma, a.shape,
+                           _lib.dtype_enum(b.dtype), mb, b.shape)
         # host arrays: the library stages through HBM itself (H2D, kernels, D2H, sync)
         h = _lib.Handle.get()
         ha = _lib.fortran(a.data)

@@ -97,11 +97,12 @@ class B200Array:
         return int(np.prod(self.shape, dtype=np.int64)) if self.shape else 1
 
     @classmethod
-    def from_host(cls, array, device=None):
-        """Upload (async on the handle's stream; a pinned source makes it a true async copy)."""
+    def from_host(cls, array, device=None, non_blocking=False):
+        """Upload on the current stream. non_blocking=True returns without synchronising: the source must be
+        pinned host memory and must stay alive and unmodified until the stream reaches the copy."""
         a = _lib.fortran(array)
         out = cls(a.shape, a.dtype, device)
-        out.copy_from_host(a)
+        out.copy_from_host(a, non_blocking=non_blocking)
         return out
 
     @classmethod
@@ -116,22 +117,26 @@ class B200Array:
         owner = t.view(torch.uint8).reshape(-1) if t.dtype != torch.uint8 else t.reshape(-1)
         return cls(shape, dtype, t.device.index, _owner=owner, _ptr=t.data_ptr())
 
-    def copy_from_host(self, a):
+    def copy_from_host(self, a, non_blocking=False):
         a = _lib.fortran(a)
         if a.shape != self.shape or a.dtype != self.dtype:
             raise DimensionMismatch(f"copy_from_host: {a.shape}/{a.dtype} into {self.shape}/{self.dtype}")
         h = _lib.Handle.get(self.device)
         if a.nbytes:
             _lib.check(_lib.lib().mb200_memcpy_h2d(h.ptr, C.c_void_p(self.ptr), C.c_void_p(a.ctypes.data), a.nbytes))
-            h.synchronize()  # the numpy source may be pageable and may die after return
+            if not non_blocking:
+                h.synchronize()  # the numpy source may be pageable and may die after return
 
-    def to_host(self, out=None):
+    def to_host(self, out=None, non_blocking=False):
+        """Download on the current stream. With non_blocking=True `out` must be pinned and is only valid after the
+        stream has been synchronised by the caller."""
         if out is None:
             out = np.empty(self.shape, dtype=self.dtype, order="F")
         h = _lib.Handle.get(self.device)
         if out.nbytes:
             _lib.check(_lib.lib().mb200_memcpy_d2h(h.ptr, C.c_void_p(out.ctypes.data), C.c_void_p(self.ptr), out.nbytes))
-        h.synchronize()
+        if not non_blocking:
+            h.synchronize()
         return out
 
     def __repr__(self):
@@ -189,10 +194,10 @@ class Tensor:
     def on_device(self) -> bool:
         return isinstance(self.data, B200Array)
 
-    def to_device(self, device=None) -> "Tensor":
+    def to_device(self, device=None, non_blocking=False) -> "Tensor":
         if self.on_device:
             return self
-        return Tensor(B200Array.from_host(self.data, device), self._inds)
+        return Tensor(B200Array.from_host(self.data, device, non_blocking=non_blocking), self._inds)
 
     def to_host(self) -> "Tensor":
         if not self.on_device:
