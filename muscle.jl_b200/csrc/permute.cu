@@ -314,18 +314,18 @@ cudaError_t launch_permute(int dtype, const PermuteParams &q, const void *src, v
     int lx_t = long_runs ? 0 : std::min(lrem / 2, 8);
     int ly_t = std::min(lrem - lx_t, 8);
     int64_t SX = 1, SY = 1;
+    // the destination unit-stride mode (after v) always belongs to y, so x cannot steal it
     if (ys < (size_t)n && role[dord[ys]] == 0 && ly_t > 0) { role[dord[ys]] = 3; SY *= q.ext[dord[ys]]; ys++; }
-    bool grow_x = lx_t > 0, grow_y = ly_t > 0;
-    while (grow_x || grow_y) {
-        if (grow_x) {
-            if (SX >= ((int64_t)1 << lx_t) || xs >= n || role[xs] != 0) grow_x = false;
-            else { role[xs] = 2; SX *= q.ext[xs]; xs++; }
-        }
-        if (grow_y) {
-            if (SY >= ((int64_t)1 << ly_t) || ys >= (size_t)n || role[dord[ys]] != 0) grow_y = false;
-            else { role[dord[ys]] = 3; SY *= q.ext[dord[ys]]; ys++; }
-        }
-    }
+    auto grow_x = [&](int lg) {
+        while (SX < ((int64_t)1 << lg) && xs < n && role[xs] == 0) { role[xs] = 2; SX *= q.ext[xs]; xs++; }
+    };
+    auto grow_y = [&](int lg) {
+        while (SY < ((int64_t)1 << lg) && ys < (size_t)n && role[dord[ys]] == 0) { role[dord[ys]] = 3; SY *= q.ext[dord[ys]]; ys++; }
+    };
+    // x to its target, then y with whatever x could not use, then x again with whatever y could not use
+    grow_x(lx_t);
+    grow_y(std::min(lrem - std::min(lx_t, ceil_log2(SX)), 8));
+    grow_x(std::min(lrem - std::min(8, ceil_log2(SY)), 8));
     for (int i = 0; i < n; i++) {
         if (role[i] == 2) { k.x_ext[k.nx] = (unsigned)q.ext[i]; k.x_ss[k.nx] = sstride[i]; k.x_ds[k.nx] = q.dst_stride[i]; k.nx++; }
         if (role[i] == 0) { k.o_ext[k.n_out] = (unsigned)q.ext[i]; k.o_ss[k.n_out] = sstride[i]; k.o_ds[k.n_out] = q.dst_stride[i]; k.n_out++; }
