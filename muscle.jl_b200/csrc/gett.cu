@@ -418,17 +418,17 @@ cudaError_t configure() {
 }
 
 // tile menus ---------------------------------------------------------------------------------------
-using Z_128x64 = CoreZ<128, 64, 32, 32, 8, 4>;   // main ComplexF64 tile: 8 warps x (32 x 32)
+using Z_128x64 = CoreZ<128, 64, 32, 32, 32, 2>;  // main ComplexF64 tile: 8 warps x (32 x 32); long k-blocks: one CTA barrier per 32 k
 using Z_128x16 = CoreZ<128, 16, 16, 16, 8, 4>;   // skinny N
 using Z_128x16s = CoreZ<128, 16, 32, 16, 8, 2>;  // skinny N and short K (MPS-MPO middle step: N = K = 16): 4 warps, 2 stages -> 4-5 CTAs/SM
 using Z_16x128 = CoreZ<16, 128, 16, 16, 8, 4>;   // skinny M
-using D_128x128 = CoreD<128, 128, 64, 32, 8, 4>; // Float64: 8 warps x (64 x 32)
+using D_128x128 = CoreD<128, 128, 64, 32, 16, 3>; // Float64: 8 warps x (64 x 32)
 using D_128x16 = CoreD<128, 16, 16, 16, 8, 4>;
 using D_16x128 = CoreD<16, 128, 16, 16, 8, 4>;
-using C_128x64 = CoreF<float2, 128, 64, 8, 4>;   // ComplexF32 FFMA: thread tile 8 x 4
+using C_128x64 = CoreF<float2, 128, 64, 16, 3>;  // ComplexF32 FFMA: thread tile 8 x 4
 using C_128x16 = CoreF<float2, 128, 16, 8, 4>;
 using C_16x128 = CoreF<float2, 16, 128, 8, 4>;
-using S_128x128 = CoreF<float, 128, 128, 8, 4>;  // Float32 FFMA: thread tile 8 x 8
+using S_128x128 = CoreF<float, 128, 128, 16, 3>; // Float32 FFMA: thread tile 8 x 8
 using S_128x16 = CoreF<float, 128, 16, 8, 4>;
 using S_16x128 = CoreF<float, 16, 128, 8, 4>;
 
