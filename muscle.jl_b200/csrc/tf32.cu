@@ -16,7 +16,14 @@
 // Roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
 // warps 2..9 = epilogue (tcgen05.ld 32 lanes x BN/2 columns each -> running sums in registers ->
 // C[rowC[m] + colC[n] + batC[l]]). Pipelines: full/empty mbarriers over a 6-stage smem ring (TMA <-> MMA),
-// tmem_full/tmem_empty over two TMEM chunk buffers (MMA <-> epilogue). One output tile (128 x BN) per CTA.
+// tmem_full/tmem_empty over two TMEM chunk buffers (MMA <-> epilogue). Persistent: one CTA per SM walks the
+// 128 x BN output tiles.
+//
+// Measured limits (ncu, config 3): the SM clock sits at ~1.57 GHz under this kernel (power), tensor sub-pipes 81 %
+// active; at N = 128 a K=8 tf32 MMA reads 8 KB of smem operands per 64 tensor cycles = all 128 B/clk of shared
+// memory (forcing BN = 64 makes the GEMM 1.77x slower). A variant issuing six N = 256 MMAs over concatenated
+// [re;im] column-operand planes (25 % fewer smem bytes) was built and verified: GEMM 2.21 -> 2.13 ms but the pack
+// and DRAM traffic grow by the same amount, so it was not kept.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -121,6 +128,7 @@ struct Tf32Params {
     float2 *C;
     const int64_t *rowC, *colC, *batC;
     int64_t M, N, L;
+    int64_t ntiles;
     int KG;   // number of 8-k groups
 };
 
@@ -129,7 +137,7 @@ struct Tf32Smem {
     static constexpr int A_BYTES = TBM * GROUP_BYTES;   // 16 KB
     static constexpr int B_BYTES = BN * GROUP_BYTES;
     static constexpr int STAGE = A_BYTES + B_BYTES;
-    static constexpr int TOTAL = TSTAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/ + BN * 8 /*colC*/;
+    static constexpr int TOTAL = TSTAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/ + 2 * BN * 8 /*colC, two tiles*/;
 };
 
 // Two-level accumulation. The tensor core adds into TMEM with truncation, so a long accumulation chain
@@ -137,6 +145,24 @@ struct Tf32Smem {
 // holds a chunk of CHUNK_GROUPS*8 = 128 k (double-buffered: the MMA warp fills buffer c&1 while the
 // epilogue warps drain the other one); the running sums live in the epilogue warps' registers and are
 // added with ordinary round-to-nearest FADDs.
+// tile id -> (m0, n0, batch): grouped rasterisation, 8 row-tiles share a B column panel in L2
+struct TileCoord { int m0, n0, l; };
+template <int BN>
+__device__ __forceinline__ TileCoord tile_coord(const Tf32Params &p, int64_t tile) {
+    const int64_t tiles_m = (p.M + TBM - 1) / TBM, tiles_n = (p.N + BN - 1) / BN;
+    const int64_t per = tiles_m * tiles_n;
+    const int64_t l = tile / per, t = tile % per;
+    const int64_t gsz_full = 8, pg = gsz_full * tiles_n, g = t / pg, gm0 = g * gsz_full;
+    const int64_t gsz = (tiles_m - gm0) < gsz_full ? (tiles_m - gm0) : gsz_full;
+    const int64_t tm = gm0 + (t % pg) % gsz, tn = (t % pg) / gsz;
+    return TileCoord{(int)(tm * TBM), (int)(tn * BN), (int)l};
+}
+
+// Persistent: CTA b walks tiles b, b + gridDim.x, ... The three roles keep running counters (smem stage / TMEM
+// chunk buffer and their mbarrier phases) across tiles, so the TMA producer prefetches the next tile's first
+// stages while the MMA warp is still on the current tile's tail, and the MMA warp starts the next tile's first
+// chunk while the epilogue warps are still storing the previous tile: per-tile prologue and epilogue are hidden
+// (K = 512 slices: 0.362 -> 0.317 ms).
 template <int BN>
 __global__ void __launch_bounds__(TTHREADS, 1)
 tf32_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
@@ -152,19 +178,11 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     uint64_t *tmem_full = empty + TSTAGES;        // [2]
     uint64_t *tmem_empty = tmem_full + 2;         // [2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
-    int64_t *sColC = reinterpret_cast<int64_t *>(tiles + TSTAGES * SM::STAGE + 256);
+    int64_t *sColC = reinterpret_cast<int64_t *>(tiles + TSTAGES * SM::STAGE + 256);   // [2][BN], per tile parity
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t tiles_m = (p.M + TBM - 1) / TBM, tiles_n = (p.N + BN - 1) / BN;
-    const int64_t per = tiles_m * tiles_n;
-    const int64_t l = blockIdx.x / per;
-    const int64_t t = blockIdx.x % per;
-    // grouped rasterisation: 8 row-tiles share a B column panel in L2
-    const int64_t gsz_full = 8, pg = gsz_full * tiles_n, g = t / pg, gm0 = g * gsz_full;
-    const int64_t gsz = (tiles_m - gm0) < gsz_full ? (tiles_m - gm0) : gsz_full;
-    const int64_t tm = gm0 + (t % pg) % gsz, tn = (t % pg) / gsz;
-    const int m0 = (int)(tm * TBM), n0 = (int)(tn * BN);
     const int nchunks = (p.KG + CHUNK_GROUPS - 1) / CHUNK_GROUPS;
+    const int64_t ntiles = p.ntiles;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -174,9 +192,6 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
-    if (warp >= 2) {
-        for (int i = threadIdx.x - 64; i < BN; i += TTHREADS - 64) sColC[i] = (n0 + i < p.N) ? p.colC[n0 + i] : 0;
-    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -184,88 +199,103 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
     if (warp == 0) {
         if (lane == 0) {   // ---- TMA producer
-            for (int kg = 0; kg < p.KG; kg++) {
-                const int s = kg % TSTAGES;
-                const uint32_t ph = (kg / TSTAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                mbar_expect_tx(&full[s], SM::STAGE);
-                unsigned char *a = tiles + s * SM::STAGE;
-                tma_load_3d(a, &mapA, &full[s], kg * 32, m0, (int)l);
-                tma_load_3d(a + SM::A_BYTES, &mapB, &full[s], kg * 32, n0, (int)l);
+            uint32_t it = 0;   // running stage counter
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const TileCoord tc = tile_coord<BN>(p, tile);
+                for (int kg = 0; kg < p.KG; kg++, it++) {
+                    const int s = it % TSTAGES;
+                    mbar_wait(&empty[s], ((it / TSTAGES) & 1) ^ 1);
+                    mbar_expect_tx(&full[s], SM::STAGE);
+                    unsigned char *a = tiles + s * SM::STAGE;
+                    tma_load_3d(a, &mapA, &full[s], kg * 32, tc.m0, tc.l);
+                    tma_load_3d(a + SM::A_BYTES, &mapB, &full[s], kg * 32, tc.n0, tc.l);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {   // ---- MMA issuer
             constexpr uint32_t IDESC = make_idesc(TBM, BN, false), IDESC_NEG = make_idesc(TBM, BN, true);
-            int kg = 0;
-            for (int c = 0; c < nchunks; c++) {
-                const int buf = c & 1;
-                mbar_wait(&tmem_empty[buf], ((c >> 1) & 1) ^ 1);   // epilogue has drained this buffer
-                tc_fence_after();
-                const uint32_t d_re = tmem_base + buf * BUF_COLS, d_im = d_re + BN;
-                const int kend = min(p.KG, (c + 1) * CHUNK_GROUPS);
-                for (bool first = true; kg < kend; kg++, first = false) {
-                    const int s = kg % TSTAGES;
-                    mbar_wait(&full[s], (kg / TSTAGES) & 1);
+            uint32_t it = 0, ch = 0;   // running stage / chunk counters
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                int kg = 0;
+                for (int c = 0; c < nchunks; c++, ch++) {
+                    const int buf = ch & 1;
+                    mbar_wait(&tmem_empty[buf], ((ch >> 1) & 1) ^ 1);   // epilogue has drained this buffer
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(tiles + s * SM::STAGE);
-                    const uint64_t da = make_desc(sa), db = make_desc(sa + SM::A_BYTES);
-                    // chunk c of a row is +32*c bytes: descriptor start-address field += 2*c
-                    const uint64_t a_rh = da, a_rl = da + 2, a_ih = da + 4, a_il = da + 6;
-                    const uint64_t b_rh = db, b_rl = db + 2, b_ih = db + 4, b_il = db + 6;
-                    const uint32_t acc = first ? 0u : 1u;
-                    umma_tf32(d_re, a_rh, b_rh, IDESC, acc);
-                    umma_tf32(d_im, a_rh, b_ih, IDESC, acc);
-                    umma_tf32(d_re, a_rh, b_rl, IDESC, 1u);
-                    umma_tf32(d_im, a_rh, b_il, IDESC, 1u);
-                    umma_tf32(d_re, a_rl, b_rh, IDESC, 1u);
-                    umma_tf32(d_im, a_rl, b_ih, IDESC, 1u);
-                    umma_tf32(d_re, a_ih, b_ih, IDESC_NEG, 1u);
-                    umma_tf32(d_im, a_ih, b_rh, IDESC, 1u);
-                    umma_tf32(d_re, a_ih, b_il, IDESC_NEG, 1u);
-                    umma_tf32(d_im, a_ih, b_rl, IDESC, 1u);
-                    umma_tf32(d_re, a_il, b_ih, IDESC_NEG, 1u);
-                    umma_tf32(d_im, a_il, b_rh, IDESC, 1u);
-                    umma_commit(&empty[s]);          // frees the smem stage when these MMAs have read it
+                    const uint32_t d_re = tmem_base + buf * BUF_COLS, d_im = d_re + BN;
+                    const int kend = min(p.KG, (c + 1) * CHUNK_GROUPS);
+                    for (bool first = true; kg < kend; kg++, it++, first = false) {
+                        const int s = it % TSTAGES;
+                        mbar_wait(&full[s], (it / TSTAGES) & 1);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(tiles + s * SM::STAGE);
+                        const uint64_t da = make_desc(sa), db = make_desc(sa + SM::A_BYTES);
+                        // chunk c of a row is +32*c bytes: descriptor start-address field += 2*c
+                        const uint64_t a_rh = da, a_rl = da + 2, a_ih = da + 4, a_il = da + 6;
+                        const uint64_t b_rh = db, b_rl = db + 2, b_ih = db + 4, b_il = db + 6;
+                        const uint32_t acc = first ? 0u : 1u;
+                        umma_tf32(d_re, a_rh, b_rh, IDESC, acc);
+                        umma_tf32(d_im, a_rh, b_ih, IDESC, acc);
+                        umma_tf32(d_re, a_rh, b_rl, IDESC, 1u);
+                        umma_tf32(d_im, a_rh, b_il, IDESC, 1u);
+                        umma_tf32(d_re, a_rl, b_rh, IDESC, 1u);
+                        umma_tf32(d_im, a_rl, b_ih, IDESC, 1u);
+                        umma_tf32(d_re, a_ih, b_ih, IDESC_NEG, 1u);
+                        umma_tf32(d_im, a_ih, b_rh, IDESC, 1u);
+                        umma_tf32(d_re, a_ih, b_il, IDESC_NEG, 1u);
+                        umma_tf32(d_im, a_ih, b_rl, IDESC, 1u);
+                        umma_tf32(d_re, a_il, b_ih, IDESC_NEG, 1u);
+                        umma_tf32(d_im, a_il, b_rh, IDESC, 1u);
+                        umma_commit(&empty[s]);          // frees the smem stage when these MMAs have read it
+                    }
+                    umma_commit(&tmem_full[buf]);        // this chunk's accumulators are complete
                 }
-                umma_commit(&tmem_full[buf]);        // this chunk's accumulators are complete
             }
         }
     } else {               // ---- epilogue: warps 2..9; TMEM lane quarter = warp % 4, column half = (warp-2)/4
         const int q = warp & 3, half = (warp - 2) >> 2;
         const int row = q * 32 + lane;
-        const int64_t m = (int64_t)m0 + row;
-        const bool row_ok = m < p.M;
-        const int64_t crow = (row_ok ? p.rowC[m] : 0) + p.batC[l];
-        float accr[HALF], acci[HALF];
+        const int et = threadIdx.x - 64;   // 0..255 among the epilogue threads
+        uint32_t ch = 0, tcount = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
+            const TileCoord tc = tile_coord<BN>(p, tile);
+            int64_t *cols = sColC + (tcount & 1) * BN;
+            for (int i = et; i < BN; i += TTHREADS - 64) cols[i] = (tc.n0 + i < p.N) ? p.colC[tc.n0 + i] : 0;
+            const int64_t m = (int64_t)tc.m0 + row;
+            const bool row_ok = m < p.M;
+            const int64_t crow = (row_ok ? p.rowC[m] : 0) + p.batC[tc.l];
+            float accr[HALF], acci[HALF];
 #pragma unroll
-        for (int j = 0; j < HALF; j++) accr[j] = acci[j] = 0.f;
-        for (int c = 0; c < nchunks; c++) {
-            const int buf = c & 1;
-            mbar_wait(&tmem_full[buf], (c >> 1) & 1);
-            tc_fence_after();
-            const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BUF_COLS + half * HALF;
+            for (int j = 0; j < HALF; j++) accr[j] = acci[j] = 0.f;
+            for (int c = 0; c < nchunks; c++, ch++) {
+                const int buf = ch & 1;
+                mbar_wait(&tmem_full[buf], (ch >> 1) & 1);
+                tc_fence_after();
+                const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BUF_COLS + half * HALF;
 #pragma unroll
-            for (int sub = 0; sub < HALF / 32; sub++) {
-                uint32_t v[32];
-                tmem_ld32(tq + sub * 32, v);
-                tmem_ld_wait();
+                for (int sub = 0; sub < HALF / 32; sub++) {
+                    uint32_t v[32];
+                    tmem_ld32(tq + sub * 32, v);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; j++) accr[sub * 32 + j] += __uint_as_float(v[j]);
-                tmem_ld32(tq + BN + sub * 32, v);
-                tmem_ld_wait();
+                    for (int j = 0; j < 32; j++) accr[sub * 32 + j] += __uint_as_float(v[j]);
+                    tmem_ld32(tq + BN + sub * 32, v);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; j++) acci[sub * 32 + j] += __uint_as_float(v[j]);
+                    for (int j = 0; j < 32; j++) acci[sub * 32 + j] += __uint_as_float(v[j]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[buf]);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
-        }
-        if (row_ok) {
+            // the column table of this tile was written by all epilogue threads: named barrier over the 8 epilogue warps
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (row_ok) {
 #pragma unroll
-            for (int j = 0; j < HALF; j++) {
-                const int cidx = half * HALF + j;
-                if (n0 + cidx < p.N) *scatter_ptr(p.sc, p.C, crow + sColC[cidx]) = make_float2(accr[j], acci[j]);
+                for (int j = 0; j < HALF; j++) {
+                    const int cidx = half * HALF + j;
+                    if (tc.n0 + cidx < p.N) *scatter_ptr(p.sc, p.C, crow + cols[cidx]) = make_float2(accr[j], acci[j]);
+                }
             }
         }
         if (p.sc.nranks) __threadfence_system();   // peer stores must be visible before the cross-rank barrier
@@ -318,9 +348,10 @@ cudaError_t launch_bn(const void *packA, const void *packB, const GettParams &g,
     p.rowC = g.rowC; p.colC = g.colC; p.batC = g.batC;
     p.M = g.M; p.N = g.N; p.L = g.L;
     p.KG = (int)(g.K / 8);
-    const int64_t grid = ((g.M + TBM - 1) / TBM) * ((g.N + BN - 1) / BN) * g.L;
-    if (grid <= 0) return cudaSuccess;
-    if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    const int64_t ntiles = ((g.M + TBM - 1) / TBM) * ((g.N + BN - 1) / BN) * g.L;
+    if (ntiles <= 0) return cudaSuccess;
+    p.ntiles = ntiles;
+    const int64_t grid = ntiles < 148 ? ntiles : 148;   // persistent: one CTA per SM
     static bool cfg = false;
     if (!cfg) {
         cudaError_t e = cudaFuncSetAttribute(tf32_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tf32Smem<BN>::TOTAL);
