@@ -142,24 +142,34 @@ void evict_one(mb200_handle_t h) {
 
 // K1 pack of one operand into the tcgen05 kernel's operand format: [batch][rows][4*K] floats, K-major,
 // every 8-k group stored as re_hi | re_lo | im_hi | im_lo chunks of 8 floats (tf32.cu). Expressed as an
-// ordinary strided permutation: the fastest summed mode (extent % 8 == 0) is split into (8, e/8) with
-// destination strides (1, 32); the other summed modes get 4*kstride, row modes rows*4K, batch modes beyond.
+// ordinary strided permutation: the leading summed modes tile the group of 8 (the mode that completes it is split
+// into (need, e/need) with destination strides (kstride, 32)); later summed modes get 4*kstride, row modes
+// rows*4K, batch modes beyond.
 bool build_pack_params(const Plan &p, int which, PermuteParams &q, int64_t &rows) {
     struct Md { int64_t ext, ss, ds; };
     std::vector<Md> v;
     const int64_t K = p.K;
     int64_t kstride = 1;
-    for (size_t i = 0; i < p.sum.size(); i++) {
-        const GroupMode &g = p.sum[i];
+    bool grouped = false;   // the first group of 8 k has been tiled by the modes seen so far
+    for (const GroupMode &g : p.sum) {
         const int64_t ss = which ? g.sb : g.sa;
-        if (i == 0) {
-            v.push_back({8, ss, 1});
-            if (g.extent / 8 > 1) v.push_back({g.extent / 8, ss * 8, 32});
+        if (grouped) {
+            v.push_back({g.extent, ss, 4 * kstride});        // kstride is a multiple of 8: (kstride / 8) groups of 32 floats
         } else {
-            v.push_back({g.extent, ss, 4 * kstride});
+            const int64_t need = 8 / kstride;
+            if (g.extent % need == 0) {                       // completes the group: split into (need, extent / need)
+                v.push_back({need, ss, kstride});
+                if (g.extent / need > 1) v.push_back({g.extent / need, ss * need, 32});
+                grouped = true;
+            } else if (need % g.extent == 0) {                // still inside the group of 8
+                v.push_back({g.extent, ss, kstride});
+            } else {
+                return false;
+            }
         }
         kstride *= g.extent;
     }
+    if (!grouped) return false;
     int64_t rstride = 1;
     for (const GroupMode &g : (which ? p.right : p.left)) {
         v.push_back({g.extent, which ? g.sb : g.sa, rstride * 4 * K});

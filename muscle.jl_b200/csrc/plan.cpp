@@ -46,6 +46,17 @@ int make_desc(TensorDesc &d, int dtype, int nmode, const int32_t *modes, const i
     return MB200_OK;
 }
 
+bool k8_groupable(const std::vector<GroupMode> &sum) {
+    int64_t ks = 1;
+    for (const GroupMode &g : sum) {
+        const int64_t need = 8 / ks;
+        if (g.extent % need == 0) return true;      // this mode completes the first group of 8
+        if (need % g.extent != 0) return false;     // straddles a group boundary
+        ks *= g.extent;
+    }
+    return false;                                   // fewer than 8 summed elements
+}
+
 static int find_mode(const TensorDesc &t, int32_t m) {
     for (int i = 0; i < t.n; i++)
         if (t.modes[i] == m) return i;
@@ -159,14 +170,25 @@ int make_plan(const TensorDesc &A, const TensorDesc &B, TensorDesc &C, const int
     if (plan.b_kmajor && !plan.a_kmajor) std::stable_sort(plan.sum.begin(), plan.sum.end(), by_sb);
     else std::stable_sort(plan.sum.begin(), plan.sum.end(), by_sa);
 
-    // ComplexF32: the tcgen05 operand format needs the fastest summed mode to be a multiple of 8 (one 8-k group =
-    // one 128 B TMA row). Any common order of the summed modes is valid, so rotate a suitable mode to the front.
-    if (plan.dtype == MB200_C64 && !plan.sum.empty() && plan.sum[0].extent % 8 != 0) {
-        for (size_t i = 1; i < plan.sum.size(); i++)
-            if (plan.sum[i].extent % 8 == 0) {
-                std::rotate(plan.sum.begin(), plan.sum.begin() + i, plan.sum.begin() + i + 1);
-                break;
+    // ComplexF32: the tcgen05 operand format stores k in groups of 8 (one 8-k group = one 128 B TMA row), so the
+    // leading summed modes must tile a group exactly: extents 8 | e, or 2*2*2, 4*2, 2*4*..., 2*16 (split) ...
+    // (tensor-network tensors are mostly dim-2 / dim-4 indices). Any common order of the summed modes is valid, so
+    // try the memory order first, then a multiple-of-8 mode in front, then power-of-two extents first.
+    if (plan.dtype == MB200_C64 && !plan.sum.empty() && !k8_groupable(plan.sum)) {
+        std::vector<GroupMode> cand = plan.sum;
+        bool found = false;
+        for (size_t i = 1; i < cand.size() && !found; i++)
+            if (cand[i].extent % 8 == 0) {
+                std::rotate(cand.begin(), cand.begin() + i, cand.begin() + i + 1);
+                found = true;
             }
+        if (!found) {
+            cand = plan.sum;
+            std::stable_partition(cand.begin(), cand.end(),
+                                  [](const GroupMode &g) { return (g.extent & (g.extent - 1)) == 0; });
+            found = k8_groupable(cand);
+        }
+        if (found) plan.sum = cand;
     }
 
     auto prod = [](const std::vector<GroupMode> &g) {
@@ -197,7 +219,7 @@ int make_plan(const TensorDesc &A, const TensorDesc &B, TensorDesc &C, const int
         }
         return true;
     };
-    plan.tc_ok = plan.dtype == MB200_C64 && !plan.sum.empty() && plan.sum[0].extent % 8 == 0 && dense(A) && dense(B) &&
+    plan.tc_ok = plan.dtype == MB200_C64 && k8_groupable(plan.sum) && dense(A) && dense(B) &&
                  plan.M >= 64 && plan.N >= 32 && plan.K >= 64 && plan.M < ((int64_t)1 << 31) &&
                  plan.N < ((int64_t)1 << 31) && plan.L < ((int64_t)1 << 31) && plan.K < ((int64_t)1 << 27);
 

@@ -47,7 +47,7 @@ struct Plan {
     bool a_kmajor = false, b_kmajor = false;
     int path = MB200_PATH_DIRECT;
     bool empty_output = false;  // some C extent is 0
-    bool tc_ok = false;         // eligible for the tcgen05 3xTF32 path (dense ComplexF32 operands, first summed extent % 8 == 0)
+    bool tc_ok = false;         // eligible for the tcgen05 3xTF32 path (dense ComplexF32 operands, leading summed modes tile groups of 8 k)
     double flops = 0, bytes = 0;
     std::string key;  // cache key (all integers of the three descriptors + dtypes + forced path)
 };
@@ -63,5 +63,8 @@ int make_plan(const TensorDesc &A, const TensorDesc &B, TensorDesc &C, const int
               int forced_path, Plan &plan);
 
 void fill_info(const Plan &plan, mb200_plan_info_t *info);
+
+// true when the leading summed modes tile a group of 8 k exactly (tcgen05 operand format, tf32.cu)
+bool k8_groupable(const std::vector<GroupMode> &sum);
 
 }  // namespace mb200

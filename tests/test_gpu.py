@@ -440,3 +440,34 @@ def test_fused_scatter_epilogue_and_slot_reduce(dt, path, tol):
             C.c_void_p(tiny_a.ptr), _lib.dtype_enum(dt), 2, _lib.i32([0, 1]), _lib.i64((8, 16)), None,
             C.c_void_p(tiny_b.ptr), _lib.dtype_enum(dt), 2, _lib.i32([0, 2]), _lib.i64((8, 16)), None,
             arr, nranks, 0, 6))
+
+
+# ---- tensor-network style operands: many dim-2 / dim-4 indices -------------------------------------------------
+QUBIT_CASES = [
+    # (name, rank-a labels, rank-b labels, out labels): every label has extent 2 unless listed in `ext`
+    ("q_rank12_6shared", "abcdefghijkl", "ghijklmnopqr", "abcdefmnopqr", {}),
+    ("q_rank14_scrambled", "kalbmcndgehf", "pgqhrkslmtnu", "abcdefpqrstu", {}),
+    ("q_mixed_4_2", "abcdefgh", "efghijkl", "lkjidcba", dict(e=4, f=2, g=4, h=2, a=8, i=8)),
+    ("q_batch", "abcdefgz", "efghijkz", "abcdhijkz", dict(z=3)),
+]
+
+
+@pytest.mark.parametrize("dt", ["complex128", "complex64"])
+@pytest.mark.parametrize("case", QUBIT_CASES, ids=[c[0] for c in QUBIT_CASES])
+def test_qubit_style_tensors(case, dt):
+    """High-rank tensors with dim-2 indices (quantum-circuit contractions): ComplexF64 on the DMMA gather-GEMM,
+    ComplexF32 through the tcgen05 path whose 8-k groups span several small summed modes."""
+    name, ia, ib, ic, extd = case
+    ext = {c: extd.get(c, 2) for c in set(ia + ib)}
+    rng = np.random.default_rng(5)
+    a = random_array(rng, tuple(ext[c] for c in ia), dt)
+    b = random_array(rng, tuple(ext[c] for c in ib), dt)
+    ref = binary_einsum_general(list(ic), a.astype(np.complex128), list(ia), b.astype(np.complex128), list(ib)).astype(dt)
+    for path in ([mb.PATH_AUTO, mb.PATH_GETT_F64] if dt == "complex128" else [mb.PATH_AUTO, mb.PATH_TCGEN05_TF32, mb.PATH_SIMT_F32]):
+        h = _lib.Handle.get()
+        h.reset_stats()
+        got = contract(a, ia, b, ib, ic, path=path)
+        if path == mb.PATH_TCGEN05_TF32 and name != "q_batch":   # q_batch is below the tcgen05 size floor (K = 8)
+            assert h.stats()["launches_tcgen05"] == 1, (name, h.stats())   # eligible: 2*2*2 / 4*2 tile the 8-k group
+        assert got.shape == ref.shape
+        assert rel_frobenius(got, ref) <= TOL[dt], (name, dt, path)
