@@ -362,6 +362,8 @@ int mb200_create(mb200_handle_t *handle, int device) {
         return fail(MB200_NOT_SUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
                     device, prop.major, prop.minor);
     MB200_CUDA(gett_configure());
+    MB200_CUDA(permute_configure());
+    MB200_CUDA(tf32_configure());
     // keep stream-ordered temporaries cached in the pool instead of returning them to the OS
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {

@@ -9,6 +9,8 @@
 // One thread per output element (grid-stride): decode the element's digits over C's walk modes
 // (left, right, batch) to get base offsets in A, B and C, then run the summed modes with the
 // fastest one as a plain strided inner loop.
+#include <algorithm>
+
 #include "kernels.cuh"
 
 namespace mb200 {
@@ -72,6 +74,68 @@ __global__ void __launch_bounds__(256) direct_kernel(const __grid_constant__ Dir
     }
 }
 
+// Few outputs, long sums (inner products, norms <psi|psi>, isometry checks): one thread per output would serialise
+// the whole sum. Here blockIdx.y cuts the summed range into `nsplit` slices; each CTA reduces its slice of one
+// output with a strided loop + warp shuffles and adds the partial with atomics (C is zeroed first by zero_kernel).
+template <typename T> struct Scalar;
+template <> struct Scalar<float> { using type = float; static constexpr int N = 1; };
+template <> struct Scalar<double> { using type = double; static constexpr int N = 1; };
+template <> struct Scalar<float2> { using type = float; static constexpr int N = 2; };
+template <> struct Scalar<double2> { using type = double; static constexpr int N = 2; };
+__device__ __forceinline__ float comp(const float &v, int) { return v; }
+__device__ __forceinline__ double comp(const double &v, int) { return v; }
+__device__ __forceinline__ float comp(const float2 &v, int i) { return i ? v.y : v.x; }
+__device__ __forceinline__ double comp(const double2 &v, int i) { return i ? v.y : v.x; }
+
+template <typename T>
+__global__ void __launch_bounds__(256) zero_kernel(const __grid_constant__ DirectParams p, T *__restrict__ C) {
+    const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= p.total_c) return;
+    int64_t r = id, oc = 0;
+    for (int i = 0; i < p.nc; i++) { int64_t e = p.c_ext[i]; oc += (r % e) * p.c_sc[i]; r /= e; }
+    C[oc] = zero_of<T>();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) direct_splitk_kernel(const __grid_constant__ DirectParams p, const T *__restrict__ A,
+                                                            const T *__restrict__ B, T *__restrict__ C) {
+    using S = typename Scalar<T>::type;
+    __shared__ S red[8][2];
+    const int64_t id = blockIdx.x;   // one output element per blockIdx.x
+    int64_t r = id, oa = 0, ob = 0, oc = 0;
+    for (int i = 0; i < p.nc; i++) {
+        int64_t e = p.c_ext[i], d = r % e;
+        r /= e;
+        oa += d * p.c_sa[i]; ob += d * p.c_sb[i]; oc += d * p.c_sc[i];
+    }
+    const int64_t per = (p.total_k + gridDim.y - 1) / gridDim.y;
+    const int64_t k_begin = (int64_t)blockIdx.y * per, k_end = min(p.total_k, k_begin + per);
+    T acc = zero_of<T>();
+    for (int64_t k = k_begin + threadIdx.x; k < k_end; k += blockDim.x) {
+        int64_t q = k, ka = oa, kb = ob;
+        for (int i = 0; i < p.nk; i++) {
+            int64_t e = p.k_ext[i], d = q % e;
+            q /= e;
+            ka += d * p.k_sa[i]; kb += d * p.k_sb[i];
+        }
+        cfma(acc, A[ka], B[kb]);
+    }
+    S part[2] = {comp(acc, 0), Scalar<T>::N == 2 ? comp(acc, 1) : S(0)};
+#pragma unroll
+    for (int c = 0; c < Scalar<T>::N; c++) {
+        S v = part[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][c] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < Scalar<T>::N) {
+        S v = 0;
+        for (int w = 0; w < 8; w++) v += red[w][threadIdx.x];
+        atomicAdd(reinterpret_cast<S *>(C + oc) + threadIdx.x, v);
+    }
+}
+
 __global__ void __launch_bounds__(256) table_kernel(int64_t *__restrict__ out, int64_t size,
                                                     const __grid_constant__ TableSpec spec) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -132,6 +196,25 @@ cudaError_t launch_build_table(int64_t *out, int64_t size, const TableSpec &spec
 cudaError_t launch_direct(int dtype, const DirectParams &p, const void *A, const void *B, void *C,
                           cudaStream_t s) {
     if (p.total_c <= 0) return cudaSuccess;
+    // few outputs, long sums: split the summed range over CTAs (two launches: zero C, then reduce + atomics)
+    if (p.total_c <= 2048 && p.total_k >= 8192) {
+        int64_t want = (148 * 8 + p.total_c - 1) / p.total_c;               // ~8 CTAs per SM in total
+        int64_t cap = p.total_k / 2048;                                      // at least 2048 terms per CTA
+        int nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(want, cap), 65535));
+        dim3 grid((unsigned)p.total_c, (unsigned)nsplit);
+        int gz = grid_for(p.total_c, 256);
+#define MB200_SPLITK(T)                                                                       \
+        zero_kernel<T><<<gz, 256, 0, s>>>(p, (T *)C);                                         \
+        direct_splitk_kernel<T><<<grid, 256, 0, s>>>(p, (const T *)A, (const T *)B, (T *)C)
+        switch (dtype) {
+            case MB200_F32: MB200_SPLITK(float); break;
+            case MB200_F64: MB200_SPLITK(double); break;
+            case MB200_C64: MB200_SPLITK(float2); break;
+            default: MB200_SPLITK(double2); break;
+        }
+#undef MB200_SPLITK
+        return cudaGetLastError();
+    }
     int g = grid_for(p.total_c, 256);
     switch (dtype) {
         case MB200_F32: direct_kernel<float><<<g, 256, 0, s>>>(p, (const float *)A, (const float *)B, (float *)C); break;

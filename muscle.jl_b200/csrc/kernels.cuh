@@ -57,6 +57,8 @@ struct GettParams {
 cudaError_t launch_gett_f64(int dtype, const GettParams &p, cudaStream_t s);   // F64 / C128, DMMA
 cudaError_t launch_simt_f32(int dtype, const GettParams &p, cudaStream_t s);   // F32 / C64, FFMA
 cudaError_t gett_configure();  // opt-in shared memory attributes; call once per device
+cudaError_t permute_configure();
+cudaError_t tf32_configure();
 
 cudaError_t launch_reduce_slots(int dtype, void *out, const void *staging, int64_t slab_elems, int nslots, cudaStream_t s);
 

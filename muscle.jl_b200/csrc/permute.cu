@@ -365,18 +365,8 @@ cudaError_t launch_permute(int dtype, const PermuteParams &q, const void *src, v
         if (k.direct) {                                                                                       \
             permute_direct_kernel<E, S, P><<<ntiles, PT_THREADS, 0, s>>>(k, (const E *)src, dst);             \
         } else if (PERSIST_OK && full_tile) {                                                                 \
-            static bool cfg = false;                                                                          \
-            if (!cfg) {                                                                                       \
-                cudaFuncSetAttribute(permute_tiled_kernel<E, S, P, NE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); \
-                cfg = true;                                                                                   \
-            }                                                                                                 \
             permute_tiled_kernel<E, S, P, NE><<<pgrid, PT_THREADS, 2 * smem, s>>>(k, ntiles, (const E *)src, dst); \
         } else {                                                                                              \
-            static bool cfg2 = false;                                                                         \
-            if (!cfg2) {                                                                                      \
-                cudaFuncSetAttribute(permute_simple_kernel<E, S, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); \
-                cfg2 = true;                                                                                  \
-            }                                                                                                 \
             permute_simple_kernel<E, S, P><<<ntiles, PT_THREADS, smem, s>>>(k, (const E *)src, dst);          \
         }                                                                                                     \
     } while (0)
@@ -392,6 +382,22 @@ cudaError_t launch_permute(int dtype, const PermuteParams &q, const void *src, v
     }
 #undef MB200_PERM
     return cudaGetLastError();
+}
+
+// opt-in shared memory sizes of every permute instantiation; called once per device from mb200_create
+cudaError_t permute_configure() {
+    cudaError_t e = cudaSuccess;
+#define MB200_PCFG(E, S, P)                                                                                              \
+    do {                                                                                                                 \
+        constexpr int NE = (int)((32 * 1024 / sizeof(E)) / PT_THREADS);                                                  \
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(permute_tiled_kernel<E, S, P, NE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); \
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(permute_simple_kernel<E, S, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);    \
+    } while (0)
+    MB200_PCFG(float, float, 0); MB200_PCFG(double, double, 0);
+    MB200_PCFG(float2, float, 0); MB200_PCFG(float2, float, 1); MB200_PCFG(float2, float, 2);
+    MB200_PCFG(double2, double, 0); MB200_PCFG(double2, double, 1);
+#undef MB200_PCFG
+    return e;
 }
 
 }  // namespace mb200

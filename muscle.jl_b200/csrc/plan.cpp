@@ -228,7 +228,10 @@ int make_plan(const TensorDesc &A, const TensorDesc &B, TensorDesc &C, const int
     bool tables_ok = plan.M <= TABLE_LIMIT && plan.N <= TABLE_LIMIT && plan.K <= TABLE_LIMIT &&
                      plan.L <= TABLE_LIMIT;
     int path;
-    if (plan.empty_output || macs <= (double)(1 << 20) || plan.K <= 2 || !tables_ok)
+    // few outputs with a long sum (inner products, norms): the direct kernel's split-K form parallelises over K
+    const bool dot_like = plan.M * plan.N * plan.L <= 2048 && plan.M * plan.N <= 64 * 64 && plan.K >= 8192 &&
+                          (plan.M < 16 || plan.N < 16);
+    if (plan.empty_output || macs <= (double)(1 << 20) || plan.K <= 2 || !tables_ok || dot_like)
         path = MB200_PATH_DIRECT;
     else if (dtype_is_double(plan.dtype))
         path = MB200_PATH_GETT_F64;

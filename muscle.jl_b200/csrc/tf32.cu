@@ -352,12 +352,6 @@ cudaError_t launch_bn(const void *packA, const void *packB, const GettParams &g,
     if (ntiles <= 0) return cudaSuccess;
     p.ntiles = ntiles;
     const int64_t grid = ntiles < 148 ? ntiles : 148;   // persistent: one CTA per SM
-    static bool cfg = false;
-    if (!cfg) {
-        cudaError_t e = cudaFuncSetAttribute(tf32_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tf32Smem<BN>::TOTAL);
-        if (e != cudaSuccess) return e;
-        cfg = true;
-    }
     tf32_gemm_kernel<BN><<<(unsigned)grid, TTHREADS, Tf32Smem<BN>::TOTAL, s>>>(mapA, mapB, p);
     return cudaGetLastError();
 }
@@ -365,6 +359,13 @@ cudaError_t launch_bn(const void *packA, const void *packB, const GettParams &g,
 }  // namespace
 
 bool tf32_available() { return encode_fn() != nullptr; }
+
+// opt-in shared memory sizes; called once per device from mb200_create
+cudaError_t tf32_configure() {
+    cudaError_t e = cudaFuncSetAttribute(tf32_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tf32Smem<128>::TOTAL);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(tf32_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tf32Smem<64>::TOTAL);
+}
 
 // C (ComplexF32, scattered through rowC/colC/batC) = packA [L][M][4K] x packB [L][N][4K]^T, K % 8 == 0
 cudaError_t launch_tf32_gemm(const void *packA, const void *packB, const GettParams &g, cudaStream_t s) {

@@ -471,3 +471,28 @@ def test_qubit_style_tensors(case, dt):
             assert h.stats()["launches_tcgen05"] == 1, (name, h.stats())   # eligible: 2*2*2 / 4*2 tile the 8-k group
         assert got.shape == ref.shape
         assert rel_frobenius(got, ref) <= TOL[dt], (name, dt, path)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_dot_like_split_k(dt):
+    """Few outputs, long sums (norms, inner products, isometry checks — src/Tensor.jl:520-536): split-K direct kernel."""
+    rng = np.random.default_rng(8)
+    h = _lib.Handle.get()
+    # <psi|phi>: full contraction of two rank-4 tensors, K = 32^4 = 1 048 576
+    a = random_array(rng, (32, 32, 32, 32), dt)
+    b = random_array(rng, (32, 32, 32, 32), dt)
+    h.reset_stats()
+    got = contract(a, "ijkl", b, "lkji", "")
+    assert h.stats()["launches_direct"] == 1
+    ref = np.einsum("ijkl,lkji->", a.astype(np.complex128), b.astype(np.complex128))
+    assert got.shape == () and abs(complex(got) - ref) <= (1e-5 if dt in ("float32", "complex64") else 1e-12) * max(abs(ref), np.sqrt(a.size))
+    # a few outputs: C[i] = sum_{jkl} A[i,j,k,l] B[l,k,j], M = 5
+    a = random_array(rng, (5, 64, 64, 16), dt)
+    b = random_array(rng, (16, 64, 64), dt)
+    got = contract(a, "ijkl", b, "lkj", "i")
+    ref = np.einsum("ijkl,lkj->i", a.astype(np.complex128), b.astype(np.complex128))
+    assert rel_frobenius(got.astype(np.complex128), ref) <= TOL[dt]
+    # integer data: exact
+    ai, bi = integer_array(rng, (3, 4096, 4), dt), integer_array(rng, (4, 4096, 2), dt)
+    got = contract(ai, "ikl", bi, "lkj", "ji")
+    assert np.array_equal(got, binary_einsum_general(list("ji"), ai, list("ikl"), bi, list("lkj")))

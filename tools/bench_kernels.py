@@ -89,6 +89,13 @@ def main():
     E.append(einsum_case("cfg4a rank6 dim16", e4, "adbecf", "fgdhei", "abcghi", "complex128"))
     e5 = {c: 8 for c in "abcdefghpqrs"}
     E.append(einsum_case("cfg5 rank8 dim8 c64 (unsliced)", e5, "aebfcgdh", "hpgqfres", "srqpdcba", "complex64"))
+    # quantum-circuit style: rank-24 x rank-24 over dim-2 indices, 12 shared (4096^3 GEMM-equivalent), interleaved labels
+    la = "aAbBcCdDeEfFgGhHiIjJkKlL"                      # lower-case free, upper-case shared, alternating in memory
+    lb = "AmBnCoDpEqFrGsHtIuJvKwLx"
+    lc = "mabncdopefqrghstijuvklwx"
+    eq = {c: 2 for c in set(la + lb)}
+    E.append(einsum_case("qubit rank-24 dim-2 c128 (interleaved)", eq, la, lb, lc, "complex128"))
+    E.append(einsum_case("qubit rank-24 dim-2 c64 (interleaved)", eq, la, lb, lc, "complex64"))
     E.append(einsum_case("dgemm 8192^3 f64", dict(i=8192, j=8192, k=8192), "ik", "kj", "ij", "float64", iters=3))
     E.append(einsum_case("sgemm 8192^3 f32", dict(i=8192, j=8192, k=8192), "ik", "kj", "ij", "float32", iters=3))
     # launch-bound tiny contraction (everything in the reference's own test-suite is this size): per-call latency
