@@ -419,6 +419,7 @@ cudaError_t configure() {
 
 // tile menus ---------------------------------------------------------------------------------------
 using Z_128x64 = CoreZ<128, 64, 32, 32, 32, 2>;  // main ComplexF64 tile: 8 warps x (32 x 32); long k-blocks: one CTA barrier per 32 k
+using Z_128x64k8 = CoreZ<128, 64, 32, 32, 8, 4>; // short K (<= 16): do not zero-fill a 32-deep k-block
 using Z_128x16 = CoreZ<128, 16, 16, 16, 8, 4>;   // skinny N
 using Z_128x16s = CoreZ<128, 16, 32, 16, 8, 2>;  // skinny N and short K (MPS-MPO middle step: N = K = 16): 4 warps, 2 stages -> 4-5 CTAs/SM
 using Z_16x128 = CoreZ<16, 128, 16, 16, 8, 4>;   // skinny M
@@ -437,7 +438,7 @@ using S_16x128 = CoreF<float, 16, 128, 8, 4>;
 cudaError_t gett_configure() {
     cudaError_t e;
 #define MB200_CFG(C) if ((e = configure<C>()) != cudaSuccess) return e
-    MB200_CFG(Z_128x64); MB200_CFG(Z_128x16); MB200_CFG(Z_128x16s); MB200_CFG(Z_16x128);
+    MB200_CFG(Z_128x64); MB200_CFG(Z_128x64k8); MB200_CFG(Z_128x16); MB200_CFG(Z_128x16s); MB200_CFG(Z_16x128);
     MB200_CFG(D_128x128); MB200_CFG(D_128x16); MB200_CFG(D_16x128);
     MB200_CFG(C_128x64); MB200_CFG(C_128x16); MB200_CFG(C_16x128);
     MB200_CFG(S_128x128); MB200_CFG(S_128x16); MB200_CFG(S_16x128);
@@ -449,7 +450,7 @@ cudaError_t launch_gett_f64(int dtype, const GettParams &p, cudaStream_t s) {
     if (dtype == MB200_C128) {
         if (p.N <= 16 && p.M > 16) return p.K <= 32 ? launch<Z_128x16s>(p, s) : launch<Z_128x16>(p, s);
         if (p.M <= 16 && p.N > 16) return launch<Z_16x128>(p, s);
-        return launch<Z_128x64>(p, s);
+        return p.K <= 16 ? launch<Z_128x64k8>(p, s) : launch<Z_128x64>(p, s);
     }
     if (p.N <= 16 && p.M > 16) return launch<D_128x16>(p, s);
     if (p.M <= 16 && p.N > 16) return launch<D_16x128>(p, s);
