@@ -17,6 +17,8 @@
 //   CoreC / CoreS : ComplexF32 / Float32 on FFMA (used for shapes the tcgen05 path does not take).
 //
 // Pipeline: STAGES-deep cp.async ring over k-blocks of BK, one __syncthreads per k-block.
+#include <algorithm>
+
 #include "kernels.cuh"
 
 namespace mb200 {
@@ -402,6 +404,114 @@ __global__ void __launch_bounds__(Core::NTHREADS, Core::NTHREADS <= 128 ? 4 : 1)
     Core::store(acc, reinterpret_cast<E *>(p.C), sRowC, sColC, cb, mrem, nrem, warp, lane, p.sc);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Streaming variant for "a small operator applied to a huge tensor" (N <= BN, K <= 32, no batch): the MPS-MPO
+// middle step (1 048 576 x 16 x 16) and gate application. HBM-bound (AI ~ 4 flop/B), so the structure is a copy
+// kernel with a DMMA in the middle: persistent CTAs, the whole B operand resident in shared memory, and a software
+// pipeline over row tiles — while tile i is multiplied and stored, the elements of tile i+1 and the row-offset
+// tables of tile i+2 are in flight (cp.async), so no tile ever exposes its load latency.
+template <class Core>
+__global__ void __launch_bounds__(Core::NTHREADS, 4) stream_kernel(const __grid_constant__ GettParams p, int kpad) {
+    using E = typename Core::Elem;
+    constexpr int BM = Core::BM, BN = Core::BN, LDA = Core::LDA, LDB = Core::LDB, NT = Core::NTHREADS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    E *sA = reinterpret_cast<E *>(smem_raw);                       // [2][kpad][LDA]
+    E *sB = sA + (size_t)2 * kpad * LDA;                           // [kpad][LDB]
+    int64_t *sRowA = reinterpret_cast<int64_t *>(sB + (size_t)kpad * LDB);   // [3][BM]
+    int64_t *sRowC = sRowA + 3 * BM;                               // [3][BM]
+    int64_t *sColC = sRowC + 3 * BM;                               // [BN]
+    int64_t *sKA = sColC + BN;                                     // [kpad] byte offsets, -1 past K
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t ntiles = (p.M + BM - 1) / BM;
+    const int nrem = (int)p.N;
+    const E *gA = reinterpret_cast<const E *>(p.A) + p.batA[0];
+    const E *gB = reinterpret_cast<const E *>(p.B) + p.batB[0];
+    const int64_t cb = p.batC[0];
+
+    // resident operand and tables
+    for (int i = tid; i < kpad * BN; i += NT) {
+        const int n = i % BN, k = i / BN;
+        E v{};
+        if (n < p.N && k < p.K) v = gB[p.colB[n] + p.kB[k]];
+        sB[k * LDB + n] = v;
+    }
+    for (int i = tid; i < BN; i += NT) sColC[i] = i < p.N ? p.colC[i] : 0;
+    for (int i = tid; i < kpad; i += NT) sKA[i] = i < p.K ? p.kA[i] * (int64_t)sizeof(E) : -1;
+
+    auto issue_tables = [&](int64_t tile, int slot) {      // 8-byte cp.async of the tile's row offsets
+        const int64_t m0 = tile * BM;
+        for (int i = tid; i < BM; i += NT) {
+            const bool v = m0 + i < p.M;
+            const unsigned da = (unsigned)__cvta_generic_to_shared(sRowA + slot * BM + i);
+            const unsigned dc = (unsigned)__cvta_generic_to_shared(sRowC + slot * BM + i);
+            const int bytes = v ? 8 : 0;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(da), "l"(p.rowA + (v ? m0 + i : 0)), "r"(bytes));
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dc), "l"(p.rowC + (v ? m0 + i : 0)), "r"(bytes));
+        }
+    };
+    auto issue_elements = [&](int64_t tile, int stage, int slot) {
+        const int mrem = (int)min((int64_t)BM, p.M - tile * BM);
+        const int64_t *rows = sRowA + slot * BM;
+        E *dstb = sA + (size_t)stage * kpad * LDA;
+        for (int i = tid; i < BM * kpad; i += NT) {
+            int m, k;
+            if (p.a_kmajor) { k = i % kpad; m = i / kpad; } else { m = i % BM; k = i / BM; }
+            const int64_t ko = sKA[k];
+            const bool v = m < mrem && ko >= 0;
+            const char *src = reinterpret_cast<const char *>(gA) + (v ? rows[m] * (int64_t)sizeof(E) + ko : 0);
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(dstb + k * LDA + m);
+            const int bytes = v ? (int)sizeof(E) : 0;
+            if constexpr (sizeof(E) == 16)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes));
+            else
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(bytes));
+        }
+    };
+
+    int64_t t0 = blockIdx.x;
+    if (t0 >= ntiles) return;
+    issue_tables(t0, 0);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();                                        // tables(t0), sB, sKA, sColC visible
+    issue_elements(t0, 0, 0);
+    if (t0 + gridDim.x < ntiles) issue_tables(t0 + gridDim.x, 1);
+    cp_async_commit();
+    int it = 0;
+    for (int64_t tile = t0; tile < ntiles; tile += gridDim.x, it++) {
+        cp_async_wait<0>();
+        __syncthreads();                                    // elements(tile) and tables(next) landed; previous tile's readers done
+        const int64_t nxt = tile + gridDim.x, nxt2 = nxt + gridDim.x;
+        if (nxt < ntiles) issue_elements(nxt, (it + 1) & 1, (it + 1) % 3);
+        if (nxt2 < ntiles) issue_tables(nxt2, (it + 2) % 3);
+        cp_async_commit();
+        typename Core::Acc acc;
+        Core::init(acc);
+        const E *a = sA + (size_t)(it & 1) * kpad * LDA;
+        for (int kb = 0; kb < kpad; kb += Core::BK)
+            Core::compute(acc, a + (size_t)kb * LDA, sB + (size_t)kb * LDB, warp, lane, [](int) {});
+        const int mrem = (int)min((int64_t)BM, p.M - tile * BM);
+        Core::store(acc, reinterpret_cast<E *>(p.C), sRowC + (it % 3) * BM, sColC, cb, mrem, nrem, warp, lane, p.sc);
+    }
+    cp_async_wait<0>();
+}
+
+template <class Core>
+cudaError_t launch_stream(const GettParams &p, cudaStream_t s) {
+    using E = typename Core::Elem;
+    const int kpad = (int)((p.K + Core::BK - 1) / Core::BK) * Core::BK;
+    const size_t smem = ((size_t)2 * kpad * Core::LDA + (size_t)kpad * Core::LDB) * sizeof(E) +
+                        (size_t)(6 * Core::BM + Core::BN + kpad) * sizeof(int64_t);
+    const int64_t ntiles = (p.M + Core::BM - 1) / Core::BM;
+    const int64_t grid = std::min<int64_t>(ntiles, 148 * 5);
+    stream_kernel<Core><<<(unsigned)grid, Core::NTHREADS, smem, s>>>(p, kpad);
+    return cudaGetLastError();
+}
+template <class Core>
+cudaError_t configure_stream() {
+    return cudaFuncSetAttribute(stream_kernel<Core>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+}
+
 template <class Core>
 cudaError_t launch(const GettParams &p, cudaStream_t s) {
     const int64_t tiles_m = (p.M + Core::BM - 1) / Core::BM, tiles_n = (p.N + Core::BN - 1) / Core::BN;
@@ -422,6 +532,7 @@ using Z_128x64 = CoreZ<128, 64, 32, 32, 32, 2>;  // main ComplexF64 tile: 8 warp
 using Z_128x64k8 = CoreZ<128, 64, 32, 32, 8, 4>; // short K (<= 16): do not zero-fill a 32-deep k-block
 using Z_128x16 = CoreZ<128, 16, 16, 16, 8, 4>;   // skinny N
 using Z_128x16s = CoreZ<128, 16, 32, 16, 8, 2>;  // skinny N and short K (MPS-MPO middle step: N = K = 16): 4 warps, 2 stages -> 4-5 CTAs/SM
+using Z_64x16t = CoreZ<64, 16, 16, 16, 8, 2>;    // streaming kernel tile: 4 warps x (16 x 16), ~42 KB smem -> 5 CTAs/SM
 using Z_16x128 = CoreZ<16, 128, 16, 16, 8, 4>;   // skinny M
 using D_128x128 = CoreD<128, 128, 64, 32, 16, 3>; // Float64: 8 warps x (64 x 32)
 using D_128x16 = CoreD<128, 16, 16, 16, 8, 4>;
@@ -438,6 +549,7 @@ using S_16x128 = CoreF<float, 16, 128, 8, 4>;
 cudaError_t gett_configure() {
     cudaError_t e;
 #define MB200_CFG(C) if ((e = configure<C>()) != cudaSuccess) return e
+    if ((e = configure_stream<Z_64x16t>()) != cudaSuccess) return e;
     MB200_CFG(Z_128x64); MB200_CFG(Z_128x64k8); MB200_CFG(Z_128x16); MB200_CFG(Z_128x16s); MB200_CFG(Z_16x128);
     MB200_CFG(D_128x128); MB200_CFG(D_128x16); MB200_CFG(D_16x128);
     MB200_CFG(C_128x64); MB200_CFG(C_128x16); MB200_CFG(C_16x128);
@@ -448,6 +560,7 @@ cudaError_t gett_configure() {
 
 cudaError_t launch_gett_f64(int dtype, const GettParams &p, cudaStream_t s) {
     if (dtype == MB200_C128) {
+        if (p.N <= 16 && p.K <= 32 && p.L == 1 && p.M >= 4096) return launch_stream<Z_64x16t>(p, s);   // streaming, HBM-bound
         if (p.N <= 16 && p.M > 16) return p.K <= 32 ? launch<Z_128x16s>(p, s) : launch<Z_128x16>(p, s);
         if (p.M <= 16 && p.N > 16) return launch<Z_16x128>(p, s);
         return p.K <= 16 ? launch<Z_128x64k8>(p, s) : launch<Z_128x64>(p, s);
