@@ -293,7 +293,7 @@ def run_ours(args):
                 "traffic": traffic, "peak_source": FP64_PEAK_SOURCE,
                 "flops_per_launch": dom_flops, "ms_per_launch": dom_ms,
                 "share_of_step": (t2a + t2c) / (t2a + t2b + t2c)}
-    roofline_2b = {"bound": "hbm", "kernel": "gett_kernel<CoreZ<128,16,16,16,8,4>> (step 2b, N=K=16)",
+    roofline_2b = {"bound": "hbm", "kernel": "stream_kernel<CoreZ<64,16,16,16,8,2>> (step 2b, N=K=16: persistent, B resident in smem, tile pipeline)",
                    "achieved": bytes_2b / (t2b * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                    "frac": bytes_2b / (t2b * 1e-3) / 1e9 / hbm_peak, "bytes_per_launch": bytes_2b, "ms_per_launch": t2b,
                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}

@@ -496,3 +496,28 @@ def test_dot_like_split_k(dt):
     ai, bi = integer_array(rng, (3, 4096, 4), dt), integer_array(rng, (4, 4096, 2), dt)
     got = contract(ai, "ikl", bi, "lkj", "ji")
     assert np.array_equal(got, binary_einsum_general(list("ji"), ai, list("ikl"), bi, list("lkj")))
+
+
+@pytest.mark.parametrize("dt", ["complex128", "complex64"])
+def test_gate_application_streaming_shape(dt):
+    """A 2-qubit gate applied to a 20-qubit state: M = 2^18 free rows, N = K = 4 — the streaming kernel's shape
+    (ComplexF64) / the skinny FFMA tile (ComplexF32); also the qiskit CX check of test/python/qiskit.jl:33-41 in spirit."""
+    nq = 20
+    rng = np.random.default_rng(12)
+    psi = random_array(rng, (2,) * nq, dt)
+    gate = random_array(rng, (2, 2, 2, 2), dt)                 # [o1, o2, i1, i2]
+    labels = [f"q{i}" for i in range(nq)]
+    q1, q2 = 3, 11
+    ia = ["o1", "o2", labels[q1], labels[q2]]
+    ic = list(labels)
+    ic[q1], ic[q2] = "o1", "o2"
+    tg = Tensor(gate, [Index(x) for x in ia]).to_device()
+    tp = Tensor(psi, [Index(x) for x in labels]).to_device()
+    h = _lib.Handle.get()
+    h.reset_stats()
+    got = binary_einsum(tg, tp, out=[Index(x) for x in ic]).to_host().data
+    assert h.stats()["launches_gett_f64" if dt == "complex128" else "launches_simt_f32"] == 1
+    perm_in = "abcdefghijklmnopqrst"
+    sub = perm_in.replace(perm_in[q1], "X").replace(perm_in[q2], "Y")
+    ref = np.einsum(f"XY{perm_in[q1]}{perm_in[q2]},{perm_in}->{sub}", gate.astype(np.complex128), psi.astype(np.complex128))
+    assert rel_frobenius(got.astype(np.complex128), ref) <= TOL[dt]
