@@ -24,6 +24,8 @@ struct CachedPlan {
     int64_t *tables = nullptr;  // one device allocation: rowA rowC colB colC kA kB batA batB batC
     GettParams gp{};
     DirectParams dp{};
+    ApplyParams ap{};
+    bool use_apply = false, apply_big_is_row = true;
     std::list<std::string>::iterator lru;
 };
 
@@ -79,10 +81,10 @@ int build_cached(mb200_handle_t h, CachedPlan &cp) {
             d.c_sb[d.nc] = in_b ? g.sb : 0;
             d.nc++;
         };
-        for (auto &g : p.left) add_c(g, true, false);
-        for (auto &g : p.right) add_c(g, false, true);
-        for (auto &g : p.batch) add_c(g, true, true);
-        for (auto &g : p.sum) {
+        for (auto &g : p.mleft) add_c(g, true, false);
+        for (auto &g : p.mright) add_c(g, false, true);
+        for (auto &g : p.mbatch) add_c(g, true, true);
+        for (auto &g : p.msum) {
             d.k_ext[d.nk] = g.extent;
             d.k_sa[d.nk] = g.sa;
             d.k_sb[d.nk] = g.sb;
@@ -90,6 +92,39 @@ int build_cached(mb200_handle_t h, CachedPlan &cp) {
         }
         d.total_c = p.M * p.N * p.L;
         d.total_k = p.K;
+        if (p.apply_like && !p.empty_output && p.M * p.N > 0) {
+            // big operand = the one with the large free group; the other one is the (<= 8 x 8) operator
+            const bool big_row = p.M >= p.N;
+            const std::vector<GroupMode> &big = big_row ? p.mleft : p.mright;
+            const std::vector<GroupMode> &small = big_row ? p.mright : p.mleft;
+            ApplyParams &a = cp.ap;
+            std::memset(&a, 0, sizeof a);
+            a.nbig = (int)big.size();
+            a.total_big = big_row ? p.M : p.N;
+            for (int i = 0; i < a.nbig; i++) {
+                a.big_ext[i] = big[i].extent;
+                a.big_sx[i] = big_row ? big[i].sa : big[i].sb;
+                a.big_sc[i] = big[i].sc;
+            }
+            auto enumerate = [](const std::vector<GroupMode> &g, int which, int64_t *out, int64_t n) {
+                for (int64_t x = 0; x < n; x++) {
+                    int64_t r = x, off = 0;
+                    for (const GroupMode &m : g) {
+                        off += (r % m.extent) * (which == 0 ? m.sa : (which == 1 ? m.sb : m.sc));
+                        r /= m.extent;
+                    }
+                    out[x] = off;
+                }
+            };
+            a.J = (int)(big_row ? p.N : p.M);
+            a.K = (int)p.K;
+            enumerate(small, big_row ? 1 : 0, a.js, a.J);
+            enumerate(small, 2, a.jc, a.J);
+            enumerate(p.msum, big_row ? 0 : 1, a.kx, a.K);
+            enumerate(p.msum, big_row ? 1 : 0, a.ks, a.K);
+            cp.use_apply = true;
+            cp.apply_big_is_row = big_row;
+        }
         return MB200_OK;
     }
     // gather-GEMM: offset tables, built on the device, cached with the plan
@@ -107,15 +142,15 @@ int build_cached(mb200_handle_t h, CachedPlan &cp) {
     int64_t *batB = t; t += L;
     int64_t *batC = t; t += L;
     cudaStream_t s = h->stream;
-    MB200_CUDA(launch_build_table(rowA, M, spec_of(p.left, 0), s));
-    MB200_CUDA(launch_build_table(rowC, M, spec_of(p.left, 2), s));
-    MB200_CUDA(launch_build_table(colB, N, spec_of(p.right, 1), s));
-    MB200_CUDA(launch_build_table(colC, N, spec_of(p.right, 2), s));
-    MB200_CUDA(launch_build_table(kA, K, spec_of(p.sum, 0), s));
-    MB200_CUDA(launch_build_table(kB, K, spec_of(p.sum, 1), s));
-    MB200_CUDA(launch_build_table(batA, L, spec_of(p.batch, 0), s));
-    MB200_CUDA(launch_build_table(batB, L, spec_of(p.batch, 1), s));
-    MB200_CUDA(launch_build_table(batC, L, spec_of(p.batch, 2), s));
+    MB200_CUDA(launch_build_table(rowA, M, spec_of(p.mleft, 0), s));
+    MB200_CUDA(launch_build_table(rowC, M, spec_of(p.mleft, 2), s));
+    MB200_CUDA(launch_build_table(colB, N, spec_of(p.mright, 1), s));
+    MB200_CUDA(launch_build_table(colC, N, spec_of(p.mright, 2), s));
+    MB200_CUDA(launch_build_table(kA, K, spec_of(p.msum, 0), s));
+    MB200_CUDA(launch_build_table(kB, K, spec_of(p.msum, 1), s));
+    MB200_CUDA(launch_build_table(batA, L, spec_of(p.mbatch, 0), s));
+    MB200_CUDA(launch_build_table(batB, L, spec_of(p.mbatch, 1), s));
+    MB200_CUDA(launch_build_table(batC, L, spec_of(p.mbatch, 2), s));
     h->stats.launches_table += 9;
     h->stats.launches_total += 9;
     GettParams &g = cp.gp;
@@ -279,7 +314,10 @@ int contract_device(mb200_handle_t h, void *C, TensorDesc &dC, const int64_t *st
     PermuteParams qa, qb;
     int64_t rows_a = 0, rows_b = 0;
     if (p.path == MB200_PATH_DIRECT) {
-        e = launch_direct(p.dtype, cp->dp, R, Q, C, s);
+        if (cp->use_apply && !sc)
+            e = launch_apply(p.dtype, cp->ap, cp->apply_big_is_row ? R : Q, cp->apply_big_is_row ? Q : R, C, s);
+        else
+            e = launch_direct(p.dtype, cp->dp, R, Q, C, s);
         h->stats.launches_direct++;
     } else if (p.path == MB200_PATH_TCGEN05_TF32 && tf32_available() && build_pack_params(p, 0, qa, rows_a) &&
                build_pack_params(p, 1, qb, rows_b)) {

@@ -136,6 +136,44 @@ __global__ void __launch_bounds__(256) direct_splitk_kernel(const __grid_constan
     }
 }
 
+// "apply": one thread per row of the big operand. The operator (J x K <= 8 x 8) sits in shared memory, the row's K
+// inputs are loaded once, all J outputs are produced from registers; offsets come from a digit decode over the
+// MERGED big-free modes (2-4 modes for a gate on an n-qubit state), so there are no tables and every byte of the
+// big tensor is read once and written once: a streaming kernel.
+template <typename T, int KP, int JP>
+__global__ void __launch_bounds__(256) apply_kernel(const __grid_constant__ ApplyParams p, const T *__restrict__ X,
+                                                    const T *__restrict__ S, T *__restrict__ C) {
+    // KP / JP: K and J rounded up to 2, 4 or 8 at compile time (operator zero-padded) so the inner loops unroll
+    // to exactly the work needed; rows are decoded with 32-bit divisions (total_big < 2^31 is checked on the host)
+    __shared__ T sS[JP][KP];
+    if (threadIdx.x < JP * KP) {
+        const int j = threadIdx.x / KP, k = threadIdx.x % KP;
+        sS[j][k] = (j < p.J && k < p.K) ? S[p.js[j] + p.ks[k]] : zero_of<T>();
+    }
+    __syncthreads();
+    const unsigned total = (unsigned)p.total_big, stride = gridDim.x * blockDim.x;
+    for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r < total; r += stride) {
+        unsigned q = r;
+        int64_t ox = 0, oc = 0;
+        for (int i = 0; i < p.nbig; i++) {
+            const unsigned e = (unsigned)p.big_ext[i], qq = q / e, d = q - qq * e;
+            q = qq;
+            ox += (int64_t)d * p.big_sx[i];
+            oc += (int64_t)d * p.big_sc[i];
+        }
+        T x[KP];
+#pragma unroll
+        for (int k = 0; k < KP; k++) x[k] = (k < p.K) ? X[ox + p.kx[k]] : zero_of<T>();
+#pragma unroll
+        for (int j = 0; j < JP; j++) {
+            T acc = zero_of<T>();
+#pragma unroll
+            for (int k = 0; k < KP; k++) cfma(acc, x[k], sS[j][k]);
+            if (j < p.J) C[oc + p.jc[j]] = acc;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) table_kernel(int64_t *__restrict__ out, int64_t size,
                                                     const __grid_constant__ TableSpec spec) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -223,6 +261,35 @@ cudaError_t launch_direct(int dtype, const DirectParams &p, const void *A, const
         default: direct_kernel<double2><<<g, 256, 0, s>>>(p, (const double2 *)A, (const double2 *)B, (double2 *)C); break;
     }
     return cudaGetLastError();
+}
+
+template <typename T>
+static cudaError_t launch_apply_t(const ApplyParams &p, const void *X, const void *S, void *C, cudaStream_t s) {
+    const int g = grid_for(p.total_big, 256, 148 * 8);
+    const int kp = p.K <= 2 ? 2 : (p.K <= 4 ? 4 : 8), jp = p.J <= 2 ? 2 : (p.J <= 4 ? 4 : 8);
+#define MB200_APPLY(KP, JP) apply_kernel<T, KP, JP><<<g, 256, 0, s>>>(p, (const T *)X, (const T *)S, (T *)C)
+    if (kp == 2 && jp == 2) MB200_APPLY(2, 2);
+    else if (kp == 2 && jp == 4) MB200_APPLY(2, 4);
+    else if (kp == 2) MB200_APPLY(2, 8);
+    else if (kp == 4 && jp == 2) MB200_APPLY(4, 2);
+    else if (kp == 4 && jp == 4) MB200_APPLY(4, 4);
+    else if (kp == 4) MB200_APPLY(4, 8);
+    else if (jp == 2) MB200_APPLY(8, 2);
+    else if (jp == 4) MB200_APPLY(8, 4);
+    else MB200_APPLY(8, 8);
+#undef MB200_APPLY
+    return cudaGetLastError();
+}
+
+cudaError_t launch_apply(int dtype, const ApplyParams &p, const void *X, const void *S, void *C, cudaStream_t s) {
+    if (p.total_big <= 0) return cudaSuccess;
+    if (p.total_big >= ((int64_t)1 << 31)) return cudaErrorInvalidValue;
+    switch (dtype) {
+        case MB200_F32: return launch_apply_t<float>(p, X, S, C, s);
+        case MB200_F64: return launch_apply_t<double>(p, X, S, C, s);
+        case MB200_C64: return launch_apply_t<float2>(p, X, S, C, s);
+        default: return launch_apply_t<double2>(p, X, S, C, s);
+    }
 }
 
 cudaError_t launch_reduce_slots(int dtype, void *out, const void *staging, int64_t slab_elems, int nslots, cudaStream_t s) {

@@ -28,6 +28,17 @@ struct DirectParams {
 cudaError_t launch_direct(int dtype, const DirectParams &p, const void *A, const void *B, void *C,
                           cudaStream_t s);
 
+// ---- apply: a tiny operator (<= 8 x 8) contracted into a huge tensor (gate application, K <= 8, one free side <= 8) ---
+// C[bigC(r) + jc[j]] = sum_k X[bigX(r) + kx[k]] * S[js[j] + ks[k]]   for every row r of the big operand X
+struct ApplyParams {
+    int nbig;
+    int64_t big_ext[MB200_MAX_MODES], big_sx[MB200_MAX_MODES], big_sc[MB200_MAX_MODES];
+    int64_t total_big;
+    int J, K;
+    int64_t kx[8], ks[8], js[8], jc[8];
+};
+cudaError_t launch_apply(int dtype, const ApplyParams &p, const void *X, const void *S, void *C, cudaStream_t s);
+
 // ---- K2 / FP32 SIMT: gather-GEMM ---------------------------------------------------------------------
 // C[rowC[m] + colC[n] + batC[l]] = sum_k A[rowA[m] + kA[k] + batA[l]] * B[colB[n] + kB[k] + batB[l]]
 // All offsets are in ELEMENTS of the compute dtype.

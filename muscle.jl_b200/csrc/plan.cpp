@@ -191,6 +191,25 @@ int make_plan(const TensorDesc &A, const TensorDesc &B, TensorDesc &C, const int
         if (found) plan.sum = cand;
     }
 
+    // merged walk groups: neighbours contiguous in every tensor that carries the group collapse into one mode
+    auto merged = [](const std::vector<GroupMode> &g, bool in_a, bool in_b, bool in_c) {
+        std::vector<GroupMode> out;
+        for (const GroupMode &m : g) {
+            if (!out.empty()) {
+                GroupMode &t = out.back();
+                const bool ok = (!in_a || m.sa == t.sa * t.extent) && (!in_b || m.sb == t.sb * t.extent) &&
+                                (!in_c || m.sc == t.sc * t.extent);
+                if (ok) { t.extent *= m.extent; continue; }
+            }
+            out.push_back(m);
+        }
+        return out;
+    };
+    plan.mleft = merged(plan.left, true, false, true);
+    plan.mright = merged(plan.right, false, true, true);
+    plan.msum = merged(plan.sum, true, true, false);
+    plan.mbatch = merged(plan.batch, true, true, true);
+
     auto prod = [](const std::vector<GroupMode> &g) {
         int64_t p = 1;
         for (auto &x : g) p *= x.extent;
@@ -231,7 +250,12 @@ int make_plan(const TensorDesc &A, const TensorDesc &B, TensorDesc &C, const int
     // few outputs with a long sum (inner products, norms): the direct kernel's split-K form parallelises over K
     const bool dot_like = plan.M * plan.N * plan.L <= 2048 && plan.M * plan.N <= 64 * 64 && plan.K >= 8192 &&
                           (plan.M < 16 || plan.N < 16);
-    if (plan.empty_output || macs <= (double)(1 << 20) || plan.K <= 2 || !tables_ok || dot_like)
+    // a tiny operator applied to a big tensor (gate application): streaming "apply" form of the direct path
+    // (for FP64 types an 8 x 8 operator is better served by the DMMA streaming kernel: 5.5 vs 4.3 TB/s)
+    const int64_t apply_cap = dtype_is_double(plan.dtype) ? 4 : 8;
+    plan.apply_like = plan.K <= apply_cap && std::min(plan.M, plan.N) <= apply_cap && plan.L == 1 && plan.K >= 1 &&
+                      std::max(plan.M, plan.N) < ((int64_t)1 << 31);
+    if (plan.empty_output || macs <= (double)(1 << 20) || plan.K <= 2 || !tables_ok || dot_like || plan.apply_like)
         path = MB200_PATH_DIRECT;
     else if (dtype_is_double(plan.dtype))
         path = MB200_PATH_GETT_F64;

@@ -43,10 +43,14 @@ struct Plan {
     int dtype_col = 0;
     bool swapped = false;   // row operand is the caller's B
     std::vector<GroupMode> left, right, sum, batch;  // extent-1 modes removed, walk order (fastest first)
+    // the same groups with neighbours merged when they are contiguous in every tensor that carries them (a run of
+    // dim-2 indices q0..q12 untouched by a gate becomes one mode of extent 8192): what the kernels actually walk
+    std::vector<GroupMode> mleft, mright, msum, mbatch;
     int64_t M = 1, N = 1, K = 1, L = 1;
     bool a_kmajor = false, b_kmajor = false;
     int path = MB200_PATH_DIRECT;
     bool empty_output = false;  // some C extent is 0
+    bool apply_like = false;    // K <= 8 and one free side <= 8, no batch: the direct path uses its streaming apply kernel
     bool tc_ok = false;         // eligible for the tcgen05 3xTF32 path (dense ComplexF32 operands, leading summed modes tile groups of 8 k)
     double flops = 0, bytes = 0;
     std::string key;  // cache key (all integers of the three descriptors + dtypes + forced path)

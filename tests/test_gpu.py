@@ -498,26 +498,44 @@ def test_dot_like_split_k(dt):
     assert np.array_equal(got, binary_einsum_general(list("ji"), ai, list("ikl"), bi, list("lkj")))
 
 
+@pytest.mark.parametrize("qs", [[7], [0], [3, 11], [0, 1], [18, 19], [2, 9, 15]], ids=lambda q: "q" + "_".join(map(str, q)))
 @pytest.mark.parametrize("dt", ["complex128", "complex64"])
-def test_gate_application_streaming_shape(dt):
-    """A 2-qubit gate applied to a 20-qubit state: M = 2^18 free rows, N = K = 4 — the streaming kernel's shape
-    (ComplexF64) / the skinny FFMA tile (ComplexF32); also the qiskit CX check of test/python/qiskit.jl:33-41 in spirit."""
+def test_gate_application(dt, qs):
+    """1-, 2- and 3-qubit gates applied to a 20-qubit state (M = 2^17..2^19 rows, N = K = 2..8): the streaming apply
+    kernel (tiny operators), the DMMA streaming kernel (8 x 8, ComplexF64); the qiskit CX check of
+    test/python/qiskit.jl:33-41 in spirit. Checked against numpy.einsum."""
     nq = 20
     rng = np.random.default_rng(12)
     psi = random_array(rng, (2,) * nq, dt)
-    gate = random_array(rng, (2, 2, 2, 2), dt)                 # [o1, o2, i1, i2]
+    k = len(qs)
+    gate = random_array(rng, (2,) * (2 * k), dt)                # [o..., i...]
     labels = [f"q{i}" for i in range(nq)]
-    q1, q2 = 3, 11
-    ia = ["o1", "o2", labels[q1], labels[q2]]
+    outs = [f"o{i}" for i in range(k)]
+    ia = outs + [labels[q] for q in qs]
     ic = list(labels)
-    ic[q1], ic[q2] = "o1", "o2"
+    for o, q in zip(outs, qs):
+        ic[q] = o
     tg = Tensor(gate, [Index(x) for x in ia]).to_device()
     tp = Tensor(psi, [Index(x) for x in labels]).to_device()
     h = _lib.Handle.get()
     h.reset_stats()
     got = binary_einsum(tg, tp, out=[Index(x) for x in ic]).to_host().data
-    assert h.stats()["launches_gett_f64" if dt == "complex128" else "launches_simt_f32"] == 1
-    perm_in = "abcdefghijklmnopqrst"
-    sub = perm_in.replace(perm_in[q1], "X").replace(perm_in[q2], "Y")
-    ref = np.einsum(f"XY{perm_in[q1]}{perm_in[q2]},{perm_in}->{sub}", gate.astype(np.complex128), psi.astype(np.complex128))
+    st = h.stats()
+    if k == 3 and dt == "complex128":
+        assert st["launches_gett_f64"] == 1, st                 # 8 x 8 operator: DMMA streaming kernel
+    else:
+        assert st["launches_direct"] == 1, st                   # apply kernel
+    letters = "abcdefghijklmnopqrst"
+    big = "XYZ"
+    sub = letters
+    for o, q in zip(big, qs):
+        sub = sub.replace(letters[q], o)
+    ref = np.einsum(f"{big[:k]}{''.join(letters[q] for q in qs)},{letters}->{sub}", gate.astype(np.complex128), psi.astype(np.complex128))
     assert rel_frobenius(got.astype(np.complex128), ref) <= TOL[dt]
+    # and the same gate through the generic direct kernel must agree bit for bit in placement (integer data)
+    gi, pi = integer_array(rng, gate.shape, dt), integer_array(rng, psi.shape, dt)
+    a1 = contract(gi, ia, pi, labels, ic, path=mb.PATH_AUTO)
+    _lib.Handle.get().set_path(mb.PATH_SIMT_F32 if dt == "complex64" else mb.PATH_GETT_F64)
+    a2 = binary_einsum(BackendB200(), [Index(x) for x in ic], Tensor(gi, [Index(x) for x in ia]).to_device(),
+                       Tensor(pi, [Index(x) for x in labels]).to_device()).to_host().data
+    assert np.array_equal(a1, a2)
