@@ -232,6 +232,10 @@ PERMUTE_CASES = [
     ((16, 16, 16, 16), (3, 2, 1, 0)), ((5, 1, 7, 1, 3), (4, 3, 2, 1, 0)), ((300, 2), (1, 0)), ((2, 300), (1, 0)),
     ((2, 2, 2, 2, 2, 2, 2, 2, 2, 2), (9, 0, 8, 1, 7, 2, 6, 3, 5, 4)), ((12, 10, 8), (0, 1, 2)), ((1000,), (0,)),
     ((7, 130, 5), (0, 2, 1)), ((200, 3, 50), (0, 2, 1)),
+    # register-tile transposition (extents % 4, % 2), ragged tiles, long y tables, widened unit-stride runs
+    ((260, 132), (1, 0)), ((2, 1030, 6), (1, 0, 2)), ((8, 8, 8, 8, 8), (4, 0, 3, 1, 2)), ((4, 6, 10), (2, 1, 0)),
+    ((6, 10, 14), (1, 0, 2)), ((4, 33, 5), (0, 2, 1)), ((8, 10, 12), (0, 2, 1)), ((6, 10, 12), (0, 2, 1)),
+    ((2, 2048, 4), (1, 2, 0)), ((1028, 4, 8), (2, 1, 0)),
 ]
 
 

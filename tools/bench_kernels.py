@@ -75,6 +75,18 @@ def main():
     P.append(permute_case("rank8 dim8 c64 interleave", (8,) * 8, (4, 0, 5, 1, 6, 2, 7, 3), "complex64"))
     P.append(permute_case("cfg3 pack+planar c64 (256,8,8,256,8)->(0,2,3,1,4)", (256, 8, 8, 256, 8), (0, 2, 3, 1, 4), "complex64", 1))
     P.append(permute_case("copy (identity) c128 64^4", (64, 64, 64, 64), (0, 1, 2, 3), "complex128"))
+    P.append(permute_case("rank8 dim8 f32 interleave", (8,) * 9, (4, 0, 5, 1, 6, 2, 7, 3, 8), "float32"))
+    P.append(permute_case("c64 (256,8,8,256,8)->(0,2,3,1,4) plain", (256, 8, 8, 256, 8), (0, 2, 3, 1, 4), "complex64"))
+    P.append(permute_case("c64 (256,8,8,256,8)->(3,1,0,2,4) plain", (256, 8, 8, 256, 8), (3, 1, 0, 2, 4), "complex64"))
+    P.append(permute_case("f64 rank6 dim16 reverse", (16,) * 6 + (2,), (5, 4, 3, 2, 1, 0, 6), "float64"))
+    P.append(permute_case("qubit rank-26 c64 bit reversal", (2,) * 26, tuple(range(25, -1, -1)), "complex64") if False else
+             permute_case("qubit rank-16 (dim 2 x13, 4096 tail) c64 reversal", (2,) * 13 + (4096,), tuple(range(13, -1, -1)), "complex64"))
+    if "--permute-only" in sys.argv:
+        for r in P:
+            print(f"PERMUTE {r['name']:<60s} {r['gbs_best']:8.0f} GB/s best {r['gbs_mean']:8.0f} mean")
+        os.makedirs("gpurun_out", exist_ok=True)
+        json.dump(out, open("gpurun_out/kernels_permute%s.json" % os.environ.get("MB200_PERMUTE_REGT", ""), "w"), indent=1)
+        return
     E = out["einsum"]
     e64 = dict(i=64, j=64, k=64, l=64, m=64, n=64)
     E.append(einsum_case("cfg1 aligned  A[i,j,k,l] B[k,l,m,n] -> [i,j,m,n]", e64, "ijkl", "klmn", "ijmn", "complex128"))
