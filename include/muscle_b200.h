@@ -138,6 +138,27 @@ int mb200_plan_describe(int dtypeC, int nmodeC, const int32_t *modesC, const int
 int mb200_permute(mb200_handle_t handle, void *dst, const void *src, int dtype, int nmode,
                   const int64_t *extents, const int32_t *perm, uint32_t flags);
 
+/* ---- the einsum family next to the hot path -----------------------------------
+ * unary_einsum: Y[modesY] = sum over the modes of X absent from Y; a mode REPEATED inside X is read on its
+ * diagonal (trace / diagonal extraction). Replaces `unary_einsum(!)(::BackendOMEinsum, y, x)`
+ * (ext/MuscleOMEinsumExt.jl:25-38 -> OMEinsum.einsum!; front-end src/Operations/unary_einsum.jl:26-46).
+ * INVALID_ARGUMENT: a mode of Y not in X ("Output indices must be a subset of input indices",
+ * MuscleOMEinsumExt.jl:32), a mode repeated inside Y, dtypeY != dtypeX. DIMENSION_MISMATCH: a repeated mode
+ * of X with different extents. Device pointers; strides NULL = dense column-major. */
+int mb200_unary_einsum(mb200_handle_t handle,
+                       void *Y, int dtypeY, int nmodeY, const int32_t *modesY, const int64_t *stridesY,
+                       const void *X, int dtypeX, int nmodeX, const int32_t *modesX,
+                       const int64_t *extentsX, const int64_t *stridesX);
+
+/* hadamard: C = A .* broadcast(B), modes(B) a subset of modes(A) in any order; C has A's extents and layout
+ * (dense column-major) and dtype promote(A, B); C may alias A when dtypeA == dtypeC. Replaces
+ * `hadamard!(::BackendBase, c, a, b)` (src/Operations/hadamard.jl:50-77: permutedims of b + reshape +
+ * broadcast multiply). INVALID_ARGUMENT: a mode of B not in A (hadamard.jl:10,29), repeated modes;
+ * DIMENSION_MISMATCH: extents of a shared mode differ. */
+int mb200_hadamard(mb200_handle_t handle, void *C, int dtypeC,
+                   const void *A, int dtypeA, int nmodeA, const int32_t *modesA, const int64_t *extentsA,
+                   const void *B, int dtypeB, int nmodeB, const int32_t *modesB, const int64_t *extentsB);
+
 /* ---- multi-GPU partition planner (host only) ------------------------------------------------
  * One process per GPU (torch.distributed / NCCL does the plumbing). Mirrors Dagger's block
  * sharding, ext/MuscleDaggerExt/binary_einsum.jl:64-119: splitting a free or batch mode gives
@@ -182,12 +203,25 @@ int mb200_binary_einsum_scatter(mb200_handle_t handle,
 int mb200_reduce_slots(mb200_handle_t handle, void *out, const void *staging_local, int dtype,
                        int64_t slab_elems, int nslots);
 
+/* ---- CUDA-graph replay of a fixed sequence of calls (n-ary contraction chains) ------------
+ * Everything enqueued on the handle's stream between graph_begin and graph_end (binary_einsum, unary_einsum,
+ * hadamard, permute ... on fixed device pointers) is captured instead of executed and can then be replayed with one
+ * launch: a launch-bound chain of small contractions costs one graph launch instead of one kernel launch (plus
+ * planner work) per step. The handle's stream must not be the legacy default stream. Every plan the sequence needs
+ * must already be cached (run the sequence once before capturing): a plan miss during capture is NOT_SUPPORTED. */
+typedef struct mb200_graph_s *mb200_graph_t;
+int mb200_graph_begin(mb200_handle_t handle);
+int mb200_graph_end(mb200_handle_t handle, mb200_graph_t *graph);
+int mb200_graph_launch(mb200_handle_t handle, mb200_graph_t graph);
+int mb200_graph_destroy(mb200_graph_t graph);
+
 /* ---- counters (bench.py's gpu_launches claim) ----------------------------------------------- */
 typedef struct {
     uint64_t launches_total;
     uint64_t launches_direct, launches_gett_f64, launches_simt_f32, launches_tcgen05;
     uint64_t launches_permute, launches_table, launches_convert, launches_reduce;
     uint64_t plans_built, plans_hit;
+    uint64_t launches_unary, launches_hadamard, graph_launches;
 } mb200_stats_t;
 int mb200_get_stats(mb200_handle_t handle, mb200_stats_t *stats);
 int mb200_reset_stats(mb200_handle_t handle);

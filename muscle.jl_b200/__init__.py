@@ -7,16 +7,20 @@ Import it as `muscle_b200` (the repo-root shim maps the dotted directory name to
 """
 from ._lib import (ArgumentError, B200Error, DimensionMismatch, Handle, LIB_PATH, PATH_AUTO, PATH_DIRECT,
                    PATH_GETT_F64, PATH_NAMES, PATH_SIMT_F32, PATH_TCGEN05_TF32, lib, plan_describe, shard_plan)
-from .backend import (Backend, BackendB200, BackendBase, Domain, DomainB200, DomainHost, choose_backend,
+from .backend import (Backend, BackendB200, BackendBase, BackendOMEinsum, Domain, DomainB200, DomainHost, choose_backend,
                       choose_backend_rule, domain, with_backend)
 from .einsum import binary_einsum, binary_einsum_, binary_einsum_inplace, flatten_labels, frontend_inds_c
+from .family import hadamard, hadamard_, unary_einsum, unary_einsum_, unary_frontend_inds_y
+from .network import CapturedProgram, ContractionProgram, contract, find_path
 from .tensor import B200Array, Index, Tensor, findperm
 from . import dist
 
 __all__ = [
     "ArgumentError", "B200Error", "DimensionMismatch", "Handle", "LIB_PATH", "lib", "plan_describe", "shard_plan",
     "PATH_AUTO", "PATH_DIRECT", "PATH_GETT_F64", "PATH_SIMT_F32", "PATH_TCGEN05_TF32", "PATH_NAMES",
-    "Backend", "BackendB200", "BackendBase", "Domain", "DomainB200", "DomainHost", "choose_backend",
+    "Backend", "BackendB200", "BackendBase", "BackendOMEinsum",
+    "CapturedProgram", "ContractionProgram", "contract", "find_path",
+    "hadamard", "hadamard_", "unary_einsum", "unary_einsum_", "unary_frontend_inds_y", "Domain", "DomainB200", "DomainHost", "choose_backend",
     "choose_backend_rule", "domain", "with_backend",
     "binary_einsum", "binary_einsum_", "binary_einsum_inplace", "flatten_labels", "frontend_inds_c",
     "B200Array", "Index", "Tensor", "findperm",

@@ -63,7 +63,8 @@ class ShardInfo(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "launches_total", "launches_direct", "launches_gett_f64", "launches_simt_f32", "launches_tcgen05",
-        "launches_permute", "launches_table", "launches_convert", "launches_reduce", "plans_built", "plans_hit")]
+        "launches_permute", "launches_table", "launches_convert", "launches_reduce", "plans_built", "plans_hit",
+        "launches_unary", "launches_hadamard", "graph_launches")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -101,6 +102,12 @@ PROTOTYPES = {
                              _i, _i, _i32p, _i64p, _i64p,
                              C.POINTER(PlanInfo)], C.c_int),
     "mb200_permute": ([_vp, _vp, _vp, _i, _i, _i64p, _i32p, C.c_uint32], C.c_int),
+    "mb200_unary_einsum": ([_vp,
+                            _vp, _i, _i, _i32p, _i64p,
+                            _vp, _i, _i, _i32p, _i64p, _i64p], C.c_int),
+    "mb200_hadamard": ([_vp, _vp, _i,
+                        _vp, _i, _i, _i32p, _i64p,
+                        _vp, _i, _i, _i32p, _i64p], C.c_int),
     "mb200_shard_plan": ([_i, _i32p, _i, _i32p, _i64p, _i, _i32p, _i64p, _i, _i, _i,
                           C.POINTER(ShardInfo)], C.c_int),
     "mb200_ipc_export": ([_vp, _vp, C.c_char_p], C.c_int),
@@ -112,6 +119,10 @@ PROTOTYPES = {
                                      _vp, _i, _i, _i32p, _i64p, _i64p,
                                      C.POINTER(_vp), _i, _i, _i], C.c_int),
     "mb200_reduce_slots": ([_vp, _vp, _vp, _i, C.c_int64, _i], C.c_int),
+    "mb200_graph_begin": ([_vp], C.c_int),
+    "mb200_graph_end": ([_vp, C.POINTER(_vp)], C.c_int),
+    "mb200_graph_launch": ([_vp, _vp], C.c_int),
+    "mb200_graph_destroy": ([_vp], C.c_int),
     "mb200_get_stats": ([_vp, C.POINTER(Stats)], C.c_int),
     "mb200_reset_stats": ([_vp], C.c_int),
 }

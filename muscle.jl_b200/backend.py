@@ -30,6 +30,11 @@ class BackendBase(Backend):
     ArgumentError (binary_einsum.jl:53-55)."""
 
 
+class BackendOMEinsum(Backend):
+    """The reference's default backend for `unary_einsum` on host arrays (src/Operations/unary_einsum.jl:20-24,
+    ext/MuscleOMEinsumExt.jl). Like BackendBase it lives in Muscle.jl, not here."""
+
+
 class BackendB200(Backend):
     """The new backend: ccall/ctypes → libmuscle_b200.so (CUDA for sm_100a)."""
 
@@ -113,3 +118,17 @@ register_rule("binary_einsum", (DomainB200, DomainHost), BackendB200())
 register_rule("binary_einsum", (DomainHost, DomainB200), BackendB200())
 register_rule("binary_einsum!", (DomainHost, DomainHost, DomainHost), BackendBase())
 register_rule("binary_einsum!", (DomainB200, DomainB200, DomainB200), BackendB200())
+
+# unary_einsum / hadamard: host arrays keep the reference's answers (unary_einsum.jl:20-24,
+# hadamard.jl:4-5); device (and mixed) operands select the new backend.
+register_rule("unary_einsum", (DomainHost,), BackendOMEinsum())
+register_rule("unary_einsum", (DomainB200,), BackendB200())
+register_rule("unary_einsum!", (DomainHost, DomainHost), BackendOMEinsum())
+register_rule("unary_einsum!", (DomainB200, DomainB200), BackendB200())
+register_rule("hadamard", (DomainHost, DomainHost), BackendBase())
+register_rule("hadamard", (DomainB200, DomainB200), BackendB200())
+register_rule("hadamard", (DomainB200, DomainHost), BackendB200())
+register_rule("hadamard", (DomainHost, DomainB200), BackendB200())
+register_rule("hadamard!", (DomainHost, DomainHost, DomainHost), BackendBase())
+register_rule("hadamard!", (DomainB200, DomainB200, DomainB200), BackendB200())
+register_rule("hadamard!", (DomainB200, DomainB200, DomainHost), BackendB200())

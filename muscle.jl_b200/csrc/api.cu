@@ -41,6 +41,13 @@ struct mb200_handle_s {
     std::list<std::string> lru;
     mb200_stats_t stats{};
     std::mutex mu;
+    bool capturing = false;
+};
+
+struct mb200_graph_s {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    int device = 0;
 };
 
 namespace {
@@ -272,6 +279,8 @@ int contract_device(mb200_handle_t h, void *C, TensorDesc &dC, const int64_t *st
         cp->lru = h->lru.begin();
         h->stats.plans_hit++;
     } else {
+        if (h->capturing)
+            return fail(MB200_NOT_SUPPORTED, "plan miss during graph capture: run the sequence once before mb200_graph_begin");
         while (h->cache.size() >= PLAN_CACHE_CAP) evict_one(h);
         auto fresh = std::make_unique<CachedPlan>();
         fresh->plan = plan;
@@ -613,6 +622,188 @@ int mb200_permute(mb200_handle_t h, void *dst, const void *src, int dtype, int n
     return MB200_OK;
 }
 
+int mb200_unary_einsum(mb200_handle_t h, void *Y, int dtypeY, int nmodeY, const int32_t *modesY, const int64_t *stridesY,
+                       const void *X, int dtypeX, int nmodeX, const int32_t *modesX, const int64_t *extentsX,
+                       const int64_t *stridesX) {
+    MB200_CHECK_HANDLE(h);
+    if (!dtype_valid(dtypeX) || dtypeY != dtypeX)
+        return fail(MB200_INVALID_ARGUMENT, "unary_einsum: eltype(y) must equal eltype(x)");
+    if (nmodeX < 0 || nmodeX > MB200_MAX_MODES || nmodeY < 0 || nmodeY > MB200_MAX_MODES)
+        return fail(MB200_INVALID_ARGUMENT, "nmode out of range");
+    if ((nmodeX > 0 && (!modesX || !extentsX)) || (nmodeY > 0 && !modesY))
+        return fail(MB200_INVALID_ARGUMENT, "modes/extents are NULL");
+    // distinct labels of x with the summed ("diagonal") stride of all their positions
+    struct Lab { int32_t label; int64_t ext, sx, sy; bool in_y; };
+    std::vector<Lab> labs;
+    int64_t dense = 1;
+    for (int i = 0; i < nmodeX; i++) {
+        if (extentsX[i] < 0) return fail(MB200_INVALID_ARGUMENT, "x: negative extent");
+        const int64_t st = stridesX ? stridesX[i] : dense;
+        dense *= extentsX[i];
+        bool found = false;
+        for (Lab &l : labs)
+            if (l.label == modesX[i]) {
+                if (l.ext != extentsX[i])
+                    return fail(MB200_DIMENSION_MISMATCH, "x: repeated mode %d has extents %lld and %lld", (int)modesX[i],
+                                (long long)l.ext, (long long)extentsX[i]);
+                l.sx += st;
+                found = true;
+            }
+        if (!found) labs.push_back({modesX[i], extentsX[i], st, 0, false});
+    }
+    int64_t ydense = 1, total_y = 1;
+    for (int i = 0; i < nmodeY; i++) {
+        Lab *hit = nullptr;
+        for (Lab &l : labs)
+            if (l.label == modesY[i]) hit = &l;
+        if (!hit) return fail(MB200_INVALID_ARGUMENT, "Output indices must be a subset of input indices (mode %d)", (int)modesY[i]);
+        if (hit->in_y) return fail(MB200_INVALID_ARGUMENT, "y: mode %d is repeated", (int)modesY[i]);
+        hit->in_y = true;
+        hit->sy = stridesY ? stridesY[i] : ydense;
+        ydense *= hit->ext;
+        total_y *= hit->ext;
+    }
+    if (total_y == 0) return MB200_OK;
+    if (!Y || !X) {
+        bool x_empty = false;
+        for (const Lab &l : labs) x_empty = x_empty || l.ext == 0;
+        if (!Y || !x_empty) return fail(MB200_INVALID_ARGUMENT, "NULL data pointer");
+    }
+    UnaryParams p{};
+    std::vector<Lab> outs, sums;
+    for (const Lab &l : labs) {
+        if (l.ext == 1) continue;
+        (l.in_y ? outs : sums).push_back(l);
+    }
+    std::stable_sort(outs.begin(), outs.end(), [](const Lab &a, const Lab &b) { return a.sy < b.sy; });
+    std::stable_sort(sums.begin(), sums.end(), [](const Lab &a, const Lab &b) { return a.sx < b.sx; });
+    p.total_c = 1; p.total_k = 1;
+    for (const Lab &l : outs) {
+        p.total_c *= l.ext;
+        if (p.nc > 0 && l.sx == p.c_sx[p.nc - 1] * p.c_ext[p.nc - 1] && l.sy == p.c_sy[p.nc - 1] * p.c_ext[p.nc - 1]) {
+            p.c_ext[p.nc - 1] *= l.ext;
+        } else {
+            p.c_ext[p.nc] = l.ext; p.c_sx[p.nc] = l.sx; p.c_sy[p.nc] = l.sy; p.nc++;
+        }
+    }
+    for (const Lab &l : sums) {
+        p.total_k *= l.ext;
+        if (p.nk > 0 && l.sx == p.k_sx[p.nk - 1] * p.k_ext[p.nk - 1]) {
+            p.k_ext[p.nk - 1] *= l.ext;
+        } else {
+            p.k_ext[p.nk] = l.ext; p.k_sx[p.nk] = l.sx; p.nk++;
+        }
+    }
+    std::lock_guard<std::mutex> lk(h->mu);
+    MB200_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    // no reduction, no diagonal, dense operands: a plain permutation -> K1
+    if (p.nk == 0 && (int)labs.size() == nmodeX && !stridesX && !stridesY && nmodeX == nmodeY) {
+        PermuteParams q{};
+        q.total = total_y;
+        for (int i = 0; i < nmodeX; i++) {
+            if (extentsX[i] == 1) continue;
+            int64_t ds = 0;
+            for (const Lab &l : labs)
+                if (l.label == modesX[i]) ds = l.sy;
+            if (q.n > 0 && ds == q.dst_stride[q.n - 1] * q.ext[q.n - 1]) {
+                q.ext[q.n - 1] *= extentsX[i];
+            } else {
+                q.ext[q.n] = extentsX[i]; q.dst_stride[q.n] = ds; q.n++;
+            }
+        }
+        MB200_CUDA(launch_permute(dtypeX, q, X, Y, s));
+        h->stats.launches_permute++;
+        h->stats.launches_total++;
+        return MB200_OK;
+    }
+    const int nsplit = unary_nsplit(p);
+    void *part = nullptr;
+    if (nsplit > 1) MB200_CUDA(cudaMallocAsync(&part, (size_t)nsplit * p.total_c * dtype_size(dtypeX), s));
+    cudaError_t e = launch_unary(dtypeX, p, X, Y, part, nsplit, s);
+    if (part) cudaFreeAsync(part, s);
+    if (e != cudaSuccess) return cuda_fail(e, "unary_einsum launch");
+    h->stats.launches_unary += nsplit > 1 ? 2 : 1;
+    h->stats.launches_total += nsplit > 1 ? 2 : 1;
+    return MB200_OK;
+}
+
+int mb200_hadamard(mb200_handle_t h, void *Cp, int dtypeC, const void *A, int dtypeA, int nmodeA, const int32_t *modesA,
+                   const int64_t *extentsA, const void *B, int dtypeB, int nmodeB, const int32_t *modesB,
+                   const int64_t *extentsB) {
+    MB200_CHECK_HANDLE(h);
+    if (!dtype_valid(dtypeA) || !dtype_valid(dtypeB)) return fail(MB200_INVALID_ARGUMENT, "unknown dtype");
+    if (dtypeC != dtype_promote(dtypeA, dtypeB))
+        return fail(MB200_INVALID_ARGUMENT, "eltype(c) = %s must be promote_eltype(a, b) = %s", dtype_name(dtypeC),
+                    dtype_name(dtype_promote(dtypeA, dtypeB)));
+    if (nmodeA < 0 || nmodeA > MB200_MAX_MODES || nmodeB < 0 || nmodeB > MB200_MAX_MODES)
+        return fail(MB200_INVALID_ARGUMENT, "nmode out of range");
+    if ((nmodeA > 0 && (!modesA || !extentsA)) || (nmodeB > 0 && (!modesB || !extentsB)))
+        return fail(MB200_INVALID_ARGUMENT, "modes/extents are NULL");
+    for (int i = 0; i < nmodeA; i++)
+        for (int j = 0; j < i; j++)
+            if (modesA[i] == modesA[j]) return fail(MB200_INVALID_ARGUMENT, "a: mode %d is repeated", (int)modesA[i]);
+    // stride of every mode of a inside b (0 = b is broadcast along it)
+    int64_t sb_of_a[MB200_MAX_MODES] = {0};
+    int64_t bdense = 1, total_b = 1;
+    for (int j = 0; j < nmodeB; j++) {
+        for (int k = 0; k < j; k++)
+            if (modesB[j] == modesB[k]) return fail(MB200_INVALID_ARGUMENT, "b: mode %d is repeated", (int)modesB[j]);
+        int ia = -1;
+        for (int i = 0; i < nmodeA; i++)
+            if (modesA[i] == modesB[j]) ia = i;
+        if (ia < 0) return fail(MB200_INVALID_ARGUMENT, "inds(b) must be a subset of inds(a) (mode %d)", (int)modesB[j]);
+        if (extentsA[ia] != extentsB[j])
+            return fail(MB200_DIMENSION_MISMATCH, "mode %d has extent %lld in a and %lld in b", (int)modesB[j],
+                        (long long)extentsA[ia], (long long)extentsB[j]);
+        sb_of_a[ia] = bdense;
+        bdense *= extentsB[j];
+        total_b *= extentsB[j];
+    }
+    HadamardParams p{};
+    p.total = 1;
+    for (int i = 0; i < nmodeA; i++) {
+        if (extentsA[i] < 0) return fail(MB200_INVALID_ARGUMENT, "negative extent");
+        p.total *= extentsA[i];
+        if (extentsA[i] == 1) continue;
+        if (p.n > 0 && sb_of_a[i] == p.sb[p.n - 1] * p.ext[p.n - 1]) {
+            p.ext[p.n - 1] *= extentsA[i];
+        } else {
+            p.ext[p.n] = extentsA[i]; p.sb[p.n] = sb_of_a[i]; p.n++;
+        }
+    }
+    if (p.total == 0) return MB200_OK;
+    if (p.n == 0) { p.n = 1; p.ext[0] = 1; p.sb[0] = 0; }
+    if (!Cp || !A || !B) return fail(MB200_INVALID_ARGUMENT, "NULL data pointer");
+    if (Cp == A && dtypeA != dtypeC) return fail(MB200_INVALID_ARGUMENT, "c may alias a only when eltype(a) == eltype(c)");
+    std::lock_guard<std::mutex> lk(h->mu);
+    MB200_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    void *tmpA = nullptr, *tmpB = nullptr;
+    if (dtypeA != dtypeC) {
+        MB200_CUDA(cudaMallocAsync(&tmpA, (size_t)p.total * dtype_size(dtypeC), s));
+        MB200_CUDA(launch_convert(dtypeC, tmpA, dtypeA, A, p.total, s));
+        h->stats.launches_convert++; h->stats.launches_total++;
+        A = tmpA;
+    }
+    if (dtypeB != dtypeC) {
+        MB200_CUDA(cudaMallocAsync(&tmpB, (size_t)std::max<int64_t>(total_b, 1) * dtype_size(dtypeC), s));
+        MB200_CUDA(launch_convert(dtypeC, tmpB, dtypeB, B, total_b, s));
+        h->stats.launches_convert++; h->stats.launches_total++;
+        B = tmpB;
+    }
+    const int vec = (int)(16 / dtype_size(dtypeC));
+    p.b_vec_aligned = (((uintptr_t)B) & 15) == 0;
+    for (int i = 1; i < p.n; i++) p.b_vec_aligned = p.b_vec_aligned && p.sb[i] % vec == 0;
+    cudaError_t e = launch_hadamard(dtypeC, p, A, B, Cp, s);
+    if (tmpA) cudaFreeAsync(tmpA, s);
+    if (tmpB) cudaFreeAsync(tmpB, s);
+    if (e != cudaSuccess) return cuda_fail(e, "hadamard launch");
+    h->stats.launches_hadamard++;
+    h->stats.launches_total++;
+    return MB200_OK;
+}
+
 int mb200_shard_plan(int nmodeC, const int32_t *modesC, int nmodeA, const int32_t *modesA,
                      const int64_t *extentsA, int nmodeB, const int32_t *modesB, const int64_t *extentsB,
                      int nranks, int rank, int prefer_sum, mb200_shard_info_t *info) {
@@ -729,6 +920,57 @@ int mb200_reduce_slots(mb200_handle_t h, void *out, const void *staging_local, i
     MB200_CUDA(launch_reduce_slots(dtype, out, staging_local, slab_elems, nslots, h->stream));
     h->stats.launches_reduce++;
     h->stats.launches_total++;
+    return MB200_OK;
+}
+
+int mb200_graph_begin(mb200_handle_t h) {
+    MB200_CHECK_HANDLE(h);
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->capturing) return fail(MB200_INVALID_ARGUMENT, "a capture is already in progress on this handle");
+    if (h->stream == nullptr || h->stream == cudaStreamLegacy)
+        return fail(MB200_NOT_SUPPORTED, "graph capture needs a non-default stream (mb200_set_stream)");
+    MB200_CUDA(cudaSetDevice(h->device));
+    MB200_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    h->capturing = true;
+    return MB200_OK;
+}
+
+int mb200_graph_end(mb200_handle_t h, mb200_graph_t *graph) {
+    MB200_CHECK_HANDLE(h);
+    if (!graph) return fail(MB200_INVALID_ARGUMENT, "graph is NULL");
+    *graph = nullptr;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!h->capturing) return fail(MB200_INVALID_ARGUMENT, "no capture in progress");
+    h->capturing = false;
+    MB200_CUDA(cudaSetDevice(h->device));
+    auto g = std::make_unique<mb200_graph_s>();
+    g->device = h->device;
+    MB200_CUDA(cudaStreamEndCapture(h->stream, &g->graph));
+    cudaError_t e = cudaGraphInstantiate(&g->exec, g->graph, 0);
+    if (e != cudaSuccess) {
+        cudaGraphDestroy(g->graph);
+        return cuda_fail(e, "cudaGraphInstantiate");
+    }
+    *graph = g.release();
+    return MB200_OK;
+}
+
+int mb200_graph_launch(mb200_handle_t h, mb200_graph_t g) {
+    MB200_CHECK_HANDLE(h);
+    if (!g || !g->exec) return fail(MB200_INVALID_ARGUMENT, "graph is NULL");
+    std::lock_guard<std::mutex> lk(h->mu);
+    MB200_CUDA(cudaSetDevice(h->device));
+    MB200_CUDA(cudaGraphLaunch(g->exec, h->stream));
+    h->stats.graph_launches++;
+    return MB200_OK;
+}
+
+int mb200_graph_destroy(mb200_graph_t g) {
+    if (!g) return MB200_OK;
+    cudaSetDevice(g->device);
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    delete g;
     return MB200_OK;
 }
 

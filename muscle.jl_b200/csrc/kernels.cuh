@@ -73,6 +73,27 @@ cudaError_t tf32_configure();
 
 cudaError_t launch_reduce_slots(int dtype, void *out, const void *staging, int64_t slab_elems, int nslots, cudaStream_t s);
 
+// ---- unary_einsum / hadamard (elementwise.cu) ------------------------------------------------------------
+// y[sum_i d_i * c_sy[i]] = sum over k of x[sum_i d_i * c_sx[i] + sum_j k_j * k_sx[j]]
+struct UnaryParams {
+    int nc;  // output-walk modes, y memory order (extent-1 removed, contiguous neighbours merged)
+    int64_t c_ext[MB200_MAX_MODES], c_sx[MB200_MAX_MODES], c_sy[MB200_MAX_MODES];
+    int nk;  // summed modes, ascending x stride
+    int64_t k_ext[MB200_MAX_MODES], k_sx[MB200_MAX_MODES];
+    int64_t total_c, total_k;
+};
+int unary_nsplit(const UnaryParams &p);   // > 1: the split form is used and needs nsplit * total_c elements of scratch
+cudaError_t launch_unary(int dtype, const UnaryParams &p, const void *X, void *Y, void *part, int nsplit, cudaStream_t s);
+
+// c[i] = a[i] * b[sum_m digit_m(i) * sb[m]] over a's (merged) modes; a and c dense, same layout
+struct HadamardParams {
+    int n;
+    int64_t ext[MB200_MAX_MODES], sb[MB200_MAX_MODES];
+    int64_t total;
+    int b_vec_aligned;   // b may be read with 16-byte loads along mode 0
+};
+cudaError_t launch_hadamard(int dtype, const HadamardParams &p, const void *A, const void *B, void *C, cudaStream_t s);
+
 // ---- dtype promotion (mixed-eltype operands) -------------------------------------------------------
 cudaError_t launch_convert(int dtype_dst, void *dst, int dtype_src, const void *src, int64_t n,
                            cudaStream_t s);

@@ -1,4 +1,5 @@
-"""TEST INFRASTRUCTURE ONLY — CPU oracle for Muscle.jl's `binary_einsum` hot path.
+"""TEST INFRASTRUCTURE ONLY — CPU oracle for Muscle.jl's `binary_einsum` hot path (and its einsum-family
+neighbours `unary_einsum` / `hadamard`).
 
 Nothing in the product package (`muscle.jl_b200/`) may import this. Only `tests/`,
 `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` legs use it,
@@ -14,4 +15,11 @@ from .muscle_oracle import (  # noqa: F401
     binary_einsum,
     permutedims,
     rel_frobenius,
+)
+from .family_oracle import (  # noqa: F401
+    contract_path_oracle,
+    hadamard_base,
+    unary_einsum,
+    unary_einsum_general,
+    unary_frontend_inds_y,
 )

@@ -1,0 +1,128 @@
+"""TEST INFRASTRUCTURE ONLY — CPU restatement of Muscle.jl v0.3.20 `unary_einsum` and `hadamard`
+(the einsum-family neighbours of the hot path). NumPy, column-major semantics.
+
+Pinned by the reference's own known-answer tests: test/integration/omeinsum.jl:6-100 (unary_einsum: axis sum,
+diagonal, trace) and test/unit/operations/hadamard.jl:4-139 (scalar / vector / tensor broadcast), transcribed in
+tests/test_family.py. The arithmetic of `unary_einsum` lives in the third-party OMEinsum.jl (compat "0.8, 0.9",
+Project.toml; no Manifest is checked in, so the version is unpinned); its published semantics are plain Einstein
+summation, restated here as diagonal extraction + axis sums + permutation.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .muscle_oracle import ArgumentError, DimensionMismatch, _fortran, _intersect, _setdiff, _unique, check_tensor
+
+
+def _nonunique(seq):
+    """Muscle's `nonunique`: the labels that occur more than once, in order of first appearance."""
+    seq = list(seq)
+    return [x for x in _unique(seq) if seq.count(x) > 1]
+
+
+def unary_frontend_inds_y(inds_x, dims=None, out=None):
+    """kwargs → inds_y — src/Operations/unary_einsum.jl:26-33:
+    inds_sum = dims ∩ inds(x) (dims defaults to the repeated labels); inds_y = out, or setdiff(inds(x), inds_sum)."""
+    if dims is None:
+        dims = _nonunique(inds_x)
+    inds_sum = _intersect(list(dims), list(inds_x))
+    if out is None:
+        return _setdiff(list(inds_x), inds_sum)
+    return list(out)
+
+
+def unary_einsum_general(inds_y, x: np.ndarray, inds_x):
+    """`unary_einsum!(::BackendOMEinsum, y, x)` — ext/MuscleOMEinsumExt.jl:31-38:
+    `@argcheck inds(y) ⊆ inds(x)`, then `einsum!((inds(x),), inds(y), (x,), y, true, false, size_dict)`, i.e.
+    y[inds_y] = Σ_{labels of x not in y} x[inds_x] with repeated labels of x tied together (diagonal)."""
+    inds_x, inds_y = list(inds_x), list(inds_y)
+    check_tensor(x, inds_x)
+    for i in inds_y:
+        if i not in inds_x:
+            raise ArgumentError("Output indices must be a subset of input indices")
+    if len(_unique(inds_y)) != len(inds_y):
+        raise ArgumentError("repeated output indices are not supported")
+    # 1. diagonal of every repeated label: keep its first position
+    cur, cur_inds = x, list(inds_x)
+    for lab in _nonunique(inds_x):
+        pos = [d for d, j in enumerate(cur_inds) if j == lab]
+        while len(pos) > 1:
+            d0, d1 = pos[0], pos[1]
+            diag = np.diagonal(cur, axis1=d0, axis2=d1)           # diagonal axis goes last
+            cur = np.moveaxis(diag, -1, d0)                        # put it back at the first position
+            cur_inds = [j for d, j in enumerate(cur_inds) if d != d1]
+            pos = [d for d, j in enumerate(cur_inds) if j == lab]
+    # 2. sum over the labels missing from y
+    axes = tuple(d for d, j in enumerate(cur_inds) if j not in inds_y)
+    if axes:
+        cur = np.sum(cur, axis=axes)
+        cur_inds = [j for j in cur_inds if j in inds_y]
+    # 3. permute to y's label order
+    cur = np.asarray(cur)
+    if cur.ndim:
+        cur = np.transpose(cur, [cur_inds.index(i) for i in inds_y])
+    return _fortran(np.array(cur, dtype=x.dtype))
+
+
+def unary_einsum(x, inds_x, dims=None, out=None):
+    """Front-end + backend (unary_einsum.jl:26-36)."""
+    inds_y = unary_frontend_inds_y(inds_x, dims=dims, out=out)
+    return unary_einsum_general(inds_y, x, inds_x), inds_y
+
+
+def hadamard_base(a: np.ndarray, inds_a, b: np.ndarray, inds_b):
+    """`hadamard(::BackendBase, a, b)` → `hadamard!(::BackendBase, c, a, b)` — src/Operations/hadamard.jl:42-77.
+    Returns (c, inds_c); c has the labels of the higher-rank operand."""
+    inds_a, inds_b = list(inds_a), list(inds_b)
+    if a.ndim < b.ndim:                                        # :44 / :52  `b` must be broadcastable to `a`
+        return hadamard_base(b, inds_b, a, inds_a)
+    check_tensor(a, inds_a)
+    check_tensor(b, inds_b)
+    for i in inds_b:                                           # :10  @argcheck inds(b) ⊆ inds(a)
+        if i not in inds_a:
+            raise ArgumentError("inds(b) ⊆ inds(a) must hold")
+    T = np.result_type(a.dtype, b.dtype)
+    if b.ndim == 0:                                            # :57-60 tensor-scalar
+        return _fortran(np.asarray(a * b, dtype=T)), inds_a
+    shape_b_bcast = [1] * a.ndim                               # :66-71
+    for d, ind in enumerate(inds_a):
+        if ind in inds_b:
+            if a.shape[d] != b.shape[inds_b.index(ind)]:
+                raise DimensionMismatch(f"extent mismatch for index {ind!r}")
+            shape_b_bcast[d] = b.shape[inds_b.index(ind)]
+    data_b = b
+    if b.ndim > 1:                                             # :74-77 permute b into a's label order
+        order = [i for i in inds_a if i in inds_b]
+        data_b = np.transpose(b, [inds_b.index(i) for i in order])
+    data_b = np.reshape(np.asfortranarray(data_b), shape_b_bcast, order="F")   # :80
+    return _fortran(np.asarray(a * data_b, dtype=T)), inds_a   # :81
+
+
+def contract_path_oracle(arrays, inds_list, out, path):
+    """n-ary contraction as the reference's callers do it: a fold of pairwise `binary_einsum`s along a path
+    (src/Operations/simple_update.jl:51-80, test/integration/reactant.jl:111). A label is summed at the step where
+    it is no longer needed by any other live tensor nor by `out`; labels dangling in one operand are summed first
+    (`unary_einsum`), labels shared by more tensors stay as hyperindices. Returns the result in `out` order."""
+    from .muscle_oracle import binary_einsum_general
+    live = {i: (np.asarray(a), list(ix)) for i, (a, ix) in enumerate(zip(arrays, inds_list))}
+    nxt = len(arrays)
+    out = list(out)
+    for (a, b) in path:
+        xa, ia = live.pop(a)
+        xb, ib = live.pop(b)
+        needed = set(out)
+        for _, ix in live.values():
+            needed.update(ix)
+        ops = []
+        for (x, ix, other) in ((xa, ia, ib), (xb, ib, ia)):
+            keep = [l for l in ix if l in other or l in needed]
+            if len(keep) != len(ix):
+                x = unary_einsum_general(keep, x, ix)
+                ix = keep
+            ops.append((x, ix))
+        (xa, ia), (xb, ib) = ops
+        ic = [l for l in dict.fromkeys(ia + ib) if l in needed]
+        live[nxt] = (binary_einsum_general(ic, xa, ia, xb, ib), ic)
+        nxt += 1
+    (x, ix), = live.values()
+    return unary_einsum_general(out, x, ix)

@@ -50,6 +50,49 @@ def permute_case(name, shape, perm, dtype, flags=0):
             "bytes": nbytes, "ms_best": best, "ms_mean": mean, "gbs_best": nbytes / best / 1e6, "gbs_mean": nbytes / mean / 1e6}
 
 
+def family_cases():
+    """unary_einsum / hadamard streaming kernels: GB/s over the algorithmic bytes (|x|+|y|, |a|+|b|+|c|)."""
+    out = []
+    h = _lib.Handle.get()
+    L = mb.lib()
+
+    def unary(name, shape, ix, iy, dtype):
+        x = dev_rand(shape, dtype)
+        m = {c: k for k, c in enumerate(dict.fromkeys(ix))}
+        ext = {c: shape[ix.index(c)] for c in ix}
+        y = B200Array([ext[c] for c in iy], dtype)
+        fn = lambda: _lib.check(L.mb200_unary_einsum(h.ptr, C.c_void_p(y.ptr), _lib.dtype_enum(dtype), len(iy), _lib.i32([m[c] for c in iy]), None,
+                                                     C.c_void_p(x.ptr), _lib.dtype_enum(dtype), len(ix), _lib.i32([m[c] for c in ix]), _lib.i64(shape), None))
+        best, mean = timeit(fn)
+        # algorithmic bytes: every DISTINCT-label element of x is read once (a repeated label reads only its diagonal)
+        nb = int(np.prod(list(ext.values()))) * np.dtype(dtype).itemsize + y.nbytes
+        out.append({"name": name, "op": "unary_einsum", "dtype": dtype, "bytes": nb, "ms_best": best, "gbs_best": nb / best / 1e6, "gbs_mean": nb / mean / 1e6})
+
+    def had(name, sa, ia, sb, ib, dtype):
+        a, b = dev_rand(sa, dtype, 1), dev_rand(sb, dtype, 2)
+        c = B200Array(sa, dtype)
+        m = {ch: k for k, ch in enumerate(ia)}
+        fn = lambda: _lib.check(L.mb200_hadamard(h.ptr, C.c_void_p(c.ptr), _lib.dtype_enum(dtype),
+                                                 C.c_void_p(a.ptr), _lib.dtype_enum(dtype), len(ia), _lib.i32([m[ch] for ch in ia]), _lib.i64(sa),
+                                                 C.c_void_p(b.ptr), _lib.dtype_enum(dtype), len(ib), _lib.i32([m[ch] for ch in ib]), _lib.i64(sb)))
+        best, mean = timeit(fn)
+        nb = 2 * a.nbytes + b.nbytes
+        out.append({"name": name, "op": "hadamard", "dtype": dtype, "bytes": nb, "ms_best": best, "gbs_best": nb / best / 1e6, "gbs_mean": nb / mean / 1e6})
+
+    for dt in ("complex128", "complex64"):
+        n = 1024 if dt == "complex128" else 2048
+        unary(f"column sums  x[a,b]->y[a]  {n}x16384 {dt}", (n, 16384), "ab", "a", dt)
+        unary(f"row sums     x[a,b]->y[b]  16384x{n} {dt}", (16384, n), "ab", "b", dt)
+        unary(f"sum of all   x[a,b]->y[]   {dt}", (n, 16384), "ab", "", dt)
+        unary(f"partial trace x[a,b,a]->y[b] (64,{n * 4},64) {dt}", (64, n * 4, 64), "aba", "b", dt)
+        unary(f"axis sum rank-4 x[a,b,c,d]->y[a,c] (256,64,{n // 4},64) {dt}", (256, 64, n // 4, 64), "abcd", "ac", dt)
+        unary(f"axis sum rank-4 x[a,b,c,d]->y[d,b] (256,64,{n // 4},64) {dt}", (256, 64, n // 4, 64), "abcd", "db", dt)
+        had(f"hadamard bond weights a[l,p,r] .* s[r] (1024,16,{n}) {dt}", (1024, 16, n), "lpr", (n,), "r", dt)
+        had(f"hadamard a[l,p,r] .* s[l] {dt}", (1024, 16, n), "lpr", (1024,), "l", dt)
+        had(f"hadamard full a .* b {dt}", (1024, 16, n), "lpr", (1024, 16, n), "lpr", dt)
+    return out
+
+
 def einsum_case(name, ext, ia, ib, ic, dtype, iters=5):
     A = Tensor(dev_rand([ext[c] for c in ia], dtype, 1), I(ia))
     B = Tensor(dev_rand([ext[c] for c in ib], dtype, 2), I(ib))
@@ -81,6 +124,13 @@ def main():
     P.append(permute_case("f64 rank6 dim16 reverse", (16,) * 6 + (2,), (5, 4, 3, 2, 1, 0, 6), "float64"))
     P.append(permute_case("qubit rank-26 c64 bit reversal", (2,) * 26, tuple(range(25, -1, -1)), "complex64") if False else
              permute_case("qubit rank-16 (dim 2 x13, 4096 tail) c64 reversal", (2,) * 13 + (4096,), tuple(range(13, -1, -1)), "complex64"))
+    if "--family" in sys.argv:
+        out["family"] = family_cases()
+        for r in out["family"]:
+            print(f"FAMILY  {r['name']:<72s} {r['gbs_best']:8.0f} GB/s best {r['gbs_mean']:8.0f} mean  {r['ms_best']:.3f} ms")
+        os.makedirs("gpurun_out", exist_ok=True)
+        json.dump(out, open("gpurun_out/kernels_family.json", "w"), indent=1)
+        return
     if "--permute-only" in sys.argv:
         for r in P:
             print(f"PERMUTE {r['name']:<60s} {r['gbs_best']:8.0f} GB/s best {r['gbs_mean']:8.0f} mean")
