@@ -12,7 +12,8 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmuscle_b200.so")
+# MB200_LIB_PATH: A/B benchmarking against another build of the same library (tools/); never a fallback
+LIB_PATH = os.environ.get("MB200_LIB_PATH") or os.path.join(_HERE, "libmuscle_b200.so")
 
 MAX_MODES = 32
 
@@ -142,6 +143,8 @@ def lib() -> C.CDLL:
                     "(there is no Python or CPU fallback for binary_einsum)")
             L = C.CDLL(LIB_PATH)
             for name, (argtypes, restype) in PROTOTYPES.items():
+                if os.environ.get("MB200_LIB_PATH") and not hasattr(L, name):
+                    continue           # an older build under A/B test
                 fn = getattr(L, name)  # AttributeError if the symbol is not exported
                 fn.argtypes = argtypes
                 fn.restype = restype

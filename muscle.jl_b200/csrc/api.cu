@@ -191,17 +191,18 @@ bool build_pack_params(const Plan &p, int which, PermuteParams &q, int64_t &rows
     struct Md { int64_t ext, ss, ds; };
     std::vector<Md> v;
     const int64_t K = p.K;
+    const int64_t W = p.dtype == MB200_F32 ? 2 : 4;   // floats per k: (hi, lo) real, (re_hi, re_lo, im_hi, im_lo) complex
     int64_t kstride = 1;
     bool grouped = false;   // the first group of 8 k has been tiled by the modes seen so far
     for (const GroupMode &g : p.sum) {
         const int64_t ss = which ? g.sb : g.sa;
         if (grouped) {
-            v.push_back({g.extent, ss, 4 * kstride});        // kstride is a multiple of 8: (kstride / 8) groups of 32 floats
+            v.push_back({g.extent, ss, W * kstride});        // kstride is a multiple of 8: (kstride / 8) groups of 8 W floats
         } else {
             const int64_t need = 8 / kstride;
             if (g.extent % need == 0) {                       // completes the group: split into (need, extent / need)
                 v.push_back({need, ss, kstride});
-                if (g.extent / need > 1) v.push_back({g.extent / need, ss * need, 32});
+                if (g.extent / need > 1) v.push_back({g.extent / need, ss * need, 8 * W});
                 grouped = true;
             } else if (need % g.extent == 0) {                // still inside the group of 8
                 v.push_back({g.extent, ss, kstride});
@@ -214,13 +215,13 @@ bool build_pack_params(const Plan &p, int which, PermuteParams &q, int64_t &rows
     if (!grouped) return false;
     int64_t rstride = 1;
     for (const GroupMode &g : (which ? p.right : p.left)) {
-        v.push_back({g.extent, which ? g.sb : g.sa, rstride * 4 * K});
+        v.push_back({g.extent, which ? g.sb : g.sa, rstride * W * K});
         rstride *= g.extent;
     }
     rows = rstride;
     int64_t bstride = 1;
     for (const GroupMode &g : p.batch) {
-        v.push_back({g.extent, which ? g.sb : g.sa, bstride * rows * 4 * K});
+        v.push_back({g.extent, which ? g.sb : g.sa, bstride * rows * W * K});
         bstride *= g.extent;
     }
     std::sort(v.begin(), v.end(), [](const Md &a, const Md &b) { return a.ss < b.ss; });
@@ -332,18 +333,19 @@ int contract_device(mb200_handle_t h, void *C, TensorDesc &dC, const int64_t *st
                build_pack_params(p, 1, qb, rows_b)) {
         // pack A, pack B (K1 with the tf32 hi/lo split writer), then the tcgen05 GEMM with the permuting epilogue
         void *pa = nullptr, *pb = nullptr;
-        const size_t ba = (size_t)p.L * rows_a * 4 * p.K * sizeof(float), bb = (size_t)p.L * rows_b * 4 * p.K * sizeof(float);
+        const size_t W = p.dtype == MB200_F32 ? 2 : 4;
+        const size_t ba = (size_t)p.L * rows_a * W * p.K * sizeof(float), bb = (size_t)p.L * rows_b * W * p.K * sizeof(float);
         MB200_CUDA(cudaMallocAsync(&pa, ba, s));
         MB200_CUDA(cudaMallocAsync(&pb, bb, s));
-        e = launch_permute(MB200_C64, qa, R, pa, s);
-        if (e == cudaSuccess) e = launch_permute(MB200_C64, qb, Q, pb, s);
+        e = launch_permute(p.dtype, qa, R, pa, s);
+        if (e == cudaSuccess) e = launch_permute(p.dtype, qb, Q, pb, s);
         h->stats.launches_permute += 2;
         h->stats.launches_total += 2;
         if (e == cudaSuccess) {
             GettParams g = cp->gp;
             g.C = C;
             if (sc) g.sc = *sc;
-            e = launch_tf32_gemm(pa, pb, g, s);
+            e = launch_tf32_gemm(p.dtype, pa, pb, g, s);
             h->stats.launches_tcgen05++;
         }
         cudaFreeAsync(pa, s);

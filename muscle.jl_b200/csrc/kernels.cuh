@@ -106,12 +106,13 @@ struct PermuteParams {
     int64_t total;
     int64_t plane_stride;                // != 0: complex dst written planar, im plane at +plane_stride
     int split;                           // 1: ComplexF32 -> tf32 hi/lo chunks (re_hi, re_lo, im_hi, im_lo at +0,+8,+16,+24
-                                         //    floats), the operand format of the tcgen05 kernel (tf32.cu)
+                                         //    floats), Float32 -> (hi, lo at +0,+8): the operand formats of the tcgen05
+                                         //    kernel (tf32.cu)
 };
 cudaError_t launch_permute(int dtype, const PermuteParams &p, const void *src, void *dst, cudaStream_t s);
 
 // ---- K3: tcgen05 / TMEM 3xTF32 ComplexF32 GEMM on packed operands (tf32.cu) ---------------------------------
 bool tf32_available();
-cudaError_t launch_tf32_gemm(const void *packA, const void *packB, const GettParams &g, cudaStream_t s);
+cudaError_t launch_tf32_gemm(int dtype, const void *packA, const void *packB, const GettParams &g, cudaStream_t s);
 
 }  // namespace mb200

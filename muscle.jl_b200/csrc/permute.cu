@@ -63,7 +63,8 @@ __device__ __forceinline__ void digits_off(unsigned idx, int n, const unsigned *
 
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
-// PLANAR: 0 = interleaved (plain), 1 = two planes, 2 = tf32 hi/lo split into four 8-float chunks
+// PLANAR: 0 = interleaved (plain), 1 = two planes, 2 = ComplexF32 tf32 hi/lo split into four 8-float chunks,
+//         3 = Float32 tf32 hi/lo split into two 8-float chunks
 template <typename E, typename S, int PLANAR>
 __device__ __forceinline__ void put(void *dstv, int64_t off, const E &val, int64_t plane_stride) {
     if constexpr (PLANAR == 1) {
@@ -77,6 +78,11 @@ __device__ __forceinline__ void put(void *dstv, int64_t off, const E &val, int64
         d[off + 8] = val.x - rh;
         d[off + 16] = ih;
         d[off + 24] = val.y - ih;
+    } else if constexpr (PLANAR == 3) {
+        S *d = reinterpret_cast<S *>(dstv);
+        const float h = tf32_hi(val);
+        d[off] = h;
+        d[off + 8] = val - h;
     } else {
         reinterpret_cast<E *>(dstv)[off] = val;
     }
@@ -521,7 +527,7 @@ cudaError_t launch_permute(int dtype, const PermuteParams &q_in, const void *src
 #define MB200_PERM(E, S, P)                                                                                   \
     do {                                                                                                      \
         constexpr int NE = (int)((32 * 1024 / sizeof(E)) / PT_THREADS);                                       \
-        constexpr bool PERSIST_OK = sizeof(E) == 16 || (sizeof(E) == 8 && (P) != 0) || std::is_same<E, float2>::value; \
+        constexpr bool PERSIST_OK = sizeof(E) == 16 || (sizeof(E) == 8 && (P) != 0) || std::is_same<E, float2>::value || (P) == 3; \
         if (k.direct) {                                                                                       \
             permute_direct_kernel<E, S, P><<<ntiles, PT_THREADS, 0, s>>>(k, (const E *)src, dst);             \
         } else if (PERSIST_OK && full_tile) {                                                                 \
@@ -539,6 +545,8 @@ cudaError_t launch_permute(int dtype, const PermuteParams &q_in, const void *src
         else MB200_PERM(float2, float, 1);
     } else if (dtype == MB200_C128) {
         MB200_PERM(double2, double, 1);
+    } else if (dtype == MB200_F32 && q.split) {
+        MB200_PERM(float, float, 3);
     } else {
         return cudaErrorInvalidValue;   // planar / split need a complex dtype
     }
@@ -555,7 +563,7 @@ cudaError_t permute_configure() {
         if (e == cudaSuccess) e = cudaFuncSetAttribute(permute_tiled_kernel<E, S, P, NE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); \
         if (e == cudaSuccess) e = cudaFuncSetAttribute(permute_simple_kernel<E, S, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);    \
     } while (0)
-    MB200_PCFG(float, float, 0);
+    MB200_PCFG(float, float, 0); MB200_PCFG(float, float, 3);
     MB200_PCFG(float2, float, 0); MB200_PCFG(float2, float, 1); MB200_PCFG(float2, float, 2);
     MB200_PCFG(double2, double, 0); MB200_PCFG(double2, double, 1);
 #undef MB200_PCFG

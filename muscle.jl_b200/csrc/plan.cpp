@@ -174,7 +174,7 @@ int make_plan(const TensorDesc &A, const TensorDesc &B, TensorDesc &C, const int
     // leading summed modes must tile a group exactly: extents 8 | e, or 2*2*2, 4*2, 2*4*..., 2*16 (split) ...
     // (tensor-network tensors are mostly dim-2 / dim-4 indices). Any common order of the summed modes is valid, so
     // try the memory order first, then a multiple-of-8 mode in front, then power-of-two extents first.
-    if (plan.dtype == MB200_C64 && !plan.sum.empty() && !k8_groupable(plan.sum)) {
+    if ((plan.dtype == MB200_C64 || plan.dtype == MB200_F32) && !plan.sum.empty() && !k8_groupable(plan.sum)) {
         std::vector<GroupMode> cand = plan.sum;
         bool found = false;
         for (size_t i = 1; i < cand.size() && !found; i++)
@@ -238,7 +238,7 @@ int make_plan(const TensorDesc &A, const TensorDesc &B, TensorDesc &C, const int
         }
         return true;
     };
-    plan.tc_ok = plan.dtype == MB200_C64 && k8_groupable(plan.sum) && dense(A) && dense(B) &&
+    plan.tc_ok = (plan.dtype == MB200_C64 || plan.dtype == MB200_F32) && k8_groupable(plan.sum) && dense(A) && dense(B) &&
                  plan.M >= 64 && plan.N >= 32 && plan.K >= 64 && plan.M < ((int64_t)1 << 31) &&
                  plan.N < ((int64_t)1 << 31) && plan.L < ((int64_t)1 << 31) && plan.K < ((int64_t)1 << 27);
 

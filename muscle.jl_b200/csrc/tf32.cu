@@ -8,6 +8,10 @@
 // 128 B swizzle-128B line; each 32 B chunk is exactly one K=8 tf32 MMA operand, so the MMA descriptor
 // for chunk p is the tile descriptor advanced by 32*p bytes.
 //
+// Float32 (REAL) operands use the same 128 B lines with two 8-k groups per line: | hi(k0..7) | lo(k0..7) | hi(k8..15) |
+// lo(k8..15) | (SPLIT2 writer), 6 MMAs per line (3xTF32 for each 8-k group) into ONE accumulator, and a 128 x 256
+// tile (N = 256 keeps the smem operand traffic per MMA at 12 KB / 128 cycles, under the 128 B/clk limit).
+//
 // Per group of 8 k the MMA warp issues 12 MMAs (3xTF32 x 4M) into two TMEM accumulators:
 //     D_re += rh*rh' + rh*rl' + rl*rh' - (ih*ih' + ih*il' + il*ih')      (minus = a_negate in the idesc)
 //     D_im += rh*ih' + rh*il' + rl*ih' +  ih*rh' + ih*rl' + il*rh'
@@ -36,10 +40,9 @@ namespace mb200 {
 namespace {
 
 constexpr int TBM = 128;          // tile rows = TMEM lanes
-constexpr int TSTAGES = 6;
 constexpr int TTHREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-constexpr int GROUP_BYTES = 128;  // bytes per row per 8-k group
-constexpr int CHUNK_GROUPS = 16;  // 128 k per TMEM accumulation chunk (two-level accumulation)
+constexpr int GROUP_BYTES = 128;  // bytes per row per smem line: one 8-k group (complex) or two (real)
+constexpr int CHUNK_K = 128;      // k per TMEM accumulation chunk (two-level accumulation)
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -125,15 +128,16 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool neg_a) {
 
 struct Tf32Params {
     ScatterDesc sc;
-    float2 *C;
+    void *C;
     const int64_t *rowC, *colC, *batC;
     int64_t M, N, L;
     int64_t ntiles;
-    int KG;   // number of 8-k groups
+    int KG;   // number of smem lines along k: K / 8 (complex), ceil(K / 16) (real)
 };
 
-template <int BN>
+template <int BN, bool REAL>
 struct Tf32Smem {
+    static constexpr int TSTAGES = BN == 256 ? 4 : 6;
     static constexpr int A_BYTES = TBM * GROUP_BYTES;   // 16 KB
     static constexpr int B_BYTES = BN * GROUP_BYTES;
     static constexpr int STAGE = A_BYTES + B_BYTES;
@@ -163,13 +167,15 @@ __device__ __forceinline__ TileCoord tile_coord(const Tf32Params &p, int64_t til
 // stages while the MMA warp is still on the current tile's tail, and the MMA warp starts the next tile's first
 // chunk while the epilogue warps are still storing the previous tile: per-tile prologue and epilogue are hidden
 // (K = 512 slices: 0.362 -> 0.317 ms).
-template <int BN>
+template <int BN, bool REAL>
 __global__ void __launch_bounds__(TTHREADS, 1)
 tf32_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const __grid_constant__ Tf32Params p) {
-    using SM = Tf32Smem<BN>;
+    using SM = Tf32Smem<BN, REAL>;
+    constexpr int TSTAGES = SM::TSTAGES;
+    constexpr int CHUNK_GROUPS = CHUNK_K / (REAL ? 16 : 8);   // smem lines per TMEM chunk
     constexpr int HALF = BN / 2;                  // columns per epilogue thread
-    constexpr uint32_t BUF_COLS = 2 * BN;         // D_re | D_im
+    constexpr uint32_t BUF_COLS = REAL ? BN : 2 * BN;   // D (real) or D_re | D_im
     constexpr uint32_t TMEM_COLS = 2 * BUF_COLS;  // two chunk buffers (256 or 512: powers of two)
     extern __shared__ unsigned char smem_raw[];
     unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -234,6 +240,16 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         const uint64_t a_rh = da, a_rl = da + 2, a_ih = da + 4, a_il = da + 6;
                         const uint64_t b_rh = db, b_rl = db + 2, b_ih = db + 4, b_il = db + 6;
                         const uint32_t acc = first ? 0u : 1u;
+                        if constexpr (REAL) {   // line = hi0 | lo0 | hi1 | lo1: 3xTF32 for each 8-k group
+                            umma_tf32(d_re, a_rh, b_rh, IDESC, acc);
+                            umma_tf32(d_re, a_rh, b_rl, IDESC, 1u);
+                            umma_tf32(d_re, a_rl, b_rh, IDESC, 1u);
+                            umma_tf32(d_re, a_ih, b_ih, IDESC, 1u);
+                            umma_tf32(d_re, a_ih, b_il, IDESC, 1u);
+                            umma_tf32(d_re, a_il, b_ih, IDESC, 1u);
+                            umma_commit(&empty[s]);
+                            continue;
+                        }
                         umma_tf32(d_re, a_rh, b_rh, IDESC, acc);
                         umma_tf32(d_im, a_rh, b_ih, IDESC, acc);
                         umma_tf32(d_re, a_rh, b_rl, IDESC, 1u);
@@ -264,9 +280,11 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             const int64_t m = (int64_t)tc.m0 + row;
             const bool row_ok = m < p.M;
             const int64_t crow = (row_ok ? p.rowC[m] : 0) + p.batC[tc.l];
-            float accr[HALF], acci[HALF];
+            float accr[HALF], acci[REAL ? 1 : HALF];
 #pragma unroll
-            for (int j = 0; j < HALF; j++) accr[j] = acci[j] = 0.f;
+            for (int j = 0; j < HALF; j++) accr[j] = 0.f;
+#pragma unroll
+            for (int j = 0; j < (REAL ? 1 : HALF); j++) acci[j] = 0.f;
             for (int c = 0; c < nchunks; c++, ch++) {
                 const int buf = ch & 1;
                 mbar_wait(&tmem_full[buf], (ch >> 1) & 1);
@@ -279,10 +297,12 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 32; j++) accr[sub * 32 + j] += __uint_as_float(v[j]);
-                    tmem_ld32(tq + BN + sub * 32, v);
-                    tmem_ld_wait();
+                    if constexpr (!REAL) {
+                        tmem_ld32(tq + BN + sub * 32, v);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; j++) acci[sub * 32 + j] += __uint_as_float(v[j]);
+                        for (int j = 0; j < 32; j++) acci[sub * 32 + j] += __uint_as_float(v[j]);
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -294,7 +314,10 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
                 for (int j = 0; j < HALF; j++) {
                     const int cidx = half * HALF + j;
-                    if (tc.n0 + cidx < p.N) *scatter_ptr(p.sc, p.C, crow + cols[cidx]) = make_float2(accr[j], acci[j]);
+                    if (tc.n0 + cidx < p.N) {
+                        if constexpr (REAL) *scatter_ptr(p.sc, reinterpret_cast<float *>(p.C), crow + cols[cidx]) = accr[j];
+                        else *scatter_ptr(p.sc, reinterpret_cast<float2 *>(p.C), crow + cols[cidx]) = make_float2(accr[j], acci[j]);
+                    }
                 }
             }
         }
@@ -323,12 +346,12 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// packed operand: [L][rows][4*K] floats, K-major, rows of KG*128 bytes
-bool make_map(CUtensorMap *map, const void *base, int64_t K, int64_t rows, int64_t L, int box_rows) {
+// packed operand: [L][rows][W*K] floats, K-major (W = 4 complex, 2 real), rows of KG*128 bytes
+bool make_map(CUtensorMap *map, const void *base, int64_t K, int W, int64_t rows, int64_t L, int box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
-    cuuint64_t dims[3] = {(cuuint64_t)(4 * K), (cuuint64_t)rows, (cuuint64_t)L};
-    cuuint64_t strides[2] = {(cuuint64_t)(16 * K), (cuuint64_t)(16 * K) * (cuuint64_t)rows};
+    cuuint64_t dims[3] = {(cuuint64_t)(W * K), (cuuint64_t)rows, (cuuint64_t)L};
+    cuuint64_t strides[2] = {(cuuint64_t)(4 * W * K), (cuuint64_t)(4 * W * K) * (cuuint64_t)rows};
     cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(base), dims, strides, box, estr,
@@ -337,22 +360,23 @@ bool make_map(CUtensorMap *map, const void *base, int64_t K, int64_t rows, int64
     return r == CUDA_SUCCESS;
 }
 
-template <int BN>
+template <int BN, bool REAL>
 cudaError_t launch_bn(const void *packA, const void *packB, const GettParams &g, cudaStream_t s) {
     CUtensorMap mapA, mapB;
-    if (!make_map(&mapA, packA, g.K, g.M, g.L, TBM) || !make_map(&mapB, packB, g.K, g.N, g.L, BN))
+    constexpr int W = REAL ? 2 : 4;
+    if (!make_map(&mapA, packA, g.K, W, g.M, g.L, TBM) || !make_map(&mapB, packB, g.K, W, g.N, g.L, BN))
         return cudaErrorInvalidValue;
     Tf32Params p{};
     p.sc = g.sc;
-    p.C = reinterpret_cast<float2 *>(g.C);
+    p.C = g.C;
     p.rowC = g.rowC; p.colC = g.colC; p.batC = g.batC;
     p.M = g.M; p.N = g.N; p.L = g.L;
-    p.KG = (int)(g.K / 8);
+    p.KG = REAL ? (int)((g.K + 15) / 16) : (int)(g.K / 8);   // a half-filled last line reads zeros (TMA out-of-bounds fill)
     const int64_t ntiles = ((g.M + TBM - 1) / TBM) * ((g.N + BN - 1) / BN) * g.L;
     if (ntiles <= 0) return cudaSuccess;
     p.ntiles = ntiles;
     const int64_t grid = ntiles < 148 ? ntiles : 148;   // persistent: one CTA per SM
-    tf32_gemm_kernel<BN><<<(unsigned)grid, TTHREADS, Tf32Smem<BN>::TOTAL, s>>>(mapA, mapB, p);
+    tf32_gemm_kernel<BN, REAL><<<(unsigned)grid, TTHREADS, Tf32Smem<BN, REAL>::TOTAL, s>>>(mapA, mapB, p);
     return cudaGetLastError();
 }
 
@@ -362,16 +386,23 @@ bool tf32_available() { return encode_fn() != nullptr; }
 
 // opt-in shared memory sizes; called once per device from mb200_create
 cudaError_t tf32_configure() {
-    cudaError_t e = cudaFuncSetAttribute(tf32_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tf32Smem<128>::TOTAL);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(tf32_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tf32Smem<64>::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(tf32_gemm_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tf32Smem<128, false>::TOTAL);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tf32_gemm_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tf32Smem<64, false>::TOTAL);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tf32_gemm_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tf32Smem<256, true>::TOTAL);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tf32_gemm_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tf32Smem<128, true>::TOTAL);
+    return e;
 }
 
-// C (ComplexF32, scattered through rowC/colC/batC) = packA [L][M][4K] x packB [L][N][4K]^T, K % 8 == 0
-cudaError_t launch_tf32_gemm(const void *packA, const void *packB, const GettParams &g, cudaStream_t s) {
+// C (scattered through rowC/colC/batC) = packA [L][M][W*K] x packB [L][N][W*K]^T, K % 8 == 0;
+// dtype ComplexF32 (W = 4) or Float32 (W = 2)
+cudaError_t launch_tf32_gemm(int dtype, const void *packA, const void *packB, const GettParams &g, cudaStream_t s) {
     if (g.K % 8 != 0 || g.K < 8) return cudaErrorInvalidValue;
-    if (g.N > 64) return launch_bn<128>(packA, packB, g, s);
-    return launch_bn<64>(packA, packB, g, s);
+    if (dtype == MB200_F32) {
+        if (g.N > 128) return launch_bn<256, true>(packA, packB, g, s);
+        return launch_bn<128, true>(packA, packB, g, s);
+    }
+    if (g.N > 64) return launch_bn<128, false>(packA, packB, g, s);
+    return launch_bn<64, false>(packA, packB, g, s);
 }
 
 }  // namespace mb200

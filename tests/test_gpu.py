@@ -355,13 +355,15 @@ def _tc_planned(case):
     return labels
 
 
+@pytest.mark.parametrize("dt", ["complex64", "float32"])
 @pytest.mark.parametrize("integer", [False, True], ids=["random", "integer_exact"])
 @pytest.mark.parametrize("case", TC_CASES, ids=[c[0] for c in TC_CASES])
-def test_tcgen05_tf32x3_parity(case, integer):
-    """ComplexF32 through pack (K1 split writer) + tcgen05 GEMM, forced; <= 1e-5 rel. Frobenius against the
+def test_tcgen05_tf32x3_parity(case, integer, dt):
+    """ComplexF32 / Float32 through pack (K1 split writer) + tcgen05 GEMM, forced; <= 1e-5 rel. Frobenius against the
     oracle, and bit-exact on integer-valued inputs (hi parts exact, lo parts zero, fp32 accumulation exact)."""
-    a, ia, b, ib, ic = build_case(case, "complex64", seed=31, integer=integer)
-    ref = binary_einsum_general(ic, a.astype(np.complex128), ia, b.astype(np.complex128), ib).astype(np.complex64)
+    wide = np.complex128 if dt == "complex64" else np.float64
+    a, ia, b, ib, ic = build_case(case, dt, seed=31, integer=integer)
+    ref = binary_einsum_general(ic, a.astype(wide), ia, b.astype(wide), ib).astype(dt)
     h = _lib.Handle.get()
     h.reset_stats()
     got = contract(a, ia, b, ib, ic, device=True, path=mb.PATH_TCGEN05_TF32)
@@ -384,12 +386,24 @@ def test_tcgen05_accuracy_beats_plain_tf32():
     got = contract(a, "ki", b, "kj", "ij", path=mb.PATH_TCGEN05_TF32)
     err = rel_frobenius(got.astype(np.complex128), ref)
     assert err <= 5e-6, err   # measured 2.4e-6, flat in K thanks to the two-level accumulation
+    # Float32: 128 x 256 tiles, one accumulator, K not a multiple of 16 (half-filled last smem line)
+    ar = random_array(rng, (4104, 256), "float32")
+    br = random_array(rng, (4104, 392), "float32")
+    refr = ar.astype(np.float64).T @ br.astype(np.float64)
+    h = _lib.Handle.get()
+    h.reset_stats()
+    gotr = contract(ar, "ki", br, "kj", "ij", path=mb.PATH_TCGEN05_TF32)
+    assert h.stats()["launches_tcgen05"] == 1
+    errr = rel_frobenius(gotr.astype(np.float64), refr)
+    assert errr <= 5e-6, errr
 
 
 def test_tcgen05_auto_selected_for_large_c64():
     info = mb.plan_describe(_lib.C64, [0, 2, 4, 5, 6], _lib.C64, [0, 1, 2, 3, 6], [256, 8, 8, 256, 8],
                             _lib.C64, [3, 1, 4, 5, 6], [256, 8, 8, 256, 8])
     assert info.path == mb.PATH_TCGEN05_TF32
+    info = mb.plan_describe(_lib.F32, [0, 2], _lib.F32, [0, 1], [4096, 4096], _lib.F32, [1, 2], [4096, 4096])
+    assert info.path == mb.PATH_TCGEN05_TF32      # Float32 takes the tensor cores too (3xTF32, 128 x 256 tiles)
     # strided operand or first summed extent not a multiple of 8 -> FFMA path
     info = mb.plan_describe(_lib.C64, [0, 2], _lib.C64, [1, 0], [100, 512], _lib.C64, [1, 2], [100, 512])
     assert info.path == mb.PATH_SIMT_F32
