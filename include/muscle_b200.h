@@ -159,6 +159,16 @@ int mb200_hadamard(mb200_handle_t handle, void *C, int dtypeC,
                    const void *A, int dtypeA, int nmodeA, const int32_t *modesA, const int64_t *extentsA,
                    const void *B, int dtypeB, int nmodeB, const int32_t *modesB, const int64_t *extentsB);
 
+/* ---- thin SVD of a matricised tensor ---------------------------------------------
+ * A (rows x cols, dense column-major, device) = U * diag(S) * V^H with k = min(rows, cols):
+ * U rows x k, S k singular values (Float32 for Float32/ComplexF32, Float64 otherwise) in descending order,
+ * Vt cols x k = conj(V) - exactly the three arrays `tensor_svd_thin(::BackendBase, A)` tensorifies
+ * (src/Operations/tensor_svd.jl:100-124; `Vt = reshape(conj(V), ...)` :121), so A[u,v] = sum_s U[u,s] S[s] Vt[v,s].
+ * Hand-written one-sided Jacobi (svd.cu). tol <= 0 selects sqrt(max(rows, cols)) * eps; max_sweeps <= 0 selects 30.
+ * Stream-ordered, no host synchronisation. Limits: rows, cols < 2^31 and rows * cols elements of workspace. */
+int mb200_svd_thin(mb200_handle_t handle, void *U, void *S, void *Vt, const void *A, int dtype,
+                   int64_t rows, int64_t cols, double tol, int max_sweeps);
+
 /* ---- multi-GPU partition planner (host only) ------------------------------------------------
  * One process per GPU (torch.distributed / NCCL does the plumbing). Mirrors Dagger's block
  * sharding, ext/MuscleDaggerExt/binary_einsum.jl:64-119: splitting a free or batch mode gives
@@ -221,7 +231,7 @@ typedef struct {
     uint64_t launches_direct, launches_gett_f64, launches_simt_f32, launches_tcgen05;
     uint64_t launches_permute, launches_table, launches_convert, launches_reduce;
     uint64_t plans_built, plans_hit;
-    uint64_t launches_unary, launches_hadamard, graph_launches;
+    uint64_t launches_unary, launches_hadamard, graph_launches, launches_svd;
 } mb200_stats_t;
 int mb200_get_stats(mb200_handle_t handle, mb200_stats_t *stats);
 int mb200_reset_stats(mb200_handle_t handle);

@@ -65,7 +65,7 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "launches_total", "launches_direct", "launches_gett_f64", "launches_simt_f32", "launches_tcgen05",
         "launches_permute", "launches_table", "launches_convert", "launches_reduce", "plans_built", "plans_hit",
-        "launches_unary", "launches_hadamard", "graph_launches")]
+        "launches_unary", "launches_hadamard", "graph_launches", "launches_svd")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -109,6 +109,7 @@ PROTOTYPES = {
     "mb200_hadamard": ([_vp, _vp, _i,
                         _vp, _i, _i, _i32p, _i64p,
                         _vp, _i, _i, _i32p, _i64p], C.c_int),
+    "mb200_svd_thin": ([_vp, _vp, _vp, _vp, _vp, _i, C.c_int64, C.c_int64, C.c_double, _i], C.c_int),
     "mb200_shard_plan": ([_i, _i32p, _i, _i32p, _i64p, _i, _i32p, _i64p, _i, _i, _i,
                           C.POINTER(ShardInfo)], C.c_int),
     "mb200_ipc_export": ([_vp, _vp, C.c_char_p], C.c_int),

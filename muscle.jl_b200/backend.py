@@ -132,3 +132,9 @@ register_rule("hadamard", (DomainHost, DomainB200), BackendB200())
 register_rule("hadamard!", (DomainHost, DomainHost, DomainHost), BackendBase())
 register_rule("hadamard!", (DomainB200, DomainB200, DomainB200), BackendB200())
 register_rule("hadamard!", (DomainB200, DomainB200, DomainHost), BackendB200())
+
+# tensor_svd_thin / simple_update: tensor_svd.jl:38-39, simple_update.jl:4-5
+register_rule("tensor_svd_thin", (DomainHost,), BackendBase())
+register_rule("tensor_svd_thin", (DomainB200,), BackendB200())
+register_rule("simple_update", (DomainHost, DomainHost, DomainHost), BackendBase())
+register_rule("simple_update", (DomainB200, DomainB200, DomainB200), BackendB200())

@@ -18,7 +18,7 @@ BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libmuscle_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
-SOURCES = ["plan.cpp", "api.cu", "direct.cu", "gett.cu", "permute.cu", "tf32.cu", "elementwise.cu"]
+SOURCES = ["plan.cpp", "api.cu", "direct.cu", "gett.cu", "permute.cu", "tf32.cu", "elementwise.cu", "svd.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
           "-Xptxas", "-v" if os.environ.get("MB200_PTXAS_V") else "-O3"]

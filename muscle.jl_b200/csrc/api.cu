@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <list>
 #include <memory>
@@ -802,6 +803,36 @@ int mb200_hadamard(mb200_handle_t h, void *Cp, int dtypeC, const void *A, int dt
     if (tmpB) cudaFreeAsync(tmpB, s);
     if (e != cudaSuccess) return cuda_fail(e, "hadamard launch");
     h->stats.launches_hadamard++;
+    h->stats.launches_total++;
+    return MB200_OK;
+}
+
+int mb200_svd_thin(mb200_handle_t h, void *U, void *S, void *Vt, const void *A, int dtype, int64_t rows, int64_t cols,
+                   double tol, int max_sweeps) {
+    MB200_CHECK_HANDLE(h);
+    if (!dtype_valid(dtype)) return fail(MB200_INVALID_ARGUMENT, "unknown dtype %d", dtype);
+    if (rows < 0 || cols < 0 || rows >= ((int64_t)1 << 31) || cols >= ((int64_t)1 << 31))
+        return fail(MB200_INVALID_ARGUMENT, "svd: bad shape %lld x %lld", (long long)rows, (long long)cols);
+    const int64_t k = std::min(rows, cols), m = std::max(rows, cols);
+    if (k == 0) return MB200_OK;
+    if (!U || !S || !Vt || !A) return fail(MB200_INVALID_ARGUMENT, "NULL data pointer");
+    if (tol <= 0) tol = std::sqrt((double)m) * (dtype_is_double(dtype) ? 2.220446049250313e-16 : 1.1920929e-7);
+    if (max_sweeps <= 0) max_sweeps = 30;
+    std::lock_guard<std::mutex> lk(h->mu);
+    MB200_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    void *G = nullptr, *V = nullptr;
+    int *counters = nullptr;
+    const size_t esz = dtype_size(dtype);
+    MB200_CUDA(cudaMallocAsync(&G, (size_t)m * k * esz, s));
+    MB200_CUDA(cudaMallocAsync(&V, (size_t)k * k * esz, s));
+    MB200_CUDA(cudaMallocAsync((void **)&counters, 2 * sizeof(int), s));
+    cudaError_t e = launch_svd(dtype, A, (int)rows, (int)cols, U, S, Vt, G, V, counters, tol, max_sweeps, s);
+    cudaFreeAsync(G, s);
+    cudaFreeAsync(V, s);
+    cudaFreeAsync(counters, s);
+    if (e != cudaSuccess) return cuda_fail(e, "svd launch");
+    h->stats.launches_svd++;
     h->stats.launches_total++;
     return MB200_OK;
 }

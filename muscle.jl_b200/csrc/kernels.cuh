@@ -94,6 +94,12 @@ struct HadamardParams {
 };
 cudaError_t launch_hadamard(int dtype, const HadamardParams &p, const void *A, const void *B, void *C, cudaStream_t s);
 
+// ---- thin SVD (svd.cu): one-sided Jacobi, cooperative launch ---------------------------------------------
+// A rows x cols (dense column-major) -> U rows x k, S k (real), Vt cols x k = conj(right vectors), k = min(rows, cols).
+// work_G: max(rows, cols) * k elements, work_V: k * k elements, counters: 2 ints.
+cudaError_t launch_svd(int dtype, const void *A, int rows, int cols, void *U, void *S, void *Vt, void *work_G, void *work_V,
+                       int *counters, double tol, int max_sweeps, cudaStream_t s);
+
 // ---- dtype promotion (mixed-eltype operands) -------------------------------------------------------
 cudaError_t launch_convert(int dtype_dst, void *dst, int dtype_src, const void *src, int64_t n,
                            cudaStream_t s);

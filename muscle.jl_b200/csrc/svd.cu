@@ -1,0 +1,248 @@
+// Thin SVD on the device for the callers of the hot path: `tensor_svd_thin`
+// (src/Operations/tensor_svd.jl:100-124: permutedims -> reshape -> LinearAlgebra.svd -> tensorify) and through it
+// `simple_update` (src/Operations/simple_update.jl:35-82). The reference calls LAPACK (host) or cuTensorNet
+// `gateSplit!` (ext/MusclecuTensorNetExt.jl); this is a hand-written one-sided Jacobi (Hestenes) SVD:
+//
+//   G <- A (m x n, m >= n; a wide matrix is factorised through its conjugate transpose), V <- I.
+//   Sweep: every column pair (p, q) once, in round-robin tournament order: n/2 disjoint pairs per step, one WARP per
+//   pair, all steps of a sweep separated by a grid-wide barrier (cooperative launch, every CTA resident).
+//   Pair update: alpha = |g_p|^2, beta = |g_q|^2, gamma = g_p^H g_q; if |gamma| > tol sqrt(alpha beta) the plane
+//   rotation that makes the two columns orthogonal is applied to G and V.
+//   Converged when a sweep rotates nothing: sigma_j = |g_j|, u_j = g_j / sigma_j, sorted descending by a rank count.
+//
+// One-sided Jacobi is backward stable and computes small singular values to high RELATIVE accuracy; columns stay
+// contiguous, so every access is a coalesced lane-strided walk down one or two columns (L2 resident at tensor-network
+// bond sizes). Cost per sweep: 3 m n^2 complex flops, n - 1 grid barriers.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+
+#include "kernels.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace mb200 {
+
+namespace {
+
+template <typename T> struct SvdTraits;
+template <> struct SvdTraits<float> { using R = float; static constexpr bool cplx = false; };
+template <> struct SvdTraits<double> { using R = double; static constexpr bool cplx = false; };
+template <> struct SvdTraits<float2> { using R = float; static constexpr bool cplx = true; };
+template <> struct SvdTraits<double2> { using R = double; static constexpr bool cplx = true; };
+
+__device__ __forceinline__ float conj_(float a) { return a; }
+__device__ __forceinline__ double conj_(double a) { return a; }
+__device__ __forceinline__ float2 conj_(float2 a) { return make_float2(a.x, -a.y); }
+__device__ __forceinline__ double2 conj_(double2 a) { return make_double2(a.x, -a.y); }
+__device__ __forceinline__ float abs2(float a) { return a * a; }
+__device__ __forceinline__ double abs2(double a) { return a * a; }
+__device__ __forceinline__ float abs2(float2 a) { return a.x * a.x + a.y * a.y; }
+__device__ __forceinline__ double abs2(double2 a) { return a.x * a.x + a.y * a.y; }
+// conj(a) * b accumulated into (re, im)
+__device__ __forceinline__ void cdot(float a, float b, float &re, float &) { re = fmaf(a, b, re); }
+__device__ __forceinline__ void cdot(double a, double b, double &re, double &) { re = fma(a, b, re); }
+__device__ __forceinline__ void cdot(float2 a, float2 b, float &re, float &im) {
+    re = fmaf(a.x, b.x, re); re = fmaf(a.y, b.y, re);
+    im = fmaf(a.x, b.y, im); im = fmaf(-a.y, b.x, im);
+}
+__device__ __forceinline__ void cdot(double2 a, double2 b, double &re, double &im) {
+    re = fma(a.x, b.x, re); re = fma(a.y, b.y, re);
+    im = fma(a.x, b.y, im); im = fma(-a.y, b.x, im);
+}
+// x' = c x - s conj(ph) y ; y' = s ph x + c y      (ph = gamma / |gamma|, real case: ph = +-1)
+template <typename R> __device__ __forceinline__ void rot(R &x, R &y, R c, R s, R phr, R) {
+    const R nx = c * x - s * phr * y, ny = s * phr * x + c * y;
+    x = nx; y = ny;
+}
+__device__ __forceinline__ void rot(float2 &x, float2 &y, float c, float s, float phr, float phi) {
+    // conj(ph) y = (phr y.x + phi y.y, phr y.y - phi y.x) ; ph x = (phr x.x - phi x.y, phr x.y + phi x.x)
+    const float2 nx = make_float2(c * x.x - s * (phr * y.x + phi * y.y), c * x.y - s * (phr * y.y - phi * y.x));
+    const float2 ny = make_float2(s * (phr * x.x - phi * x.y) + c * y.x, s * (phr * x.y + phi * x.x) + c * y.y);
+    x = nx; y = ny;
+}
+__device__ __forceinline__ void rot(double2 &x, double2 &y, double c, double s, double phr, double phi) {
+    const double2 nx = make_double2(c * x.x - s * (phr * y.x + phi * y.y), c * x.y - s * (phr * y.y - phi * y.x));
+    const double2 ny = make_double2(s * (phr * x.x - phi * x.y) + c * y.x, s * (phr * x.y + phi * x.x) + c * y.y);
+    x = nx; y = ny;
+}
+template <typename T, typename R> __device__ __forceinline__ T scale(T a, R f);
+template <> __device__ __forceinline__ float scale(float a, float f) { return a * f; }
+template <> __device__ __forceinline__ double scale(double a, double f) { return a * f; }
+template <> __device__ __forceinline__ float2 scale(float2 a, float f) { return make_float2(a.x * f, a.y * f); }
+template <> __device__ __forceinline__ double2 scale(double2 a, double f) { return make_double2(a.x * f, a.y * f); }
+template <typename T> __device__ __forceinline__ T one_of();
+template <> __device__ __forceinline__ float one_of<float>() { return 1.f; }
+template <> __device__ __forceinline__ double one_of<double>() { return 1.0; }
+template <> __device__ __forceinline__ float2 one_of<float2>() { return make_float2(1.f, 0.f); }
+template <> __device__ __forceinline__ double2 one_of<double2>() { return make_double2(1.0, 0.0); }
+template <typename T> __device__ __forceinline__ T zero_of_();
+template <> __device__ __forceinline__ float zero_of_<float>() { return 0.f; }
+template <> __device__ __forceinline__ double zero_of_<double>() { return 0.0; }
+template <> __device__ __forceinline__ float2 zero_of_<float2>() { return make_float2(0.f, 0.f); }
+template <> __device__ __forceinline__ double2 zero_of_<double2>() { return make_double2(0.0, 0.0); }
+
+template <typename R> __device__ __forceinline__ R warp_sum(R v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+struct SvdParams {
+    const void *A;      // rows x cols, dense column-major
+    void *G, *V;        // work: G (m x n), V (n x n)      [m >= n after the optional conjugate transpose]
+    void *U, *Vt;       // outputs: U (rows x k), Vt (cols x k) = conj(right singular vectors), k = min(rows, cols)
+    void *S;            // k singular values (real), descending
+    int *counters;      // [0] rotations of the current sweep, [1] sweeps done
+    int rows, cols, m, n, transposed;
+    double tol;
+    int max_sweeps;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) jacobi_svd_kernel(const __grid_constant__ SvdParams p) {
+    using R = typename SvdTraits<T>::R;
+    cg::grid_group grid = cg::this_grid();
+    const int m = p.m, n = p.n;
+    const T *A = reinterpret_cast<const T *>(p.A);
+    T *G = reinterpret_cast<T *>(p.G), *V = reinterpret_cast<T *>(p.V);
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (int64_t)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = tid >> 5, nwarps = nthreads >> 5;
+
+    // ---- init: G = A or A^H, V = I
+    for (int64_t e = tid; e < (int64_t)m * n; e += nthreads) {
+        const int i = (int)(e % m), j = (int)(e / m);
+        G[e] = p.transposed ? conj_(A[(int64_t)i * p.rows + j]) : A[e];
+    }
+    for (int64_t e = tid; e < (int64_t)n * n; e += nthreads) V[e] = (e % n == e / n) ? one_of<T>() : zero_of_<T>();
+    if (tid == 0) { p.counters[0] = 0; p.counters[1] = 0; }
+    grid.sync();
+
+    const int np = (n + 1) & ~1;          // players of the tournament (one dummy when n is odd)
+    const R tol = (R)p.tol;
+    for (int sweep = 0; sweep < p.max_sweeps && n > 1; sweep++) {
+        for (int r = 0; r < np - 1; r++) {
+            for (int64_t k = warp; k < np / 2; k += nwarps) {
+                int a, b;
+                if (k == 0) { a = np - 1; b = r; }
+                else { a = (int)((r + k) % (np - 1)); b = (int)((r - k + (np - 1)) % (np - 1)); }
+                const int pc = min(a, b), qc = max(a, b);
+                if (qc >= n) continue;    // the dummy player sits out
+                T *gp = G + (int64_t)pc * m, *gq = G + (int64_t)qc * m;
+                R alpha = 0, beta = 0, gre = 0, gim = 0;
+                for (int i = lane; i < m; i += 32) {
+                    const T x = gp[i], y = gq[i];
+                    alpha += abs2(x); beta += abs2(y);
+                    cdot(x, y, gre, gim);
+                }
+                alpha = warp_sum(alpha); beta = warp_sum(beta); gre = warp_sum(gre); gim = warp_sum(gim);
+                const R g2 = gre * gre + gim * gim;
+                if (!(g2 > tol * tol * alpha * beta) || g2 == (R)0) continue;
+                const R gabs = sqrt(g2);
+                const R zeta = (beta - alpha) / ((R)2 * gabs);
+                const R t = (zeta >= 0 ? (R)1 : (R)-1) / (fabs(zeta) + sqrt((R)1 + zeta * zeta));
+                const R c = (R)1 / sqrt((R)1 + t * t), s = c * t;
+                const R phr = gre / gabs, phi = gim / gabs;
+                for (int i = lane; i < m; i += 32) {
+                    T x = gp[i], y = gq[i];
+                    rot(x, y, c, s, phr, phi);
+                    gp[i] = x; gq[i] = y;
+                }
+                T *vp = V + (int64_t)pc * n, *vq = V + (int64_t)qc * n;
+                for (int i = lane; i < n; i += 32) {
+                    T x = vp[i], y = vq[i];
+                    rot(x, y, c, s, phr, phi);
+                    vp[i] = x; vq[i] = y;
+                }
+                if (lane == 0) atomicAdd(&p.counters[0], 1);
+            }
+            grid.sync();
+        }
+        const int rotated = *(volatile int *)&p.counters[0];
+        grid.sync();
+        if (tid == 0) { p.counters[0] = 0; p.counters[1] = sweep + 1; }
+        grid.sync();
+        if (rotated == 0) break;
+    }
+
+    // ---- singular values: column norms, first in column order
+    R *S = reinterpret_cast<R *>(p.S);
+    for (int64_t j = warp; j < n; j += nwarps) {
+        const T *g = G + (int64_t)j * m;
+        R a = 0;
+        for (int i = lane; i < m; i += 32) a += abs2(g[i]);
+        a = warp_sum(a);
+        if (lane == 0) S[j] = sqrt(a);
+    }
+    grid.sync();
+    // rank of column j among the norms (descending, ties by index), then scatter the normalised vectors
+    T *U = reinterpret_cast<T *>(p.U), *Vt = reinterpret_cast<T *>(p.Vt);
+    for (int64_t j = warp; j < n; j += nwarps) {
+        const R sj = S[j];
+        int rank = 0;
+        for (int i = lane; i < n; i += 32) {
+            const R si = S[i];
+            rank += (si > sj || (si == sj && i < j)) ? 1 : 0;
+        }
+        rank = (int)warp_sum((R)rank);
+        const R inv = sj > (R)0 ? (R)1 / sj : (R)0;
+        const T *g = G + (int64_t)j * m, *v = V + (int64_t)j * n;
+        // m >= n: left vectors are the normalised columns of G (m long), right vectors the columns of V (n long).
+        // transposed: A = V' S U'^H, so U <- V' and the right vectors <- U'.
+        T *left = p.transposed ? Vt : U;     // receives the m-long vectors
+        T *right = p.transposed ? U : Vt;    // receives the n-long vectors
+        for (int i = lane; i < m; i += 32) {
+            const T u = scale<T, R>(g[i], inv);
+            left[(int64_t)rank * m + i] = p.transposed ? conj_(u) : u;
+        }
+        for (int i = lane; i < n; i += 32) right[(int64_t)rank * n + i] = p.transposed ? v[i] : conj_(v[i]);
+    }
+    grid.sync();
+    // S sorted: every thread recomputes the rank of its entry (n is small) into a register, then writes after a barrier
+    R mine = 0;
+    int myrank = -1;
+    if (tid < n) {
+        mine = S[tid];
+        int rank = 0;
+        for (int i = 0; i < n; i++) {
+            const R si = S[i];
+            rank += (si > mine || (si == mine && i < (int)tid)) ? 1 : 0;
+        }
+        myrank = rank;
+    }
+    grid.sync();
+    if (myrank >= 0) S[myrank] = mine;
+}
+
+}  // namespace
+
+cudaError_t launch_svd(int dtype, const void *A, int rows, int cols, void *U, void *S, void *Vt, void *work_G, void *work_V,
+                       int *counters, double tol, int max_sweeps, cudaStream_t s) {
+    SvdParams p{};
+    p.A = A; p.G = work_G; p.V = work_V; p.U = U; p.Vt = Vt; p.S = S; p.counters = counters;
+    p.rows = rows; p.cols = cols;
+    p.transposed = rows < cols ? 1 : 0;
+    p.m = std::max(rows, cols); p.n = std::min(rows, cols);
+    p.tol = tol; p.max_sweeps = max_sweeps;
+    const void *fn;
+    switch (dtype) {
+        case MB200_F32: fn = (const void *)jacobi_svd_kernel<float>; break;
+        case MB200_F64: fn = (const void *)jacobi_svd_kernel<double>; break;
+        case MB200_C64: fn = (const void *)jacobi_svd_kernel<float2>; break;
+        default: fn = (const void *)jacobi_svd_kernel<double2>; break;
+    }
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0);
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // one warp per column pair: n/2 warps are enough; never more CTAs than can be resident (cooperative launch)
+    const int64_t want = std::max<int64_t>(1, ((int64_t)(p.n + 1) / 2 + 7) / 8);
+    const int grid = (int)std::min<int64_t>(want, (int64_t)sms * std::max(1, std::min(per_sm, 2)));
+    void *args[] = {(void *)&p};
+    return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(256), args, 0, s);
+}
+
+}  // namespace mb200

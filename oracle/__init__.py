@@ -18,6 +18,8 @@ from .muscle_oracle import (  # noqa: F401
 )
 from .family_oracle import (  # noqa: F401
     contract_path_oracle,
+    simple_update_theta,
+    tensor_svd_thin_base,
     hadamard_base,
     unary_einsum,
     unary_einsum_general,

@@ -126,3 +126,29 @@ def contract_path_oracle(arrays, inds_list, out, path):
         nxt += 1
     (x, ix), = live.values()
     return unary_einsum_general(out, x, ix)
+
+
+def tensor_svd_thin_base(a: np.ndarray, inds_a, inds_u, inds_v):
+    """`tensor_svd_thin(::BackendBase, A; inds_u, inds_v)` — src/Operations/tensor_svd.jl:100-124: permutedims to
+    [inds_u..., inds_v...], reshape to a matrix, LAPACK thin SVD, tensorify: U[inds_u..., s], s, Vt = conj(V)[inds_v..., s]
+    (numpy returns V^H, so Vt = (V^H)^T)."""
+    inds_a, inds_u, inds_v = list(inds_a), list(inds_u), list(inds_v)
+    left = tuple(a.shape[inds_a.index(i)] for i in inds_u)
+    right = tuple(a.shape[inds_a.index(i)] for i in inds_v)
+    amat = np.reshape(np.asfortranarray(np.transpose(a, [inds_a.index(i) for i in inds_u + inds_v])),
+                      (int(np.prod(left)), int(np.prod(right))), order="F")
+    u, s, vh = np.linalg.svd(amat, full_matrices=False)
+    k = s.shape[0]
+    U = np.reshape(np.asfortranarray(u), left + (k,), order="F")
+    Vt = np.reshape(np.asfortranarray(vh.T), right + (k,), order="F")
+    return _fortran(U), s, _fortran(Vt)
+
+
+def simple_update_theta(a, inds_a, b, inds_b, g, inds_g, ind_pa, ind_pb, ind_bond, ind_ga, ind_gb):
+    """Θ of `simple_update` — src/Operations/simple_update.jl:51-52: contract A·B over the bond, then with G over the
+    physical indices, and rename G's output physical indices to the sites' ones. Returns (Θ, inds)."""
+    from .muscle_oracle import binary_einsum
+    ab, iab = binary_einsum(a, list(inds_a), b, list(inds_b), dims=[ind_bond])
+    th, ith = binary_einsum(ab, iab, g, list(inds_g), dims=[ind_pa, ind_pb])
+    ren = {ind_ga: ind_pa, ind_gb: ind_pb}
+    return th, [ren.get(i, i) for i in ith]

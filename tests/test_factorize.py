@@ -1,0 +1,172 @@
+"""`tensor_svd_thin` / `simple_update`. Singular vectors are unique only up to phases (and any
+rotation inside a degenerate subspace), so parity is checked through the invariants the reference's own tests use
+(test/unit/operations/tensor_svd_thin.jl:24-38, simple_update.jl:33-70): index/shape bookkeeping, singular values
+against LAPACK (the oracle), reconstruction A = U·s·Vt, isometry of U and Vt, descending order."""
+import numpy as np
+import pytest
+
+from cases import random_array
+from oracle import rel_frobenius, simple_update_theta, tensor_svd_thin_base
+
+DTYPES = ["float32", "float64", "complex64", "complex128"]
+TOL = {"float32": 2e-5, "complex64": 2e-5, "float64": 1e-12, "complex128": 1e-12}
+
+SVD_SHAPES = [((2, 4, 6, 8), "ijkl", "ij"), ((2, 4, 6, 8), "ijkl", "ikl"), ((2, 4, 6, 8), "ijkl", "l"), ((2, 4, 6, 8), "ijkl", "kj"),
+              ((64, 64), "ab", "a"), ((200, 37), "ab", "a"), ((37, 200), "ab", "a"), ((1, 5), "ab", "a"), ((5, 1), "ab", "a"),
+              ((33, 33), "ab", "b"), ((16, 2, 16, 2), "lpqr", "lp")]
+
+
+def _gamma():
+    # test/unit/operations/simple_update.jl:8-31: MPS factorisation of |00>+|01>+|10>+|11>, identity and CX gates
+    ga = np.eye(2)
+    gb = np.eye(2)
+    ident = np.reshape(np.eye(4), (2, 2, 2, 2), order="F")
+    cx = np.reshape(np.array([[1.0, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0]]), (2, 2, 2, 2), order="F")
+    return ga, gb, ident, cx
+
+
+# ------------------------------------------------------------------------------------------------ CPU
+def test_factorinds_rules():
+    import muscle_b200 as mb
+    I = lambda s: [mb.Index(c) for c in s]
+    assert mb.factorinds(I("ijkl"), I("ij"), []) == (I("ij"), I("kl"))
+    assert mb.factorinds(I("ijkl"), [], I("l")) == (I("ijk"), I("l"))
+    assert mb.factorinds(I("ijkl"), I("ki"), I("jl")) == (I("ki"), I("jl"))
+    for lu, lv in ((I("z"), []), ([], I("z")), (I("ijkl"), []), ([], I("ijkl")), (I("ij"), I("jk"))):
+        with pytest.raises(mb.ArgumentError):                   # tensor_svd_thin.jl:10-18
+            mb.factorinds(I("ijkl"), lu, lv)
+    A = mb.Tensor(np.ones((2, 4, 6, 8)), I("ijkl"))
+    with pytest.raises(mb.ArgumentError):                       # :9 (no inds given), host tensor -> reference backend
+        mb.tensor_svd_thin(A)
+
+
+def test_oracle_svd_and_simple_update_reference_known_answers():
+    rng = np.random.default_rng(0)
+    a = random_array(rng, (2, 4, 6, 8), "complex128")
+    U, s, Vt = tensor_svd_thin_base(a, list("ijkl"), list("ij"), list("kl"))
+    assert U.shape == (2, 4, 8) and s.shape == (8,) and Vt.shape == (6, 8, 8)          # tensor_svd_thin.jl:28-30
+    assert rel_frobenius(np.einsum("ijx,x,klx->ijkl", U, s, Vt), a) < 1e-13             # :32
+    assert np.allclose(np.einsum("ijx,ijy->xy", U.conj(), U), np.eye(8))                 # :33 isisometry
+    ga, gb, ident, cx = _gamma()
+    for g, sv in ((ident, [1.0, 1.0]), (cx, [np.sqrt(2.0), 0.0])):                      # simple_update.jl:47, :68
+        th, ith = simple_update_theta(ga, ["pa", "bond"], gb, ["pb", "bond"], g, ["pa", "pb", "ga", "gb"],
+                                      "pa", "pb", "bond", "ga", "gb")
+        assert ith == ["pa", "pb"]
+        _, s, _ = tensor_svd_thin_base(th, ith, ["pa"], ["pb"])
+        assert np.allclose(s, sv, atol=1e-15)
+        assert np.isclose(np.sum(np.abs(th) ** 2), 2.0)                                  # :49-50, :70-71
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+def _check_svd(mb, a, inds, inds_u, dt):
+    I = lambda s: [mb.Index(c) for c in s]
+    A = mb.Tensor(a, I(inds)).to_device()
+    U, S, Vt = mb.tensor_svd_thin(A, inds_u=I(inds_u), ind_s=mb.Index("x"))
+    inds_v = [c for c in inds if c not in inds_u]
+    assert U.inds == I(inds_u) + [mb.Index("x")] and S.inds == [mb.Index("x")] and Vt.inds == I(inds_v) + [mb.Index("x")]
+    u, s, vt = U.to_host().data, S.to_host().data, Vt.to_host().data
+    wide = np.complex128 if np.dtype(dt).kind == "c" else np.float64
+    Uo, so, Vto = tensor_svd_thin_base(a.astype(wide), list(inds), list(inds_u), inds_v)
+    assert u.shape == Uo.shape and s.shape == so.shape and vt.shape == Vto.shape
+    assert s.dtype == (np.float32 if dt in ("float32", "complex64") else np.float64)
+    assert np.all(np.diff(s) <= 0) and np.all(s >= 0)                       # descending, non-negative
+    assert np.linalg.norm(s - so) <= TOL[dt] * max(np.linalg.norm(so), 1e-300)
+    k = s.shape[0]
+    um, vm = u.reshape(-1, k, order="F").astype(wide), vt.reshape(-1, k, order="F").astype(wide)
+    ref = np.transpose(a, [inds.index(c) for c in list(inds_u) + inds_v]).reshape(um.shape[0], vm.shape[0], order="F")
+    rec = (um * s.astype(wide)) @ vm.T
+    assert rel_frobenius(rec, ref.astype(wide)) <= TOL[dt]                  # A = U s Vt
+    keep = s > 1e-3 * s[0] if s[0] > 0 else np.zeros(k, bool)               # isometry on the numerically non-null part
+    gu = um[:, keep].conj().T @ um[:, keep]
+    gv = vm[:, keep].conj().T @ vm[:, keep]
+    assert np.linalg.norm(gu - np.eye(keep.sum())) <= 50 * TOL[dt] * max(1, keep.sum())
+    assert np.linalg.norm(gv - np.eye(keep.sum())) <= 50 * TOL[dt] * max(1, keep.sum())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("shape,inds,inds_u", SVD_SHAPES)
+def test_tensor_svd_thin_parity(shape, inds, inds_u, dt):
+    import muscle_b200 as mb
+    rng = np.random.default_rng(21)
+    _check_svd(mb, random_array(rng, shape, dt), inds, inds_u, dt)
+
+
+@pytest.mark.gpu
+def test_tensor_svd_thin_rank_deficient_and_larger():
+    import muscle_b200 as mb
+    rng = np.random.default_rng(22)
+    for dt in ("complex128", "float32"):
+        low = random_array(rng, (48, 5), dt) @ random_array(rng, (5, 40), dt)     # rank 5
+        _check_svd(mb, np.asfortranarray(low), "ab", "a", dt)
+        _check_svd(mb, np.zeros((6, 4), dt), "ab", "a", dt)
+    _check_svd(mb, random_array(rng, (256, 2, 192, 2), "complex128"), "lpqr", "lp", "complex128")   # 512 x 384
+    assert mb.Handle.get(0).stats()["launches_svd"] > 0
+
+
+@pytest.mark.gpu
+def test_tensor_svd_thin_rejects_like_the_reference():
+    import muscle_b200 as mb
+    I = lambda s: [mb.Index(c) for c in s]
+    A = mb.Tensor(np.ones((2, 4, 6, 8)), I("ijkl")).to_device()
+    for kw in (dict(), dict(inds_u=I("z")), dict(inds_v=I("z")), dict(inds_u=I("ijkl")), dict(inds_v=I("ijkl")),
+               dict(inds_u=I("i"), ind_s=mb.Index("j"))):                           # tensor_svd_thin.jl:9-21
+        with pytest.raises(mb.ArgumentError):
+            mb.tensor_svd_thin(A, **kw)
+
+
+@pytest.mark.gpu
+def test_simple_update_reference_battery():
+    """test/unit/operations/simple_update.jl:33-200 on BackendB200 (device tensors and host tensors via with_backend)."""
+    import muscle_b200 as mb
+    ga, gb, ident, cx = _gamma()
+    Ia, Ib, Ibond, Iga, Igb = (mb.Index(("site", 1, "cut", 1)), mb.Index(("site", 2, "cut", 1)), mb.Index(("bond", 1, 2)),
+                               mb.Index(("site", 1, "cut", 2)), mb.Index(("site", 2, "cut", 2)))
+    for dev in (True, False):
+        mk = (lambda x, ix: mb.Tensor(x, ix).to_device()) if dev else (lambda x, ix: mb.Tensor(x, ix))
+        run = (lambda f: f()) if dev else (lambda f: mb.with_backend(f, mb.BackendB200()))
+        Ga, Gb = mk(ga, [Ia, Ibond]), mk(gb, [Ib, Ibond])
+        for gate, sv in ((ident, [1.0, 1.0]), (cx, [np.sqrt(2.0), 0.0])):
+            Gt = mk(gate, [Ia, Ib, Iga, Igb])
+            U, s, V = run(lambda: mb.simple_update(Ga, Ia, Gb, Ib, Ibond, Gt, Iga, Igb))
+            assert U.inds == [Ia, Ibond] and V.inds == [Ib, Ibond] and s.inds == [Ibond]
+            assert np.allclose(s.to_host().data, sv, atol=1e-14)
+            psi = run(lambda: mb.binary_einsum(mb.hadamard(U, s), V))                 # :49-50
+            assert np.isclose(np.sum(np.abs(psi.to_host().data) ** 2), 2.0)
+            Un, sn, Vn = run(lambda: mb.simple_update(Ga, Ia, Gb, Ib, Ibond, Gt, Iga, Igb, normalize=True))
+            assert np.isclose(np.linalg.norm(sn.to_host().data), 1.0)                 # normalize (:73-95)
+            for absorb in (mb.AbsorbU(), mb.AbsorbV(), mb.AbsorbEqually()):           # absorb variants (:97-200)
+                Ua, Va = run(lambda: mb.simple_update(Ga, Ia, Gb, Ib, Ibond, Gt, Iga, Igb, absorb=absorb))
+                psi2 = run(lambda: mb.binary_einsum(Ua, Va))
+                assert rel_frobenius(psi2.to_host().data, psi.to_host().data) <= 1e-13
+            Um, sm, Vm = run(lambda: mb.simple_update(Ga, Ia, Gb, Ib, Ibond, Gt, Iga, Igb, maxdim=1))
+            assert sm.shape == (1,) and Um.shape == (2, 1) and Vm.shape == (2, 1)
+            assert np.isclose(sm.to_host().data[0], sv[0])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dt", ["complex128", "complex64"])
+def test_simple_update_random_mps_sites(dt):
+    """Two random MPS sites (chi = 24, d = 2) and a random two-site gate: Θ and its singular values against the
+    oracle (binary_einsum restatement + LAPACK), reconstruction of Θ from (U, s, V), truncation to maxdim."""
+    import muscle_b200 as mb
+    rng = np.random.default_rng(30)
+    chi, d = 24, 2
+    a, b = random_array(rng, (chi, d, chi), dt), random_array(rng, (chi, d, chi), dt)
+    g = random_array(rng, (d, d, d, d), dt)
+    I = mb.Index
+    ia, ib, ig = [I("l"), I("pa"), I("bond")], [I("bond"), I("pb"), I("r")], [I("pa"), I("pb"), I("ga"), I("gb")]
+    A, B, G = (mb.Tensor(x, ix).to_device() for x, ix in ((a, ia), (b, ib), (g, ig)))
+    U, s, V = mb.simple_update(A, I("pa"), B, I("pb"), I("bond"), G, I("ga"), I("gb"))
+    wide = np.complex128
+    th, ith = simple_update_theta(a.astype(wide), ["l", "pa", "bond"], b.astype(wide), ["bond", "pb", "r"], g.astype(wide),
+                                  ["pa", "pb", "ga", "gb"], "pa", "pb", "bond", "ga", "gb")
+    _, so, _ = tensor_svd_thin_base(th, ith, ["l", "pa"], ["pb", "r"])
+    tol = 1e-12 if dt == "complex128" else 2e-5
+    assert U.inds == [I("l"), I("pa"), I("bond")] and V.inds == [I("pb"), I("r"), I("bond")]
+    assert np.linalg.norm(s.to_host().data - so) <= tol * np.linalg.norm(so)
+    rec = mb.binary_einsum(mb.hadamard(U, s), V, out=[I(c) for c in ith]).to_host().data
+    assert rel_frobenius(rec.astype(wide), th) <= tol
+    Ut, st, Vt = mb.simple_update(A, I("pa"), B, I("pb"), I("bond"), G, I("ga"), I("gb"), maxdim=chi)
+    assert st.shape == (chi,) and Ut.shape == (chi, d, chi) and Vt.shape == (d, chi, chi)
+    assert np.linalg.norm(st.to_host().data - so[:chi]) <= tol * np.linalg.norm(so)

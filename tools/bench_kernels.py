@@ -124,6 +124,21 @@ def main():
     P.append(permute_case("f64 rank6 dim16 reverse", (16,) * 6 + (2,), (5, 4, 3, 2, 1, 0, 6), "float64"))
     P.append(permute_case("qubit rank-26 c64 bit reversal", (2,) * 26, tuple(range(25, -1, -1)), "complex64") if False else
              permute_case("qubit rank-16 (dim 2 x13, 4096 tail) c64 reversal", (2,) * 13 + (4096,), tuple(range(13, -1, -1)), "complex64"))
+    if "--svd" in sys.argv:
+        import time
+        from muscle_b200 import tensor_svd_thin
+        rows = []
+        for n, dt in ((128, "complex128"), (256, "complex128"), (512, "complex128"), (1024, "complex128"), (512, "complex64")):
+            A = Tensor(dev_rand((n, n), dt), I("ab"))
+            fn = lambda: tensor_svd_thin(A, inds_u=I("a"), ind_s=Index("s"))
+            best, mean = timeit(fn, iters=3, warm=1)
+            host = A.to_host().data
+            t0 = time.perf_counter(); np.linalg.svd(host, full_matrices=False); cpu = (time.perf_counter() - t0) * 1e3
+            rows.append({"n": n, "dtype": dt, "ms_best": best, "ms_mean": mean, "numpy_lapack_ms": cpu})
+            print(f"SVD     {n}x{n} {dt:<11s} jacobi {best:9.2f} ms   numpy/LAPACK on host {cpu:9.2f} ms")
+        os.makedirs("gpurun_out", exist_ok=True)
+        json.dump({"svd": rows}, open("gpurun_out/kernels_svd.json", "w"), indent=1)
+        return
     if "--family" in sys.argv:
         out["family"] = family_cases()
         for r in out["family"]:
