@@ -28,6 +28,12 @@
 // memory (forcing BN = 64 makes the GEMM 1.77x slower). A variant issuing six N = 256 MMAs over concatenated
 // [re;im] column-operand planes (25 % fewer smem bytes) was built and verified: GEMM 2.21 -> 2.13 ms but the pack
 // and DRAM traffic grow by the same amount, so it was not kept.
+// Stream-K (balanced (tile, 128-k chunk) unit ranges per CTA, tiles cut between two CTAs finished through a
+// flag-ordered workspace hand-over) was also built and verified bit-exact: for 256 tiles on 148 SMs (one 2048^3
+// batch of config 3) it gained 2.6 % instead of the 13 % the wave arithmetic promises, and contiguous unit ranges
+// lost up to 18 % elsewhere (CTAs walk distant tiles concurrently, the packed panels stop hitting in L2). The kernel
+// is POWER-bound (1.57 GHz of 1.965): SMs idle in a ragged last wave let the busy ones clock higher, so balancing
+// the waves buys almost nothing. Not kept.
 #include <cuda.h>
 #include <cuda_runtime.h>
 

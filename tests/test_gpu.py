@@ -398,6 +398,26 @@ def test_tcgen05_accuracy_beats_plain_tf32():
     assert errr <= 5e-6, errr
 
 
+@pytest.mark.parametrize("dt,m,n,k", [("complex64", 2048, 2048, 520), ("complex64", 1920, 2304, 264), ("float32", 2304, 2560, 392),
+                                      ("float32", 4096, 4096, 128 * 3), ("complex64", 1300, 2000, 1032)])
+def test_tcgen05_ragged_waves(dt, m, n, k):
+    """Tile counts that leave a ragged last wave on the 148 persistent CTAs, ragged M / N edges and a partial last
+    128-k chunk: integer-valued inputs must come out bit-exact."""
+    rng = np.random.default_rng(5)
+    a = integer_array(rng, (k, m), dt, lo=-2, hi=3)
+    b = integer_array(rng, (k, n), dt, lo=-2, hi=3)
+    wide = np.complex128 if dt == "complex64" else np.float64
+    ref = (a.astype(wide).T @ b.astype(wide)).astype(dt)
+    h = _lib.Handle.get()
+    h.reset_stats()
+    got = contract(a, "ki", b, "kj", "ij", path=mb.PATH_TCGEN05_TF32)
+    assert h.stats()["launches_tcgen05"] == 1
+    assert np.array_equal(got, ref)
+    ar, br = random_array(rng, (k, m), dt), random_array(rng, (k, n), dt)
+    got = contract(ar, "ki", br, "kj", "ij", path=mb.PATH_TCGEN05_TF32)
+    assert rel_frobenius(got.astype(wide), ar.astype(wide).T @ br.astype(wide)) <= 1e-5
+
+
 def test_tcgen05_auto_selected_for_large_c64():
     info = mb.plan_describe(_lib.C64, [0, 2, 4, 5, 6], _lib.C64, [0, 1, 2, 3, 6], [256, 8, 8, 256, 8],
                             _lib.C64, [3, 1, 4, 5, 6], [256, 8, 8, 256, 8])
