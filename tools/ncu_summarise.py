@@ -18,6 +18,8 @@ METRICS = [
     "sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active",
     "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_uniform.sum", "smsp__cycles_active.avg", "sm__cycles_elapsed.avg.per_second",
     "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__inst_issued.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
     "launch__registers_per_thread", "launch__shared_mem_per_block_allocated", "launch__waves_per_multiprocessor",
@@ -50,7 +52,8 @@ def main():
     traffic = {}
     for rep, title in (("prof_gett.ncu-rep", "gett kernels inside one bench step (2a, 2b, 2c)"),
                        ("prof_permute.ncu-rep", "K1 permute kernels (tools/bench_kernels.py, first cases)"),
-                       ("prof_tf32.ncu-rep", "K3 tcgen05 3xTF32 kernel")):
+                       ("prof_tf32.ncu-rep", "K3 tcgen05 3xTF32 kernels and their K1 split-writer packs (configs 3, 5; 8192^3 Float32)"),
+                       ("prof_family.ncu-rep", "hadamard / unary_einsum streaming kernels")):
         path = os.path.join(OUT, rep)
         if not os.path.exists(path):
             continue
