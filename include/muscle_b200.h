@@ -169,6 +169,12 @@ int mb200_hadamard(mb200_handle_t handle, void *C, int dtypeC,
 int mb200_svd_thin(mb200_handle_t handle, void *U, void *S, void *Vt, const void *A, int dtype,
                    int64_t rows, int64_t cols, double tol, int max_sweeps);
 
+/* Thin QR: A (rows x cols, dense column-major, device) = Q * R with k = min(rows, cols): Q rows x k (orthonormal
+ * columns), R k x cols (upper triangular) - the two arrays `tensor_qr_thin(::BackendBase, A)` tensorifies
+ * (src/Operations/tensor_qr.jl:57-79). Hand-written Householder (svd.cu); R's diagonal carries the phase
+ * -e^{i arg x_0} (QR is unique up to a diagonal phase). Stream-ordered. */
+int mb200_qr_thin(mb200_handle_t handle, void *Q, void *R, const void *A, int dtype, int64_t rows, int64_t cols);
+
 /* ---- multi-GPU partition planner (host only) ------------------------------------------------
  * One process per GPU (torch.distributed / NCCL does the plumbing). Mirrors Dagger's block
  * sharding, ext/MuscleDaggerExt/binary_einsum.jl:64-119: splitting a free or batch mode gives

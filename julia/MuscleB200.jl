@@ -234,6 +234,25 @@ function Muscle.tensor_svd_thin(::BackendB200, A::Tensor; inds_u=(), inds_v=(), 
     end
     return Tensor(U, [inds_u; ind_s]), Tensor(S, [ind_s]), Tensor(Vt, [inds_v; ind_s])
 end
+# tensor_qr_thin(::BackendB200, A; inds_q, inds_r, ind_virtual) — replaces src/Operations/tensor_qr.jl:57-79
+Muscle.choose_backend_rule(::typeof(Muscle.tensor_qr_thin), ::DomainB200) = BackendB200()
+function Muscle.tensor_qr_thin(::BackendB200, A::Tensor; inds_q=(), inds_r=(), ind_virtual=Index(gensym(:qr)), kwargs...)
+    ind_virtual ∉ inds(A) || throw(ArgumentError("new virtual bond name ($ind_virtual) cannot be already be present"))
+    inds_q, inds_r = Muscle.factorinds(inds(A), inds_q, inds_r)
+    left, right = map(i -> size(A, i), inds_q), map(i -> size(A, i), inds_r)
+    Amat = permutedims(A, [inds_q..., inds_r...])
+    T, k = eltype(A), min(prod(left), prod(right))
+    Q = B200Array{T,length(left) + 1}(undef, (left..., k))
+    R = B200Array{T,length(right) + 1}(undef, (k, right...))
+    pA = parent(Amat)
+    GC.@preserve pA Q R begin
+        check(ccall((:mb200_qr_thin, libmuscle_b200[]), Cint,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Int64, Int64),
+            handle().ptr, Q.ptr, R.ptr, pointer_of(pA), dtype_enum(T), prod(left), prod(right)))
+        sync()
+    end
+    return Tensor(Q, [inds_q..., ind_virtual]), Tensor(R, [ind_virtual, inds_r...])
+end
 # `simple_update(::Backend, ...)` (src/Operations/simple_update.jl:35-82) is written against binary_einsum,
 # tensor_svd_thin and hadamard! only, so with the methods above it runs on B200Arrays unchanged.
 

@@ -138,3 +138,5 @@ register_rule("tensor_svd_thin", (DomainHost,), BackendBase())
 register_rule("tensor_svd_thin", (DomainB200,), BackendB200())
 register_rule("simple_update", (DomainHost, DomainHost, DomainHost), BackendBase())
 register_rule("simple_update", (DomainB200, DomainB200, DomainB200), BackendB200())
+register_rule("tensor_qr_thin", (DomainHost,), BackendBase())
+register_rule("tensor_qr_thin", (DomainB200,), BackendB200())

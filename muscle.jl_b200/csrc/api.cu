@@ -837,6 +837,32 @@ int mb200_svd_thin(mb200_handle_t h, void *U, void *S, void *Vt, const void *A, 
     return MB200_OK;
 }
 
+int mb200_qr_thin(mb200_handle_t h, void *Q, void *R, const void *A, int dtype, int64_t rows, int64_t cols) {
+    MB200_CHECK_HANDLE(h);
+    if (!dtype_valid(dtype)) return fail(MB200_INVALID_ARGUMENT, "unknown dtype %d", dtype);
+    if (rows < 0 || cols < 0 || rows >= ((int64_t)1 << 31) || cols >= ((int64_t)1 << 31))
+        return fail(MB200_INVALID_ARGUMENT, "qr: bad shape %lld x %lld", (long long)rows, (long long)cols);
+    const int64_t k = std::min(rows, cols);
+    if (k == 0) return MB200_OK;
+    if (!Q || !R || !A) return fail(MB200_INVALID_ARGUMENT, "NULL data pointer");
+    std::lock_guard<std::mutex> lk(h->mu);
+    MB200_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const size_t esz = dtype_size(dtype);
+    void *W = nullptr, *rd = nullptr, *tau = nullptr;
+    MB200_CUDA(cudaMallocAsync(&W, (size_t)rows * cols * esz, s));
+    MB200_CUDA(cudaMallocAsync(&rd, (size_t)k * esz, s));
+    MB200_CUDA(cudaMallocAsync(&tau, (size_t)k * sizeof(double), s));
+    cudaError_t e = launch_qr(dtype, A, (int)rows, (int)cols, Q, R, W, rd, tau, s);
+    cudaFreeAsync(W, s);
+    cudaFreeAsync(rd, s);
+    cudaFreeAsync(tau, s);
+    if (e != cudaSuccess) return cuda_fail(e, "qr launch");
+    h->stats.launches_svd++;
+    h->stats.launches_total++;
+    return MB200_OK;
+}
+
 int mb200_shard_plan(int nmodeC, const int32_t *modesC, int nmodeA, const int32_t *modesA,
                      const int64_t *extentsA, int nmodeB, const int32_t *modesB, const int64_t *extentsB,
                      int nranks, int rank, int prefer_sum, mb200_shard_info_t *info) {

@@ -100,6 +100,11 @@ cudaError_t launch_hadamard(int dtype, const HadamardParams &p, const void *A, c
 cudaError_t launch_svd(int dtype, const void *A, int rows, int cols, void *U, void *S, void *Vt, void *work_G, void *work_V,
                        int *counters, double tol, int max_sweeps, cudaStream_t s);
 
+// thin QR (Householder): A m x n -> Q m x k, R k x n (k = min(m, n)); work_W m*n elements, work_rd k elements,
+// work_tau k reals
+cudaError_t launch_qr(int dtype, const void *A, int m, int n, void *Q, void *Rm, void *work_W, void *work_rd, void *work_tau,
+                      cudaStream_t s);
+
 // ---- dtype promotion (mixed-eltype operands) -------------------------------------------------------
 cudaError_t launch_convert(int dtype_dst, void *dst, int dtype_src, const void *src, int64_t n,
                            cudaStream_t s);

@@ -13,6 +13,13 @@
 // One-sided Jacobi is backward stable and computes small singular values to high RELATIVE accuracy; columns stay
 // contiguous, so every access is a coalesced lane-strided walk down one or two columns (L2 resident at tensor-network
 // bond sizes). Cost per sweep: 3 m n^2 complex flops, n - 1 grid barriers.
+//
+// Measured (ncu, 128 x 128 ComplexF64): ~11 sweeps to converge, 4.3 us per tournament step, and the step is an
+// instruction-latency chain inside one warp (720 warp instructions per step, issue slots 19 % busy), not a barrier or
+// a memory problem: a single-cluster variant with W = [G; V] in distributed shared memory and cluster barriers was
+// built, verified and measured SLOWER (7.3 vs 5.4 ms at 128^2, 24.8 vs 12.8 ms at 256^2 ComplexF32: 64 warps instead of
+// a warp per pair) and was dropped. The next lever is more lanes per pair (a CTA per pair with a shared-memory
+// reduction) or a blocked Jacobi whose inner products run on the DMMA gather-GEMM.
 #include <cooperative_groups.h>
 
 #include <algorithm>
@@ -82,6 +89,11 @@ template <> __device__ __forceinline__ double zero_of_<double>() { return 0.0; }
 template <> __device__ __forceinline__ float2 zero_of_<float2>() { return make_float2(0.f, 0.f); }
 template <> __device__ __forceinline__ double2 zero_of_<double2>() { return make_double2(0.0, 0.0); }
 
+// 1 / sqrt(x): the FP64 rsqrt is accurate to the last bits; rsqrtf is a 2-ulp approximation that makes c^2 + s^2 drift
+// from 1 over thousands of rotations (ComplexF32 singular values 1e-5 -> 5e-5), so Float32 takes the rounded form
+__device__ __forceinline__ double inv_sqrt(double x) { return rsqrt(x); }
+__device__ __forceinline__ float inv_sqrt(float x) { return 1.0f / sqrtf(x); }
+
 template <typename R> __device__ __forceinline__ R warp_sum(R v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -139,11 +151,13 @@ __global__ void __launch_bounds__(256) jacobi_svd_kernel(const __grid_constant__
                 alpha = warp_sum(alpha); beta = warp_sum(beta); gre = warp_sum(gre); gim = warp_sum(gim);
                 const R g2 = gre * gre + gim * gim;
                 if (!(g2 > tol * tol * alpha * beta) || g2 == (R)0) continue;
-                const R gabs = sqrt(g2);
-                const R zeta = (beta - alpha) / ((R)2 * gabs);
+                // four slow operations (rsqrt, sqrt, div, rsqrt) instead of eight: FP64 sqrt / div are ~40-instruction
+                // sequences and this scalar chain is a third of a step's instructions (ncu: 720 per warp per step)
+                const R inv_g = inv_sqrt(g2);
+                const R zeta = (R)0.5 * (beta - alpha) * inv_g;
                 const R t = (zeta >= 0 ? (R)1 : (R)-1) / (fabs(zeta) + sqrt((R)1 + zeta * zeta));
-                const R c = (R)1 / sqrt((R)1 + t * t), s = c * t;
-                const R phr = gre / gabs, phi = gim / gabs;
+                const R c = inv_sqrt((R)1 + t * t), s = c * t;
+                const R phr = gre * inv_g, phi = gim * inv_g;
                 for (int i = lane; i < m; i += 32) {
                     T x = gp[i], y = gq[i];
                     rot(x, y, c, s, phr, phi);
@@ -215,6 +229,106 @@ __global__ void __launch_bounds__(256) jacobi_svd_kernel(const __grid_constant__
     if (myrank >= 0) S[myrank] = mine;
 }
 
+
+// ---- thin QR (Householder) --------------------------------------------------------------------------------
+// `tensor_qr_thin` (src/Operations/tensor_qr.jl:57-79: permutedims -> reshape -> LinearAlgebra.qr -> Matrix(F.Q),
+// Matrix(F.R)). A (m x n) = Q (m x k) R (k x n), k = min(m, n). Cooperative kernel, one warp per column:
+//   for j < k:  warp 0 builds the reflector H_j = I - tau v v^H from W[j:, j] (v stored in place, R_jj kept aside);
+//               grid barrier; every trailing column c > j gets W[j:, c] -= tau v (v^H W[j:, c]); grid barrier
+//   Q = H_0 ... H_{k-1} [I; 0]: reflectors applied backwards to the columns c >= j that can be non-trivial.
+// Reflectors are Hermitian (real tau = 2 / v^H v), so R's diagonal is -e^{i arg x_0} |x|: QR is unique up to that
+// diagonal phase, which is all the reference's tests pin (Q R = A, Q isometric).
+struct QrParams {
+    const void *A;
+    void *W;        // m x n work copy
+    void *Q, *Rm;   // m x k, k x n
+    void *rd;       // k diagonal entries of R
+    void *tau;      // k reals
+    int m, n, k;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) householder_qr_kernel(const __grid_constant__ QrParams p) {
+    using R = typename SvdTraits<T>::R;
+    cg::grid_group grid = cg::this_grid();
+    const int m = p.m, n = p.n, k = p.k;
+    const T *A = reinterpret_cast<const T *>(p.A);
+    T *W = reinterpret_cast<T *>(p.W), *Q = reinterpret_cast<T *>(p.Q), *Rm = reinterpret_cast<T *>(p.Rm);
+    T *rd = reinterpret_cast<T *>(p.rd);
+    R *tau = reinterpret_cast<R *>(p.tau);
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (int64_t)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = tid >> 5, nwarps = nthreads >> 5;
+    for (int64_t e = tid; e < (int64_t)m * n; e += nthreads) W[e] = A[e];
+    for (int64_t e = tid; e < (int64_t)m * k; e += nthreads) Q[e] = (e % m == e / m) ? one_of<T>() : zero_of_<T>();
+    grid.sync();
+    for (int j = 0; j < k; j++) {
+        if (warp == 0) {   // reflector from x = W[j:, j]
+            T *x = W + (int64_t)j * m;
+            R nrm2 = 0;
+            for (int i = j + lane; i < m; i += 32) nrm2 += abs2(x[i]);
+            nrm2 = warp_sum(nrm2);
+            const T x0 = x[j];
+            const R ax0 = sqrt(abs2(x0)), nrm = sqrt(nrm2);
+            if (lane == 0) {
+                if (nrm > (R)0) {
+                    // e^{i theta} = x0 / |x0| (1 when x0 == 0); v = x + e^{i theta} |x| e_1; H x = -e^{i theta} |x| e_1
+                    const T ph = ax0 > (R)0 ? scale<T, R>(x0, (R)1 / ax0) : one_of<T>();
+                    tau[j] = (R)1 / (nrm * (nrm + ax0));
+                    rd[j] = scale<T, R>(ph, -nrm);
+                    x[j] = scale<T, R>(ph, ax0 + nrm);
+                } else {
+                    tau[j] = (R)0;
+                    rd[j] = zero_of_<T>();
+                }
+            }
+        }
+        grid.sync();
+        const R tj = tau[j];
+        const T *v = W + (int64_t)j * m;
+        if (tj != (R)0) {
+            for (int64_t c = j + 1 + warp; c < n; c += nwarps) {
+                T *w = W + c * m;
+                R re = 0, im = 0;
+                for (int i = j + lane; i < m; i += 32) cdot(v[i], w[i], re, im);
+                re = warp_sum(re) * tj; im = warp_sum(im) * tj;
+                for (int i = j + lane; i < m; i += 32) {   // w -= tau (v^H w) v
+                    T vi = v[i], wi = w[i];
+                    if constexpr (SvdTraits<T>::cplx) { wi.x -= vi.x * re - vi.y * im; wi.y -= vi.x * im + vi.y * re; }
+                    else wi -= vi * re;
+                    w[i] = wi;
+                }
+            }
+        }
+        grid.sync();
+    }
+    // R: upper triangle of W with the saved diagonal
+    for (int64_t e = tid; e < (int64_t)k * n; e += nthreads) {
+        const int i = (int)(e % k), c = (int)(e / k);
+        Rm[e] = i < c ? W[(int64_t)c * m + i] : (i == c ? rd[i] : zero_of_<T>());
+    }
+    // Q = H_0 ... H_{k-1} [I; 0]
+    for (int j = k - 1; j >= 0; j--) {
+        const R tj = tau[j];
+        const T *v = W + (int64_t)j * m;
+        if (tj != (R)0) {
+            for (int64_t c = j + warp; c < k; c += nwarps) {
+                T *q = Q + c * m;
+                R re = 0, im = 0;
+                for (int i = j + lane; i < m; i += 32) cdot(v[i], q[i], re, im);
+                re = warp_sum(re) * tj; im = warp_sum(im) * tj;
+                for (int i = j + lane; i < m; i += 32) {
+                    T vi = v[i], qi = q[i];
+                    if constexpr (SvdTraits<T>::cplx) { qi.x -= vi.x * re - vi.y * im; qi.y -= vi.x * im + vi.y * re; }
+                    else qi -= vi * re;
+                    q[i] = qi;
+                }
+            }
+        }
+        grid.sync();
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_svd(int dtype, const void *A, int rows, int cols, void *U, void *S, void *Vt, void *work_G, void *work_V,
@@ -240,6 +354,34 @@ cudaError_t launch_svd(int dtype, const void *A, int rows, int cols, void *U, vo
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // one warp per column pair: n/2 warps are enough; never more CTAs than can be resident (cooperative launch)
     const int64_t want = std::max<int64_t>(1, ((int64_t)(p.n + 1) / 2 + 7) / 8);
+    const int grid = (int)std::min<int64_t>(want, (int64_t)sms * std::max(1, std::min(per_sm, 2)));
+    void *args[] = {(void *)&p};
+    return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(256), args, 0, s);
+}
+
+}  // namespace mb200
+
+namespace mb200 {
+
+cudaError_t launch_qr(int dtype, const void *A, int m, int n, void *Q, void *Rm, void *work_W, void *work_rd, void *work_tau,
+                      cudaStream_t s) {
+    QrParams p{};
+    p.A = A; p.W = work_W; p.Q = Q; p.Rm = Rm; p.rd = work_rd; p.tau = work_tau;
+    p.m = m; p.n = n; p.k = std::min(m, n);
+    const void *fn;
+    switch (dtype) {
+        case MB200_F32: fn = (const void *)householder_qr_kernel<float>; break;
+        case MB200_F64: fn = (const void *)householder_qr_kernel<double>; break;
+        case MB200_C64: fn = (const void *)householder_qr_kernel<float2>; break;
+        default: fn = (const void *)householder_qr_kernel<double2>; break;
+    }
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0);
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t want = std::max<int64_t>(1, ((int64_t)std::max(n, p.k) + 7) / 8);   // one warp per column
     const int grid = (int)std::min<int64_t>(want, (int64_t)sms * std::max(1, std::min(per_sm, 2)));
     void *args[] = {(void *)&p};
     return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(256), args, 0, s);

@@ -88,6 +88,49 @@ def tensor_svd_thin(*args, inds_u=(), inds_v=(), ind_s=None, **kwargs):
     raise ArgumentError(f"`tensor_svd_thin` not implemented or not loaded for backend {backend!r}")   # :67-69
 
 
+def _b200_qr_thin(A: Tensor, inds_q=(), inds_r=(), ind_virtual=None):
+    if ind_virtual is None:
+        ind_virtual = Index(("qr", next(_gensym)))
+    ind_virtual = ind_virtual if isinstance(ind_virtual, Index) else Index(ind_virtual)
+    if ind_virtual in A.inds:                                # tensor_qr.jl:60
+        raise ArgumentError(f"new virtual bond name ({ind_virtual}) cannot be already be present")
+    inds_q, inds_r = factorinds(A.inds, inds_q, inds_r)
+    if set(inds_q) | set(inds_r) != set(A.inds):              # tensor_qr.jl:63
+        raise ArgumentError("issetequal(inds_q ∪ inds_r, inds(A)) must hold")
+    host = not A.on_device
+    Ad = A if A.on_device else A.to_device()
+    left_sizes = tuple(Ad.size(i) for i in inds_q)
+    right_sizes = tuple(Ad.size(i) for i in inds_r)
+    rows = int(np.prod(left_sizes, dtype=np.int64))
+    cols = int(np.prod(right_sizes, dtype=np.int64))
+    k = min(rows, cols)
+    order = inds_q + inds_r
+    Amat = Ad if Ad.inds == order else Ad.permutedims(order)      # K1 (tensor_qr.jl:68)
+    dev = Amat.data.device
+    Q = B200Array(left_sizes + (k,), A.dtype, dev)
+    R = B200Array((k,) + right_sizes, A.dtype, dev)
+    h = _lib.Handle.get(dev)
+    _lib.check(_lib.lib().mb200_qr_thin(h.ptr, C.c_void_p(Q.ptr), C.c_void_p(R.ptr), C.c_void_p(Amat.data.ptr),
+                                        _lib.dtype_enum(A.dtype), rows, cols))
+    out = (Tensor(Q, inds_q + [ind_virtual]), Tensor(R, [ind_virtual] + inds_r))
+    return tuple(t.to_host() for t in out) if host else out
+
+
+def tensor_qr_thin(*args, inds_q=(), inds_r=(), ind_virtual=None):
+    """tensor_qr_thin(A; inds_q, inds_r, ind_virtual) -> Q[inds_q..., x], R[x, inds_r...] with A = Q·R and Q isometric
+    (tensor_qr.jl:5-79); tensor_qr_thin(backend, A; ...) is the per-backend method."""
+    if len(args) == 2 and isinstance(args[0], Backend):
+        backend, A = args
+    elif len(args) == 1 and isinstance(args[0], Tensor):
+        A = args[0]
+        backend = choose_backend("tensor_qr_thin", A.parent)
+    else:
+        raise ArgumentError("tensor_qr_thin(A; inds_q, inds_r, ind_virtual)")
+    if isinstance(backend, BackendB200):
+        return _b200_qr_thin(A, inds_q, inds_r, ind_virtual)
+    raise ArgumentError(f"`tensor_qr_thin` not implemented or not loaded for backend {backend!r}")
+
+
 def _slice_last(t: Tensor, n: int) -> Tensor:
     """`view(t, ind_s => 1:n)` when ind_s is the last (slowest) dimension: the leading n slabs of the same buffer."""
     if n >= t.shape[-1]:

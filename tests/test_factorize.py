@@ -170,3 +170,53 @@ def test_simple_update_random_mps_sites(dt):
     Ut, st, Vt = mb.simple_update(A, I("pa"), B, I("pb"), I("bond"), G, I("ga"), I("gb"), maxdim=chi)
     assert st.shape == (chi,) and Ut.shape == (chi, d, chi) and Vt.shape == (d, chi, chi)
     assert np.linalg.norm(st.to_host().data - so[:chi]) <= tol * np.linalg.norm(so)
+
+
+# ---- tensor_qr_thin -------------------------------------------------------------------------------------------
+def _check_qr(mb, a, inds, inds_q, dt):
+    """test/unit/operations/tensor_qr_thin.jl:24-33: index / shape bookkeeping, Q·R ≈ A, Q isometric; plus R upper
+    triangular. (QR is unique only up to a diagonal phase, so Q and R are not compared with LAPACK entry by entry.)"""
+    I = lambda s: [mb.Index(c) for c in s]
+    A = mb.Tensor(a, I(inds)).to_device()
+    Q, R = mb.tensor_qr_thin(A, inds_q=I(inds_q), ind_virtual=mb.Index("x"))
+    inds_r = [c for c in inds if c not in inds_q]
+    left = tuple(a.shape[inds.index(c)] for c in inds_q)
+    right = tuple(a.shape[inds.index(c)] for c in inds_r)
+    k = min(int(np.prod(left)), int(np.prod(right)))
+    assert Q.inds == I(inds_q) + [mb.Index("x")] and R.inds == [mb.Index("x")] + I(inds_r)
+    assert Q.shape == left + (k,) and R.shape == (k,) + right
+    wide = np.complex128 if np.dtype(dt).kind == "c" else np.float64
+    q = Q.to_host().data.reshape(-1, k, order="F").astype(wide)
+    r = R.to_host().data.reshape(k, -1, order="F").astype(wide)
+    ref = np.transpose(a, [inds.index(c) for c in list(inds_q) + inds_r]).reshape(q.shape[0], r.shape[1], order="F").astype(wide)
+    assert rel_frobenius(q @ r, ref) <= TOL[dt]
+    assert np.linalg.norm(q.conj().T @ q - np.eye(k)) <= 50 * TOL[dt] * max(1, k)
+    assert np.linalg.norm(np.tril(r, -1)) == 0.0
+    # |R_jj| agrees with LAPACK's (the diagonal is fixed up to its phase)
+    rl = np.linalg.qr(ref, mode="r")
+    assert np.linalg.norm(np.abs(np.diag(r)) - np.abs(np.diag(rl))) <= 50 * TOL[dt] * np.linalg.norm(np.diag(rl))
+    back = mb.binary_einsum(Q, R, out=I(inds)).to_host().data                   # :31 binary_einsum(Q, R) ≈ A
+    assert rel_frobenius(back.astype(wide), a.astype(wide)) <= TOL[dt]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("shape,inds,inds_q", SVD_SHAPES)
+def test_tensor_qr_thin_parity(shape, inds, inds_q, dt):
+    import muscle_b200 as mb
+    rng = np.random.default_rng(41)
+    _check_qr(mb, random_array(rng, shape, dt), inds, inds_q, dt)
+
+
+@pytest.mark.gpu
+def test_tensor_qr_thin_larger_and_rejects():
+    import muscle_b200 as mb
+    rng = np.random.default_rng(42)
+    _check_qr(mb, random_array(rng, (256, 2, 160, 2), "complex128"), "lpqr", "lp", "complex128")    # 512 x 320
+    _check_qr(mb, random_array(rng, (96, 700), "float32"), "ab", "a", "float32")
+    I = lambda s: [mb.Index(c) for c in s]
+    A = mb.Tensor(np.ones((2, 4, 6, 8)), I("ijkl")).to_device()
+    for kw in (dict(), dict(inds_q=I("z")), dict(inds_r=I("z")), dict(inds_q=I("ijkl")), dict(inds_r=I("ijkl")),
+               dict(inds_q=I("i"), ind_virtual=mb.Index("j"))):                 # tensor_qr_thin.jl:9-21
+        with pytest.raises(mb.ArgumentError):
+            mb.tensor_qr_thin(A, **kw)
