@@ -280,7 +280,8 @@ __global__ void __launch_bounds__(PT_THREADS) permute_tiled_kernel(const __grid_
 
 
 // Register-tile transposition (no shared memory for data): used when the source and destination unit-stride modes
-// differ (pure transposition) and both the source run along x and the destination run along y are contiguous.
+// differ (pure transposition); x = source-leading modes, y = destination-leading modes (each side may skip modes the
+// other took), addressed through per-tile tables, VEC-blocks contiguous along x in the source and along y in the destination.
 // A thread owns VEC x VEC blocks (VEC = elements per 16 bytes): it reads VEC source rows (y) with one 16-byte load
 // each, transposes in registers, and writes VEC destination rows (x) with one 16-byte store each. Lanes are laid
 // 2^lxl (x) by 2^(5-lxl) (y) blocks, so neighbouring lanes touch neighbouring 16-byte pieces and every request covers
@@ -297,22 +298,25 @@ __global__ void __launch_bounds__(PT_THREADS) permute_regT_kernel(const __grid_c
     constexpr int VEC = 16 / ESZ;                 // block edge
     constexpr int LB = VEC == 4 ? 2 : (VEC == 2 ? 1 : 0);
     constexpr int UNR = ESZ / 2;                  // blocks in flight per thread: 2 / 4 / 8 -> 8 x 16 B
-    __shared__ int64_t srcY[PT_REG_TAB], dstX[PT_REG_TAB];
+    __shared__ int64_t srcY[PT_REG_TAB], dstX[PT_REG_TAB];     // per element
+    __shared__ int64_t srcX[PT_REG_TAB], dstY[PT_REG_TAB];     // per VEC-block
     const int tid = threadIdx.x;
     const TileCtx t = decode_tile(p, blockIdx.x);
     for (int i = tid; i < t.ty; i += PT_THREADS) {
         int64_t so, dof;
         digits_off(t.y0 + i, p.ny, p.y_ext, p.y_ss, p.y_ds, so, dof);
         srcY[i] = so * ESZ;
+        if ((i & (VEC - 1)) == 0) dstY[i >> LB] = dof * ESZ;
     }
     for (int i = tid; i < t.tx; i += PT_THREADS) {
         int64_t so, dof;
         digits_off(t.x0 + i, p.nx, p.x_ext, p.x_ss, p.x_ds, so, dof);
         dstX[i] = dof * ESZ;
+        if ((i & (VEC - 1)) == 0) srcX[i >> LB] = so * ESZ;
     }
     __syncthreads();
-    const unsigned char *sbase = src + (t.base_s + t.x0) * ESZ;   // the x index IS the source offset
-    unsigned char *dbase = dst + (t.base_d + t.y0) * ESZ;         // the y index IS the destination offset
+    const unsigned char *sbase = src + t.base_s * ESZ;
+    unsigned char *dbase = dst + t.base_d * ESZ;
     const int lbx = p.lx - LB, lby = p.ly - LB;
     const int lyl0 = min(5 - min(lxl_target, lbx), lby);
     const int lxl = min(5 - lyl0, lbx), lyl = lyl0, lxh = lbx - lxl;
@@ -333,7 +337,7 @@ __global__ void __launch_bounds__(PT_THREADS) permute_regT_kernel(const __grid_c
             if (ok) {
 #pragma unroll
                 for (int j = 0; j < VEC; j++)
-                    r[u][j] = __ldg(reinterpret_cast<const uint4 *>(sbase + (int64_t)x * ESZ + srcY[y + j]));
+                    r[u][j] = __ldg(reinterpret_cast<const uint4 *>(sbase + srcX[x >> LB] + srcY[y + j]));
             }
         }
 #pragma unroll
@@ -354,7 +358,7 @@ __global__ void __launch_bounds__(PT_THREADS) permute_regT_kernel(const __grid_c
             }
 #pragma unroll
             for (int i = 0; i < VEC; i++)
-                *reinterpret_cast<uint4 *>(dbase + (int64_t)y * ESZ + dstX[x + i]) = w[i];
+                *reinterpret_cast<uint4 *>(dbase + dstY[y >> LB] + dstX[x + i]) = w[i];
         }
     }
 }
@@ -403,11 +407,24 @@ bool build_tile(const PermuteParams &q, size_t esz, int cap, int ltile_bump, Per
     int64_t SX = 1, SY = 1;
     // the destination unit-stride mode (after v) always belongs to y, so x cannot steal it
     if (ys < (size_t)n && role[dord[ys]] == 0 && ly_t > 0) { role[dord[ys]] = 3; SY *= q.ext[dord[ys]]; ys++; }
+    // The smem-tile kernels need x / y to be LEADING runs of the source / destination order; the register-tile kernel
+    // (cap 10) addresses both sides through tables, so a side may skip modes the other side already took: for an
+    // interleaving permutation (dest order m4 m0 m5 m1 ...) the tile becomes {m0 m1} x {m4 m5} and writes 4 KB runs
+    // (m4 m0 m5) instead of 512 B ones.
+    const bool skip_taken = cap > 8;
     auto grow_x = [&](int lg) {
-        while (SX < ((int64_t)1 << lg) && xs < n && role[xs] == 0) { role[xs] = 2; SX *= q.ext[xs]; xs++; }
+        while (SX < ((int64_t)1 << lg) && xs < n) {
+            if (role[xs] == 0) { role[xs] = 2; SX *= q.ext[xs]; }
+            else if (!skip_taken) break;
+            xs++;
+        }
     };
     auto grow_y = [&](int lg) {
-        while (SY < ((int64_t)1 << lg) && ys < (size_t)n && role[dord[ys]] == 0) { role[dord[ys]] = 3; SY *= q.ext[dord[ys]]; ys++; }
+        while (SY < ((int64_t)1 << lg) && ys < (size_t)n) {
+            if (role[dord[ys]] == 0) { role[dord[ys]] = 3; SY *= q.ext[dord[ys]]; }
+            else if (!skip_taken) break;
+            ys++;
+        }
     };
     // x to its target, then y with whatever x could not use, then x again with whatever y could not use
     grow_x(lx_t);
@@ -440,24 +457,16 @@ bool build_tile(const PermuteParams &q, size_t esz, int cap, int ltile_bump, Per
 
 // Register-tile kernel eligibility for a tile built with the wide tables.
 bool regT_ok(const PermK &k, size_t esz, const void *src, const void *dst) {
-    if (k.v_ext != 1 || k.direct) return false;
+    if (k.v_ext != 1 || k.direct || k.nx == 0 || k.ny == 0) return false;
     if ((((uintptr_t)src) | ((uintptr_t)dst)) & 15) return false;
-    int64_t run = 1;
-    for (int i = 0; i < k.ny; i++) {   // the y index must be the destination offset
-        if (k.y_ds[i] != run) return false;
-        run *= k.y_ext[i];
-    }
-    run = 1;
-    for (int i = 0; i < k.nx; i++) {   // the x index must be the source offset
-        if (k.x_ss[i] != run) return false;
-        run *= k.x_ext[i];
-    }
     const int vec = (int)(16 / esz), lb = vec == 4 ? 2 : (vec == 2 ? 1 : 0);
-    if (k.lx < lb || k.ly < lb || k.SX % vec || k.SY % vec) return false;
-    bool ok = true;
+    // a VEC-block along x must be contiguous in the source, one along y contiguous in the destination
+    if (k.x_ss[0] != 1 || k.x_ext[0] % vec || k.y_ds[0] != 1 || k.y_ext[0] % vec) return false;
+    if (k.lx < lb || k.ly < lb) return false;
+    bool ok = true;   // every other stride keeps 16-byte alignment
     for (int i = 0; i < k.n_out; i++) ok = ok && k.o_ss[i] % vec == 0 && k.o_ds[i] % vec == 0;
-    for (int i = 0; i < k.ny; i++) ok = ok && k.y_ss[i] % vec == 0;
-    for (int i = 0; i < k.nx; i++) ok = ok && k.x_ds[i] % vec == 0;
+    for (int i = 0; i < k.ny; i++) ok = ok && k.y_ss[i] % vec == 0 && (i == 0 || k.y_ds[i] % vec == 0);
+    for (int i = 0; i < k.nx; i++) ok = ok && k.x_ds[i] % vec == 0 && (i == 0 || k.x_ss[i] % vec == 0);
     return ok;
 }
 
