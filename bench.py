@@ -185,7 +185,7 @@ def run_reference(args):
         "e2e": {"value": tf, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -390,7 +390,7 @@ def run_ours(args):
             "gpu_launch_breakdown": {k: v for k, v in stats.items() if v},
             "clocks": clocks, "sharded_configs": sharded,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -518,7 +518,27 @@ def run_sharded_configs(args, world, rank, local):
     return out
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line of this run, written to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # stdout must carry exactly one JSON line, but libraries write banners there from C (NCCL prints "NCCL version ..."
+    # with printf, NCCL_DEBUG_FILE does not catch it): point fd 1 at stderr for the whole run and keep the original
+    # stdout for the JSON line only.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

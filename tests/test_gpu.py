@@ -251,6 +251,25 @@ def test_permute_bit_exact(shape, perm, dt):
     assert np.array_equal(got.to_host().data, np.transpose(x, perm))
 
 
+def test_permute_unaligned_pointers_skip_the_wide_paths():
+    """16-byte vector paths (element widening, register-tile transposition) need 16-byte aligned buffers: a Float32
+    view that starts 4 bytes into an allocation must fall back to the element-wise kernels and still be exact."""
+    rng = np.random.default_rng(2)
+    for shape, perm in (((64, 48), (1, 0)), ((8, 12, 10), (0, 2, 1)), ((16, 16, 16), (2, 1, 0))):
+        n = int(np.prod(shape))
+        x = np.asfortranarray(rng.integers(-9, 9, size=shape).astype(np.float32))
+        src = B200Array((n + 4,), np.float32)
+        dst = B200Array((n + 4,), np.float32)
+        flat = np.zeros(n + 4, np.float32)
+        flat[1:n + 1] = x.ravel(order="F")
+        src.copy_from_host(flat)
+        h = _lib.Handle.get()
+        _lib.check(mb.lib().mb200_permute(h.ptr, C.c_void_p(dst.ptr + 4), C.c_void_p(src.ptr + 4), _lib.F32, len(shape),
+                                          _lib.i64(shape), _lib.i32(perm), 0))
+        got = dst.to_host()[1:n + 1].reshape([shape[p] for p in perm], order="F")
+        assert np.array_equal(got, np.transpose(x, perm))
+
+
 def test_permute_planar_split():
     """complex interleaved → planar (all re, then all im) in the same pass."""
     rng = np.random.default_rng(1)

@@ -173,3 +173,34 @@ def test_network_graph_replay_small_complex64_chain():
     for _ in range(3):
         b = cap.replay().to_host().data
     assert np.array_equal(a, b)
+
+
+@pytest.mark.gpu
+def test_graph_capture_error_paths():
+    """mb200_graph_begin refuses the legacy default stream; a plan that is not cached yet cannot be built while
+    capturing (NOT_SUPPORTED -> ArgumentError) and the capture is still closed cleanly."""
+    import ctypes as C
+    import torch
+    import muscle_b200 as mb
+    from muscle_b200 import _lib
+    h = _lib.Handle.get(0)
+    h.set_stream(0)
+    with pytest.raises(mb.ArgumentError, match="non-default stream"):
+        _lib.check(mb.lib().mb200_graph_begin(h.ptr))
+    I = lambda s: [mb.Index(c) for c in s]
+    a = mb.Tensor(np.ones((5, 7, 3)), I("xyz")).to_device()
+    b = mb.Tensor(np.ones((7, 11, 3)), I("ywz")).to_device()      # a shape no other test has planned
+    side = torch.cuda.Stream(device=0)
+    with torch.cuda.stream(side):
+        h = _lib.Handle.get(0)
+        _lib.check(mb.lib().mb200_graph_begin(h.ptr))
+        try:
+            with pytest.raises(mb.ArgumentError, match="plan miss during graph capture"):
+                mb.binary_einsum(mb.BackendB200(), I("xwz"), a, b)
+        finally:
+            g = C.c_void_p()
+            _lib.check(mb.lib().mb200_graph_end(h.ptr, C.byref(g)))
+            _lib.check(mb.lib().mb200_graph_destroy(g))
+    torch.cuda.synchronize()
+    c = mb.binary_einsum(a, b, out=I("xwz"))                         # the handle is usable again
+    assert np.array_equal(c.to_host().data, 7.0 * np.ones((5, 11, 3)))
