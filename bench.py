@@ -488,7 +488,8 @@ def run_sharded_configs(args, world, rank, local):
             fused = {"tflops": flops5 / (ms_f * 1e-3) / 1e12, "ms": ms_f, "rel_err_vs_nccl_allreduce": err,
                      "semantics": "reduce-scatter (each rank ends with its 1/N slab of C)",
                      "how": "tcgen05 epilogue stores each element into the owner rank's staging slot over NVLink peer "
-                            "mappings (CUDA IPC), 4-byte all_reduce as stream-ordered barrier, local sum of N slots"}
+                            "mappings (CUDA IPC); no collective: every rank signals an epoch flag into every rank's flag array "
+                            "(st.release.sys after the GEMM), the owner's slot-sum kernel waits for all N flags"}
         except Exception as e:  # noqa: BLE001
             fused = {"error": repr(e)[:300]}
     out["config5_summed_slice_allreduce"] = {

@@ -231,6 +231,16 @@ int mb200_graph_end(mb200_handle_t handle, mb200_graph_t *graph);
 int mb200_graph_launch(mb200_handle_t handle, mb200_graph_t graph);
 int mb200_graph_destroy(mb200_graph_t graph);
 
+/* Flag barrier for the fused reduce-scatter (replaces a collective between the scatter contraction and the slot sum).
+ * Every rank owns an array of nranks ints (zero-initialised once, peer-mapped like the staging buffers).
+ * mb200_signal_peers: enqueued after mb200_binary_einsum_scatter, stores `epoch` into entry `rank` of every rank's
+ * array. mb200_reduce_slots_wait: like mb200_reduce_slots, but the kernel first waits until all nslots entries of the
+ * LOCAL array have reached `epoch` (epochs must increase from call to call; a rank that never signals traps the
+ * waiting kernel after ~10 s instead of hanging the GPU). */
+int mb200_signal_peers(mb200_handle_t handle, void *const *flag_arrays, int nranks, int rank, int epoch);
+int mb200_reduce_slots_wait(mb200_handle_t handle, void *out, const void *staging_local, int dtype,
+                            int64_t slab_elems, int nslots, const void *flags_local, int epoch);
+
 /* ---- counters (bench.py's gpu_launches claim) ----------------------------------------------- */
 typedef struct {
     uint64_t launches_total;

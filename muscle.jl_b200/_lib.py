@@ -126,6 +126,8 @@ PROTOTYPES = {
     "mb200_graph_end": ([_vp, C.POINTER(_vp)], C.c_int),
     "mb200_graph_launch": ([_vp, _vp], C.c_int),
     "mb200_graph_destroy": ([_vp], C.c_int),
+    "mb200_signal_peers": ([_vp, C.POINTER(_vp), _i, _i, _i], C.c_int),
+    "mb200_reduce_slots_wait": ([_vp, _vp, _vp, _i, C.c_int64, _i, _vp, _i], C.c_int),
     "mb200_get_stats": ([_vp, C.POINTER(Stats)], C.c_int),
     "mb200_reset_stats": ([_vp], C.c_int),
 }

@@ -1033,6 +1033,37 @@ int mb200_graph_destroy(mb200_graph_t g) {
     return MB200_OK;
 }
 
+int mb200_signal_peers(mb200_handle_t h, void *const *flag_arrays, int nranks, int rank, int epoch) {
+    MB200_CHECK_HANDLE(h);
+    if (!flag_arrays || nranks < 1 || nranks > MB200_MAX_PEERS || rank < 0 || rank >= nranks)
+        return fail(MB200_INVALID_ARGUMENT, "bad arguments to mb200_signal_peers");
+    ScatterDesc f{};
+    for (int r = 0; r < nranks; r++) {
+        if (!flag_arrays[r]) return fail(MB200_INVALID_ARGUMENT, "flag_arrays[%d] is NULL", r);
+        f.peer[r] = flag_arrays[r];
+    }
+    f.nranks = nranks; f.rank = rank;
+    std::lock_guard<std::mutex> lk(h->mu);
+    MB200_CUDA(cudaSetDevice(h->device));
+    MB200_CUDA(launch_signal_peers(f, epoch, h->stream));
+    h->stats.launches_reduce++;
+    h->stats.launches_total++;
+    return MB200_OK;
+}
+
+int mb200_reduce_slots_wait(mb200_handle_t h, void *out, const void *staging_local, int dtype, int64_t slab_elems, int nslots,
+                            const void *flags_local, int epoch) {
+    MB200_CHECK_HANDLE(h);
+    if (!dtype_valid(dtype) || !out || !staging_local || !flags_local || slab_elems < 0 || nslots < 1 || nslots > MB200_MAX_PEERS)
+        return fail(MB200_INVALID_ARGUMENT, "bad arguments to mb200_reduce_slots_wait");
+    std::lock_guard<std::mutex> lk(h->mu);
+    MB200_CUDA(cudaSetDevice(h->device));
+    MB200_CUDA(launch_reduce_slots_wait(dtype, out, staging_local, slab_elems, nslots, (const int *)flags_local, epoch, h->stream));
+    h->stats.launches_reduce++;
+    h->stats.launches_total++;
+    return MB200_OK;
+}
+
 int mb200_get_stats(mb200_handle_t h, mb200_stats_t *stats) {
     MB200_CHECK_HANDLE(h);
     if (!stats) return fail(MB200_INVALID_ARGUMENT, "stats is NULL");

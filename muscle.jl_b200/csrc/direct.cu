@@ -217,6 +217,42 @@ __global__ void __launch_bounds__(256) reduce_slots_kernel(T *__restrict__ out, 
     }
 }
 
+// Cross-rank barrier of the fused reduce-scatter, without a collective: after its contraction every rank stores the
+// call's epoch into ITS entry of every rank's flag array (peer mappings, system scope); the owner's slot-sum kernel
+// spins until all nslots entries carry the epoch. The GEMM epilogue ended with __threadfence_system() and the kernel
+// boundary orders this store after it, so a rank that acquires the flag also sees the slot data.
+__global__ void signal_peers_kernel(ScatterDesc flags, int epoch) {
+    const int r = threadIdx.x;
+    if (r < flags.nranks) {
+        __threadfence_system();
+        int *f = reinterpret_cast<int *>(flags.peer[r]) + flags.rank;
+        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) reduce_slots_wait_kernel(T *__restrict__ out, const T *in, int64_t n, int nslots,
+                                                                const int *flags, int epoch) {
+    if (threadIdx.x < nslots) {
+        const long long t0 = clock64();
+        int f;
+        do {
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(f) : "l"(flags + threadIdx.x) : "memory");
+            if (clock64() - t0 > 20000000000LL) __trap();   // a rank that never arrives must not hang the GPU
+        } while (f - epoch < 0);
+    }
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        T acc = in[i];   // first touched after the acquire above: never a stale L1 line
+        for (int s = 1; s < nslots; s++) {
+            T v = in[(int64_t)s * n + i];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        out[i] = acc;
+    }
+}
+
 inline int grid_for(int64_t n, int threads, int cap = 148 * 16) {
     int64_t g = (n + threads - 1) / threads;
     if (g < 1) g = 1;
@@ -302,6 +338,26 @@ cudaError_t launch_reduce_slots(int dtype, void *out, const void *staging, int64
     } else {
         const int64_t n = bytes / 16;   // float4
         reduce_slots_kernel<float4><<<grid_for(n, 256), 256, 0, s>>>((float4 *)out, (const float4 *)staging, n, nslots);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_signal_peers(const ScatterDesc &flags, int epoch, cudaStream_t s) {
+    signal_peers_kernel<<<1, 32, 0, s>>>(flags, epoch);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_reduce_slots_wait(int dtype, void *out, const void *staging, int64_t slab_elems, int nslots, const int *flags,
+                                     int epoch, cudaStream_t s) {
+    const int64_t bytes = slab_elems * (int64_t)dtype_size(dtype);
+    if (bytes <= 0) return cudaSuccess;
+    if (bytes % 32 != 0 || nslots > 32) return cudaErrorInvalidValue;
+    if (dtype_is_double(dtype)) {
+        const int64_t n = bytes / 32;   // double4
+        reduce_slots_wait_kernel<double4><<<grid_for(n, 256, 148 * 8), 256, 0, s>>>((double4 *)out, (const double4 *)staging, n, nslots, flags, epoch);
+    } else {
+        const int64_t n = bytes / 16;   // float4
+        reduce_slots_wait_kernel<float4><<<grid_for(n, 256, 148 * 8), 256, 0, s>>>((float4 *)out, (const float4 *)staging, n, nslots, flags, epoch);
     }
     return cudaGetLastError();
 }

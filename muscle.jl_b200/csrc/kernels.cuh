@@ -72,6 +72,10 @@ cudaError_t permute_configure();
 cudaError_t tf32_configure();
 
 cudaError_t launch_reduce_slots(int dtype, void *out, const void *staging, int64_t slab_elems, int nslots, cudaStream_t s);
+// flag barrier of the fused reduce-scatter: flags.peer[r] = rank r's flag array (nranks ints), flags.rank = this rank
+cudaError_t launch_signal_peers(const ScatterDesc &flags, int epoch, cudaStream_t s);
+cudaError_t launch_reduce_slots_wait(int dtype, void *out, const void *staging, int64_t slab_elems, int nslots, const int *flags,
+                                     int epoch, cudaStream_t s);
 
 // ---- unary_einsum / hadamard (elementwise.cu) ------------------------------------------------------------
 // y[sum_i d_i * c_sy[i]] = sum over k of x[sum_i d_i * c_sx[i] + sum_j k_j * k_sx[j]]

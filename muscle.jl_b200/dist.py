@@ -134,9 +134,12 @@ class _PeerStaging:
         self.nranks = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.own, exported = [], []
+        self.flag_off = (nbytes + 255) // 256 * 256      # nranks ints after the slots: the flag barrier's array
+        self.epoch = 0
         for _ in range(2):
             p = C.c_void_p()
-            _lib.check(L.mb200_malloc(self.handle.ptr, C.byref(p), nbytes))
+            _lib.check(L.mb200_malloc(self.handle.ptr, C.byref(p), self.flag_off + 256))
+            _lib.check(L.mb200_memset(self.handle.ptr, C.c_void_p(p.value + self.flag_off), 0, 256))
             self.own.append(int(p.value))
             buf = C.create_string_buffer(64)
             if self.nranks > 1:
@@ -158,6 +161,9 @@ class _PeerStaging:
                     ptrs.append(int(q.value))
             self.peers.append(ptrs)
         self.turn = 0
+        self.handle.synchronize()                        # flag arrays are zero before any peer can signal
+        if self.nranks > 1:
+            dist.barrier(group=group)
 
 
 _STAGING: dict = {}
@@ -207,14 +213,16 @@ def sum_slice_reduce_scatter(a_loc: Tensor, b_loc: Tensor, inds_c, group=None) -
         C.c_void_p(a_loc.data.ptr), _lib.dtype_enum(a_loc.dtype), len(ma), _lib.i32(ma), _lib.i64(a_loc.shape), None,
         C.c_void_p(b_loc.data.ptr), _lib.dtype_enum(b_loc.dtype), len(mb), _lib.i32(mb), _lib.i64(b_loc.shape), None,
         arr, nranks, rank, slab.bit_length() - 1))
-    if nranks > 1:
-        # stream-ordered cross-rank barrier: every rank's GEMM (and its peer stores) precedes its all_reduce
-        flag = torch.zeros(1, device=f"cuda:{dev}")
-        dist.all_reduce(flag, group=group)
+    # cross-rank barrier without a collective: signal this call's epoch into every rank's flag array (stream-ordered
+    # after the GEMM and its peer stores); the slot-sum kernel waits for all nranks entries of the local array
+    st.epoch += 1
+    flags = (C.c_void_p * nranks)(*[p + st.flag_off for p in st.peers[b]])
+    _lib.check(L.mb200_signal_peers(h.ptr, flags, nranks, rank, st.epoch))
     # slab as an array: split C's slowest mode when it divides evenly, else a flat vector
     shaped = bool(shape_c) and shape_c[-1] % nranks == 0
     out = B200Array(shape_c[:-1] + (shape_c[-1] // nranks,) if shaped else (slab,), T, dev)
-    _lib.check(L.mb200_reduce_slots(h.ptr, C.c_void_p(out.ptr), C.c_void_p(st.own[b]), _lib.dtype_enum(T), slab, nranks))
+    _lib.check(L.mb200_reduce_slots_wait(h.ptr, C.c_void_p(out.ptr), C.c_void_p(st.own[b]), _lib.dtype_enum(T), slab, nranks,
+                                         C.c_void_p(st.own[b] + st.flag_off), st.epoch))
     if shaped:
         return Tensor(out, inds_c)
     from .tensor import Index

@@ -488,6 +488,21 @@ def test_fused_scatter_epilogue_and_slot_reduce(dt, path, tol):
         out[o * slab:(o + 1) * slab] = d.to_host()
     got = out.reshape((Mx, Nx), order="F")
     assert rel_frobenius(got, ref.astype(dt)) <= tol
+    # the flag barrier: every emulated rank signals epoch 7 into every flag array, then the waiting slot sum runs
+    flags = [B200Array((nranks,), np.float32) for _ in range(nranks)]
+    for f in flags:
+        _lib.check(L.mb200_memset(h.ptr, C.c_void_p(f.ptr), 0, f.nbytes))
+    farr = (C.c_void_p * nranks)(*[f.ptr for f in flags])
+    for r in range(nranks):
+        _lib.check(L.mb200_signal_peers(h.ptr, farr, nranks, r, 7))
+    out2 = np.empty(numel, dtype=dt)
+    for o in range(nranks):
+        d = B200Array((slab,), dt)
+        _lib.check(L.mb200_reduce_slots_wait(h.ptr, C.c_void_p(d.ptr), C.c_void_p(staging[o].ptr), _lib.dtype_enum(dt), slab, nranks,
+                                             C.c_void_p(flags[o].ptr), 7))
+        out2[o * slab:(o + 1) * slab] = d.to_host()
+    assert np.array_equal(out2, out)
+    assert np.array_equal(flags[0].to_host().view(np.int32), np.full(nranks, 7, np.int32))
     # a contraction that is not on a tensor-core path is refused (callers fall back to all_reduce)
     h.set_path(mb.PATH_AUTO)
     tiny_a, tiny_b = B200Array.from_host(a[:8, :16].copy(order="F")), B200Array.from_host(b[:8, :16].copy(order="F"))
