@@ -11,7 +11,7 @@ from .backend import (Backend, BackendB200, BackendBase, BackendOMEinsum, Domain
                       choose_backend_rule, domain, with_backend)
 from .einsum import binary_einsum, binary_einsum_, binary_einsum_inplace, flatten_labels, frontend_inds_c
 from .factorize import (AbsorbEqually, AbsorbU, AbsorbV, DontAbsorb, factorinds, simple_update,
-                        tensor_qr_thin, tensor_svd_thin)
+                        tensor_qr_thin, tensor_svd_thin, tensor_svd_trunc)
 from .family import hadamard, hadamard_, unary_einsum, unary_einsum_, unary_frontend_inds_y
 from .network import CapturedProgram, ContractionProgram, contract, find_path
 from .tensor import B200Array, Index, Tensor, findperm
@@ -21,7 +21,7 @@ __all__ = [
     "ArgumentError", "B200Error", "DimensionMismatch", "Handle", "LIB_PATH", "lib", "plan_describe", "shard_plan",
     "PATH_AUTO", "PATH_DIRECT", "PATH_GETT_F64", "PATH_SIMT_F32", "PATH_TCGEN05_TF32", "PATH_NAMES",
     "Backend", "BackendB200", "BackendBase", "BackendOMEinsum",
-    "AbsorbEqually", "AbsorbU", "AbsorbV", "DontAbsorb", "factorinds", "simple_update", "tensor_qr_thin", "tensor_svd_thin",
+    "AbsorbEqually", "AbsorbU", "AbsorbV", "DontAbsorb", "factorinds", "simple_update", "tensor_qr_thin", "tensor_svd_thin", "tensor_svd_trunc",
     "CapturedProgram", "ContractionProgram", "contract", "find_path",
     "hadamard", "hadamard_", "unary_einsum", "unary_einsum_", "unary_frontend_inds_y", "Domain", "DomainB200", "DomainHost", "choose_backend",
     "choose_backend_rule", "domain", "with_backend",

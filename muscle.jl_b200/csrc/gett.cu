@@ -18,6 +18,7 @@
 //
 // Pipeline: STAGES-deep cp.async ring over k-blocks of BK, one __syncthreads per k-block.
 #include <algorithm>
+#include <cstdlib>
 
 #include "kernels.cuh"
 
@@ -264,8 +265,12 @@ constexpr size_t gett_smem_bytes() {
 // wave share a few A row-panels (kept in the 126 MB L2) while B column-panels stream through.
 constexpr int GROUP_M = 8;
 
+// Split-K (gridDim.y > 1): a contraction with too few tiles to fill the 148 SMs runs every tile's k-range in
+// gridDim.y slices; slice s of tile t writes its partial tile to ws[(s * ntiles + t) * BM * BN ...] (tile-linear,
+// coalesced) and splitk_reduce_kernel adds the slices in order and scatters to C through the tables (deterministic).
 template <class Core>
-__global__ void __launch_bounds__(Core::NTHREADS, Core::NTHREADS <= 128 ? 4 : 1) gett_kernel(const __grid_constant__ GettParams p) {
+__global__ void __launch_bounds__(Core::NTHREADS, Core::NTHREADS <= 128 ? 4 : 1) gett_kernel(const __grid_constant__ GettParams p,
+                                                                                            typename Core::Elem *ws) {
     using E = typename Core::Elem;
     constexpr int BM = Core::BM, BN = Core::BN, BK = Core::BK, S = Core::STAGES;
     constexpr int LDA = Core::LDA, LDB = Core::LDB, NT = Core::NTHREADS;
@@ -294,22 +299,28 @@ __global__ void __launch_bounds__(Core::NTHREADS, Core::NTHREADS <= 128 ? 4 : 1)
     const int mrem = (int)((p.M - m0) < BM ? (p.M - m0) : BM);
     const int nrem = (int)((p.N - n0) < BN ? (p.N - n0) : BN);
 
+    const bool split = gridDim.y > 1;
     for (int i = tid; i < BM; i += NT) {
         bool v = i < mrem;
         sRowA[i] = v ? p.rowA[m0 + i] : 0;
-        sRowC[i] = v ? p.rowC[m0 + i] : 0;
+        sRowC[i] = split ? i : (v ? p.rowC[m0 + i] : 0);
     }
     for (int i = tid; i < BN; i += NT) {
         bool v = i < nrem;
         sColB[i] = v ? p.colB[n0 + i] : 0;
-        sColC[i] = v ? p.colC[n0 + i] : 0;
+        sColC[i] = split ? (int64_t)i * BM : (v ? p.colC[n0 + i] : 0);
     }
-    const int64_t ab = p.batA[l], bb = p.batB[l], cb = p.batC[l];
+    const int64_t ab = p.batA[l], bb = p.batB[l];
+    const int64_t cb = split ? ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * (BM * BN) : p.batC[l];
     __syncthreads();
 
     const E *gA = reinterpret_cast<const E *>(p.A) + ab;
     const E *gB = reinterpret_cast<const E *>(p.B) + bb;
-    const int64_t KB = (p.K + BK - 1) / BK;
+    // this slice's k-blocks [kb0, kb0 + KB); k beyond the slice (or beyond K) is zero-filled
+    const int64_t KB_all = (p.K + BK - 1) / BK;
+    const int64_t kb0 = KB_all * blockIdx.y / gridDim.y, kb1 = KB_all * (blockIdx.y + 1) / gridDim.y;
+    const int64_t KB = kb1 - kb0;
+    const int64_t k_limit = min(p.K, kb1 * BK);
 
     // One "unit" = one element-granular cp.async. Units [0, UA) belong to A, [UA, UA+UB) to B. A unit's (row, k)
     // assignment is fixed per thread, so its global row pointer and smem slot are hoisted out of the k loop; the
@@ -364,9 +375,9 @@ __global__ void __launch_bounds__(Core::NTHREADS, Core::NTHREADS <= 128 ? 4 : 1)
     auto stage_koff = [&](int64_t kblock, int slot) {
         if (tid < 2 * BK) {
             const int k = tid % BK;
-            const int64_t kg = kblock * BK + k;
+            const int64_t kg = (kb0 + kblock) * BK + k;
             int64_t v = -1;
-            if (kg < p.K) v = ((tid < BK) ? p.kA[kg] : p.kB[kg]) * (int64_t)sizeof(E);
+            if (kg < k_limit) v = ((tid < BK) ? p.kA[kg] : p.kB[kg]) * (int64_t)sizeof(E);
             sK[slot * 2 * BK + tid] = v;
         }
     };
@@ -401,7 +412,48 @@ __global__ void __launch_bounds__(Core::NTHREADS, Core::NTHREADS <= 128 ? 4 : 1)
         });
     }
     cp_async_wait<0>();
-    Core::store(acc, reinterpret_cast<E *>(p.C), sRowC, sColC, cb, mrem, nrem, warp, lane, p.sc);
+    if (split) {
+        ScatterDesc none{};
+        Core::store(acc, ws, sRowC, sColC, cb, BM, BN, warp, lane, none);   // whole tile: rows / columns past the edge are zeros
+    } else {
+        Core::store(acc, reinterpret_cast<E *>(p.C), sRowC, sColC, cb, mrem, nrem, warp, lane, p.sc);
+    }
+}
+
+template <typename E> __device__ __forceinline__ E add_e(E a, E b);
+template <> __device__ __forceinline__ float add_e(float a, float b) { return a + b; }
+template <> __device__ __forceinline__ double add_e(double a, double b) { return a + b; }
+template <> __device__ __forceinline__ float2 add_e(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+template <> __device__ __forceinline__ double2 add_e(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+
+// C[rowC[m] + colC[n] + batC[l]] = sum over slices of ws[(s * ntiles + tile) * BM * BN + c * BM + r]
+template <typename E, int BM, int BN>
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const __grid_constant__ GettParams p, const E *__restrict__ ws, int nsplit,
+                                                            int64_t ntiles) {
+    // one thread per output element (tile-linear index: consecutive threads read consecutive workspace elements and,
+    // rows being C's fastest mode, write consecutive C elements); slices added in order, four loads in flight
+    const int64_t tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+    const int64_t tiles = tiles_m * tiles_n;
+    const int64_t total = ntiles * (BM * BN), stride = (int64_t)gridDim.x * blockDim.x, slice = ntiles * (BM * BN);
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const int64_t tile = idx / (BM * BN);
+        const int e = (int)(idx - tile * (BM * BN));
+        const int r = e % BM, c = e / BM;
+        const int64_t l = tile / tiles, t = tile % tiles;
+        const int64_t per_group = GROUP_M * tiles_n, g = t / per_group, gm0 = g * GROUP_M;
+        const int64_t gsz = (tiles_m - gm0) < GROUP_M ? (tiles_m - gm0) : GROUP_M;
+        const int64_t m0 = (gm0 + (t % per_group) % gsz) * BM, n0 = ((t % per_group) / gsz) * BN;
+        if (m0 + r >= p.M || n0 + c >= p.N) continue;
+        const E *w = ws + idx;
+        E acc = w[0];
+        int s = 1;
+        for (; s + 3 < nsplit; s += 4) {
+            const E v0 = w[(int64_t)s * slice], v1 = w[(int64_t)(s + 1) * slice], v2 = w[(int64_t)(s + 2) * slice], v3 = w[(int64_t)(s + 3) * slice];
+            acc = add_e(add_e(add_e(add_e(acc, v0), v1), v2), v3);
+        }
+        for (; s < nsplit; s++) acc = add_e(acc, w[(int64_t)s * slice]);
+        reinterpret_cast<E *>(p.C)[p.rowC[m0 + r] + p.colC[n0 + c] + p.batC[l]] = acc;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -518,7 +570,25 @@ cudaError_t launch(const GettParams &p, cudaStream_t s) {
     const int64_t grid = tiles_m * tiles_n * p.L;
     if (grid <= 0) return cudaSuccess;
     if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    gett_kernel<Core><<<(unsigned)grid, Core::NTHREADS, gett_smem_bytes<Core>(), s>>>(p);
+    using E = typename Core::Elem;
+    // split-K when the tiles cannot fill the GPU: slices = how many times the tile set fits into the resident CTA
+    // slots, at most one slice per k-block (a k-block of work per CTA is the granularity of the pipeline)
+    static const int sk_mode = [] { const char *e = getenv("MB200_SPLITK"); return e ? atoi(e) : 1; }();
+    const int64_t KB = (p.K + Core::BK - 1) / Core::BK;
+    const int64_t slots = 148 * (Core::NTHREADS <= 128 ? 4 : 1);
+    int64_t nsplit = 1;
+    if (sk_mode && p.sc.nranks == 0 && grid * 4 <= slots * 3 && KB >= 2) nsplit = std::min<int64_t>(KB, std::max<int64_t>(1, slots / grid));
+    if (nsplit > 1) {
+        E *ws = nullptr;
+        cudaError_t e = cudaMallocAsync((void **)&ws, (size_t)nsplit * grid * Core::BM * Core::BN * sizeof(E), s);
+        if (e != cudaSuccess) return e;
+        gett_kernel<Core><<<dim3((unsigned)grid, (unsigned)nsplit), Core::NTHREADS, gett_smem_bytes<Core>(), s>>>(p, ws);
+        splitk_reduce_kernel<E, Core::BM, Core::BN><<<(unsigned)std::min<int64_t>((grid * Core::BM * Core::BN + 255) / 256, 148 * 16), 256, 0, s>>>(p, ws, (int)nsplit, grid);
+        e = cudaGetLastError();
+        cudaFreeAsync(ws, s);
+        return e;
+    }
+    gett_kernel<Core><<<(unsigned)grid, Core::NTHREADS, gett_smem_bytes<Core>(), s>>>(p, nullptr);
     return cudaGetLastError();
 }
 template <class Core>

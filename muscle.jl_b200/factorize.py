@@ -131,6 +131,34 @@ def tensor_qr_thin(*args, inds_q=(), inds_r=(), ind_virtual=None):
     raise ArgumentError(f"`tensor_qr_thin` not implemented or not loaded for backend {backend!r}")
 
 
+def tensor_svd_trunc(*args, inds_u=(), inds_v=(), ind_s=None, threshold=None, maxdim=None, **kwargs):
+    """tensor_svd_trunc(A; inds_u, inds_v, ind_s, threshold, maxdim) (tensor_svd.jl:153-201): thin SVD, then keep
+    k = min(length(s), maxdim) values and cut at the first one below `threshold * norm(s)`. With the defaults it is
+    `tensor_svd_thin`. The cut is a slice of the slowest dimension (no copy); only s visits the host."""
+    if len(args) == 2 and isinstance(args[0], Backend):
+        backend, A = args
+    elif len(args) == 1 and isinstance(args[0], Tensor):
+        A = args[0]
+        backend = choose_backend("tensor_svd_thin", A.parent)
+    else:
+        raise ArgumentError("tensor_svd_trunc(A; inds_u, inds_v, ind_s, threshold, maxdim)")
+    if not isinstance(backend, BackendB200):
+        raise ArgumentError(f"`tensor_svd_trunc` not implemented or not loaded for backend {backend!r}")
+    host = not A.on_device
+    U, S, Vt = _b200_svd_thin(A.to_device(), inds_u, inds_v, ind_s, **kwargs)
+    k = S.shape[0]
+    if maxdim is not None:                                    # tensor_svd.jl:181-183
+        k = min(k, int(maxdim))
+    if threshold is not None:                                 # :185-188
+        s = S.to_host().data
+        cut = float(np.linalg.norm(s)) * float(threshold)
+        below = np.nonzero(s[:k] < cut)[0]
+        if below.size:
+            k = int(below[0]) + 1                             # Julia's findfirst is 1-based: keep = 1:findfirst(...)
+    out = (_slice_last(U, k), _slice_last(S, k), _slice_last(Vt, k))
+    return tuple(t.to_host() for t in out) if host else out
+
+
 def _slice_last(t: Tensor, n: int) -> Tensor:
     """`view(t, ind_s => 1:n)` when ind_s is the last (slowest) dimension: the leading n slabs of the same buffer."""
     if n >= t.shape[-1]:

@@ -220,3 +220,29 @@ def test_tensor_qr_thin_larger_and_rejects():
                dict(inds_q=I("i"), ind_virtual=mb.Index("j"))):                 # tensor_qr_thin.jl:9-21
         with pytest.raises(mb.ArgumentError):
             mb.tensor_qr_thin(A, **kw)
+
+
+@pytest.mark.gpu
+def test_tensor_svd_trunc_matches_reference_rule():
+    """tensor_svd.jl:153-201 / test/unit/operations/tensor_svd_trunc.jl: defaults = thin SVD; maxdim caps k; threshold
+    cuts at the first singular value below threshold * norm(s) (that value is kept, as `keep = 1:findfirst(...)`)."""
+    import muscle_b200 as mb
+    I = lambda s: [mb.Index(c) for c in s]
+    rng = np.random.default_rng(50)
+    a = random_array(rng, (200, 100), "complex128")
+    A = mb.Tensor(a, I("ij")).to_device()
+    U, s, Vt = mb.tensor_svd_trunc(A, inds_u=I("i"), ind_s=mb.Index("x"))
+    assert s.shape == (100,) and U.shape == (200, 100) and Vt.shape == (100, 100)
+    rec = mb.binary_einsum(mb.hadamard(U, s), Vt, out=I("ij")).to_host().data
+    assert rel_frobenius(rec, a) <= 1e-12                                        # tensor_svd_trunc.jl:38-40
+    so = np.linalg.svd(a, compute_uv=False)
+    U, s, Vt = mb.tensor_svd_trunc(A, inds_u=I("i"), ind_s=mb.Index("x"), maxdim=17)
+    assert s.shape == (17,) and U.shape == (200, 17) and Vt.shape == (100, 17)
+    assert np.linalg.norm(s.to_host().data - so[:17]) <= 1e-12 * np.linalg.norm(so)
+    thr = 0.08
+    k_ref = int(np.nonzero(so < np.linalg.norm(so) * thr)[0][0]) + 1
+    U, s, Vt = mb.tensor_svd_trunc(A, inds_u=I("i"), ind_s=mb.Index("x"), threshold=thr)
+    assert s.shape == (k_ref,) and U.shape == (200, k_ref)
+    # the truncated factors are the leading part of the full ones: best rank-k approximation error = tail norm
+    rec = mb.binary_einsum(mb.hadamard(U, s), Vt, out=I("ij")).to_host().data
+    assert abs(np.linalg.norm(rec - a) - np.linalg.norm(so[k_ref:])) <= 1e-10 * np.linalg.norm(so)

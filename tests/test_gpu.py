@@ -437,6 +437,27 @@ def test_tcgen05_ragged_waves(dt, m, n, k):
     assert rel_frobenius(got.astype(wide), ar.astype(wide).T @ br.astype(wide)) <= 1e-5
 
 
+@pytest.mark.parametrize("dt", ["complex128", "float64", "complex64", "float32"])
+@pytest.mark.parametrize("m,n,k,l", [(256, 256, 4096, 1), (64, 64, 8192, 1), (130, 70, 1000, 1), (512, 16, 2048, 1),
+                                      (2048, 2, 2048, 1), (96, 96, 520, 3), (8, 300, 3000, 2)])
+def test_gather_gemm_split_k(m, n, k, l, dt):
+    """Too few tiles for 148 SMs -> the gather-GEMM runs every tile's k-range in slices (partial tiles to a workspace,
+    ordered reduction pass). Integer-valued inputs must be bit-exact, ragged edges / batches / skinny tiles included."""
+    rng = np.random.default_rng(8)
+    a = integer_array(rng, (k, m, l), dt, lo=-2, hi=3)
+    b = integer_array(rng, (n, l, k), dt, lo=-2, hi=3)
+    ref = binary_einsum_general(list("nml"), a, list("kml"), b, list("nlk"))
+    h = _lib.Handle.get()
+    path = mb.PATH_GETT_F64 if dt in ("complex128", "float64") else mb.PATH_SIMT_F32
+    got = contract(a, "kml", b, "nlk", "nml", device=True, path=path)
+    assert np.array_equal(got, ref)
+    ar, br = random_array(rng, (k, m, l), dt), random_array(rng, (n, l, k), dt)
+    wide = np.complex128 if np.dtype(dt).kind == "c" else np.float64
+    refr = binary_einsum_general(list("nml"), ar.astype(wide), list("kml"), br.astype(wide), list("nlk"))
+    got = contract(ar, "kml", br, "nlk", "nml", device=True, path=path)
+    assert rel_frobenius(got.astype(wide), refr) <= (1e-12 if dt in ("complex128", "float64") else 1e-5)
+
+
 def test_tcgen05_auto_selected_for_large_c64():
     info = mb.plan_describe(_lib.C64, [0, 2, 4, 5, 6], _lib.C64, [0, 1, 2, 3, 6], [256, 8, 8, 256, 8],
                             _lib.C64, [3, 1, 4, 5, 6], [256, 8, 8, 256, 8])
