@@ -37,7 +37,10 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <cstdlib>
 #include <mutex>
+#include <type_traits>
 
 #include "kernels.cuh"
 
@@ -139,6 +142,11 @@ struct Tf32Params {
     int64_t M, N, L;
     int64_t ntiles;
     int KG;   // number of smem lines along k: K / 8 (complex), ceil(K / 16) (real)
+    // split-K (too few tiles for 148 SMs): work unit u = (tile u % ntiles, slice u / ntiles); slice s covers the smem
+    // lines [KG * s / nsplit, KG * (s + 1) / nsplit) and leaves its partial tile in ws (tile-linear, row fastest);
+    // tf32_splitk_reduce_kernel adds the slices in order and scatters through the C tables.
+    int nsplit;
+    void *ws;
 };
 
 template <int BN, bool REAL>
@@ -193,8 +201,7 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     int64_t *sColC = reinterpret_cast<int64_t *>(tiles + TSTAGES * SM::STAGE + 256);   // [2][BN], per tile parity
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nchunks = (p.KG + CHUNK_GROUPS - 1) / CHUNK_GROUPS;
-    const int64_t ntiles = p.ntiles;
+    const int64_t ntiles = p.ntiles, nunits = p.ntiles * p.nsplit;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -212,9 +219,11 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     if (warp == 0) {
         if (lane == 0) {   // ---- TMA producer
             uint32_t it = 0;   // running stage counter
-            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int64_t unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+                const int64_t tile = unit % ntiles, sp = unit / ntiles;
                 const TileCoord tc = tile_coord<BN>(p, tile);
-                for (int kg = 0; kg < p.KG; kg++, it++) {
+                const int kg0 = (int)((int64_t)p.KG * sp / p.nsplit), kg1 = (int)((int64_t)p.KG * (sp + 1) / p.nsplit);
+                for (int kg = kg0; kg < kg1; kg++, it++) {
                     const int s = it % TSTAGES;
                     mbar_wait(&empty[s], ((it / TSTAGES) & 1) ^ 1);
                     mbar_expect_tx(&full[s], SM::STAGE);
@@ -228,14 +237,17 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         if (lane == 0) {   // ---- MMA issuer
             constexpr uint32_t IDESC = make_idesc(TBM, BN, false), IDESC_NEG = make_idesc(TBM, BN, true);
             uint32_t it = 0, ch = 0;   // running stage / chunk counters
-            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                int kg = 0;
+            for (int64_t unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+                const int64_t sp = unit / ntiles;
+                const int kg0 = (int)((int64_t)p.KG * sp / p.nsplit), kg1 = (int)((int64_t)p.KG * (sp + 1) / p.nsplit);
+                const int nchunks = (kg1 - kg0 + CHUNK_GROUPS - 1) / CHUNK_GROUPS;
+                int kg = kg0;
                 for (int c = 0; c < nchunks; c++, ch++) {
                     const int buf = ch & 1;
                     mbar_wait(&tmem_empty[buf], ((ch >> 1) & 1) ^ 1);   // epilogue has drained this buffer
                     tc_fence_after();
                     const uint32_t d_re = tmem_base + buf * BUF_COLS, d_im = d_re + BN;
-                    const int kend = min(p.KG, (c + 1) * CHUNK_GROUPS);
+                    const int kend = min(kg1, kg0 + (c + 1) * CHUNK_GROUPS);
                     for (bool first = true; kg < kend; kg++, it++, first = false) {
                         const int s = it % TSTAGES;
                         mbar_wait(&full[s], (it / TSTAGES) & 1);
@@ -279,7 +291,10 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         const int row = q * 32 + lane;
         const int et = threadIdx.x - 64;   // 0..255 among the epilogue threads
         uint32_t ch = 0, tcount = 0;
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
+        for (int64_t unit = blockIdx.x; unit < nunits; unit += gridDim.x, tcount++) {
+            const int64_t tile = unit % ntiles, sp = unit / ntiles;
+            const int kg0 = (int)((int64_t)p.KG * sp / p.nsplit), kg1 = (int)((int64_t)p.KG * (sp + 1) / p.nsplit);
+            const int nchunks = (kg1 - kg0 + CHUNK_GROUPS - 1) / CHUNK_GROUPS;
             const TileCoord tc = tile_coord<BN>(p, tile);
             int64_t *cols = sColC + (tcount & 1) * BN;
             for (int i = et; i < BN; i += TTHREADS - 64) cols[i] = (tc.n0 + i < p.N) ? p.colC[tc.n0 + i] : 0;
@@ -314,6 +329,17 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[buf]);
             }
+            if (p.nsplit > 1) {   // partial tile -> workspace, row fastest (coalesced), every row / column of the tile
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const size_t base = (size_t)unit * (TBM * BN) + row;
+#pragma unroll
+                for (int j = 0; j < HALF; j++) {
+                    const size_t o = base + (size_t)(half * HALF + j) * TBM;
+                    if constexpr (REAL) reinterpret_cast<float *>(p.ws)[o] = accr[j];
+                    else reinterpret_cast<float2 *>(p.ws)[o] = make_float2(accr[j], acci[j]);
+                }
+                continue;
+            }
             // the column table of this tile was written by all epilogue threads: named barrier over the 8 epilogue warps
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (row_ok) {
@@ -332,6 +358,27 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// C[rowC[m] + colC[n] + batC[l]] = sum over slices of ws[(s * ntiles + tile) * 128 * BN + col * 128 + row]
+template <int BN, bool REAL>
+__global__ void __launch_bounds__(256) tf32_splitk_reduce_kernel(const __grid_constant__ Tf32Params p) {
+    using E = typename std::conditional<REAL, float, float2>::type;
+    const E *ws = reinterpret_cast<const E *>(p.ws);
+    const int64_t per = (int64_t)TBM * BN, total = p.ntiles * per, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const int64_t tile = idx / per;
+        const int e = (int)(idx - tile * per), r = e % TBM, c = e / TBM;
+        const TileCoord tc = tile_coord<BN>(p, tile);
+        if (tc.m0 + r >= p.M || tc.n0 + c >= p.N) continue;
+        E acc = ws[idx];
+        for (int s = 1; s < p.nsplit; s++) {
+            const E v = ws[(int64_t)s * total + idx];
+            if constexpr (REAL) acc += v;
+            else { acc.x += v.x; acc.y += v.y; }
+        }
+        reinterpret_cast<E *>(p.C)[p.rowC[tc.m0 + r] + p.colC[tc.n0 + c] + p.batC[tc.l]] = acc;
+    }
 }
 
 // ---- host side ----------------------------------------------------------------------------------------
@@ -381,9 +428,28 @@ cudaError_t launch_bn(const void *packA, const void *packB, const GettParams &g,
     const int64_t ntiles = ((g.M + TBM - 1) / TBM) * ((g.N + BN - 1) / BN) * g.L;
     if (ntiles <= 0) return cudaSuccess;
     p.ntiles = ntiles;
-    const int64_t grid = ntiles < 148 ? ntiles : 148;   // persistent: one CTA per SM
+    p.nsplit = 1;
+    // split-K when the tiles cannot fill the SMs: at most one slice per 128-k TMEM chunk
+    const int64_t chunks = (g.K + CHUNK_K - 1) / CHUNK_K;
+    static const int sk_mode = [] { const char *e = getenv("MB200_SPLITK"); return e ? atoi(e) : 1; }();
+    if (sk_mode && g.sc.nranks == 0 && ntiles * 4 <= 148 * 3 && chunks >= 2)
+        p.nsplit = (int)std::min<int64_t>(chunks, std::max<int64_t>(1, 148 / ntiles));
+    void *ws = nullptr;
+    if (p.nsplit > 1) {
+        cudaError_t e = cudaMallocAsync(&ws, (size_t)p.nsplit * ntiles * TBM * BN * (REAL ? 4 : 8), s);
+        if (e != cudaSuccess) return e;
+        p.ws = ws;
+    }
+    const int64_t nunits = ntiles * p.nsplit;
+    const int64_t grid = nunits < 148 ? nunits : 148;   // persistent: one CTA per SM
     tf32_gemm_kernel<BN, REAL><<<(unsigned)grid, TTHREADS, Tf32Smem<BN, REAL>::TOTAL, s>>>(mapA, mapB, p);
-    return cudaGetLastError();
+    if (p.nsplit > 1) {
+        const int64_t threads = ntiles * TBM * BN;
+        tf32_splitk_reduce_kernel<BN, REAL><<<(unsigned)std::min<int64_t>((threads + 255) / 256, 148 * 16), 256, 0, s>>>(p);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (ws) cudaFreeAsync(ws, s);
+    return e;
 }
 
 }  // namespace

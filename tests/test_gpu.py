@@ -458,6 +458,27 @@ def test_gather_gemm_split_k(m, n, k, l, dt):
     assert rel_frobenius(got.astype(wide), refr) <= (1e-12 if dt in ("complex128", "float64") else 1e-5)
 
 
+@pytest.mark.parametrize("dt", ["complex64", "float32"])
+@pytest.mark.parametrize("m,n,k,l", [(256, 256, 4096, 1), (64, 64, 8192, 1), (130, 70, 1032, 1), (512, 512, 1024, 1), (96, 96, 520, 3)])
+def test_tcgen05_split_k(m, n, k, l, dt):
+    """The tcgen05 kernel's split-K schedule (few tiles: work units = (tile, k-slice), partial tiles through the
+    workspace): bit-exact on integer-valued inputs, 1e-5 on random ones."""
+    rng = np.random.default_rng(9)
+    a = integer_array(rng, (k, m, l), dt, lo=-2, hi=3)
+    b = integer_array(rng, (k, n, l), dt, lo=-2, hi=3)
+    ref = binary_einsum_general(list("nml"), a, list("kml"), b, list("knl"))
+    h = _lib.Handle.get()
+    h.reset_stats()
+    got = contract(a, "kml", b, "knl", "nml", device=True, path=mb.PATH_TCGEN05_TF32)
+    assert h.stats()["launches_tcgen05"] == 1
+    assert np.array_equal(got, ref)
+    ar, br = random_array(rng, (k, m, l), dt), random_array(rng, (k, n, l), dt)
+    wide = np.complex128 if dt == "complex64" else np.float64
+    refr = binary_einsum_general(list("nml"), ar.astype(wide), list("kml"), br.astype(wide), list("knl"))
+    got = contract(ar, "kml", br, "knl", "nml", device=True, path=mb.PATH_TCGEN05_TF32)
+    assert rel_frobenius(got.astype(wide), refr) <= 1e-5
+
+
 def test_tcgen05_auto_selected_for_large_c64():
     info = mb.plan_describe(_lib.C64, [0, 2, 4, 5, 6], _lib.C64, [0, 1, 2, 3, 6], [256, 8, 8, 256, 8],
                             _lib.C64, [3, 1, 4, 5, 6], [256, 8, 8, 256, 8])

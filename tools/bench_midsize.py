@@ -9,6 +9,9 @@ from muscle_b200 import B200Array, _lib
 import bench_kernels as bk
 
 
+ROWS = []
+
+
 def case(m, n, k, dt, reps=50):
     a, b = bk.dev_rand((k, m), dt, 1), bk.dev_rand((k, n), dt, 2)
     c = B200Array((m, n), dt)
@@ -31,6 +34,7 @@ def case(m, n, k, dt, reps=50):
         best = min(best, e0.elapsed_time(e1) / reps)
     flops = (8.0 if np.dtype(dt).kind == "c" else 2.0) * m * n * k
     info = mb.plan_describe(e, [1, 2], e, [0, 1], [k, m], e, [0, 2], [k, n])
+    ROWS.append({"m": m, "n": n, "k": k, "dtype": dt, "us": best * 1e3, "tflops": flops / best / 1e9, "path": mb.PATH_NAMES[info.path]})
     print("MID %5dx%5dx%6d %-10s %8.2f TF/s  %9.2f us  path=%s" % (m, n, k, dt, flops / best / 1e9, best * 1e3, mb.PATH_NAMES[info.path]))
 
 
@@ -39,3 +43,8 @@ for dt in ("complex128", "complex64"):
         case(n, n, n, dt)
     for (m, n, k) in ((512, 512, 4096), (256, 256, 16384), (4096, 64, 4096), (1024, 16, 1024), (2048, 2, 2048), (64, 64, 65536)):
         case(m, n, k, dt)
+
+import json, os
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump({"midsize": ROWS, "note": "device time per call, 50 calls back to back through the C ABI; split-K active (MB200_SPLITK=0 disables)"},
+          open("gpurun_out/kernels_midsize.json", "w"), indent=1)

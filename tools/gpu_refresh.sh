@@ -11,6 +11,8 @@ python tools/bench_kernels.py > gpurun_out/kernels.log 2>&1
 python tools/bench_kernels.py --family > gpurun_out/kernels_family.log 2>&1
 python tools/bench_kernels.py --svd > gpurun_out/kernels_svd.log 2>&1
 python tools/bench_network.py > gpurun_out/network.log 2>&1
+python tools/bench_midsize.py > gpurun_out/kernels_midsize.log 2>&1
+MB200_SPLITK=0 python tools/bench_midsize.py > gpurun_out/kernels_midsize_nosplit.log 2>&1
 NCU="ncu --clock-control none"
 $NCU --metrics gpu__time_duration.sum -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 3 > gpurun_out/ncu_bench.log 2>&1
 $NCU --set full --import-source on -k regex:'gett_kernel|stream_kernel' -c 3 -f -o gpurun_out/prof_gett python bench.py --steps 1 --warmup 3 > gpurun_out/ncu_full.log 2>&1
