@@ -183,12 +183,19 @@ void evict_one(mb200_handle_t h) {
     }
 }
 
+// Split scheme of the tcgen05 path: mixed TF32 + BF16 (8 MMAs per 8 k of a complex product) unless MB200_SPLIT_SCHEME=3xtf32
+// asks for the all-TF32 scheme (12 MMAs; A/B measurements, tools/ab_c64.py).
+bool tf32_mixed() {
+    static const bool mixed = [] { const char *e = getenv("MB200_SPLIT_SCHEME"); return !(e && std::string(e) == "3xtf32"); }();
+    return mixed;
+}
+
 // K1 pack of one operand into the tcgen05 kernel's operand format: [batch][rows][4*K] floats, K-major,
 // every 8-k group stored as re_hi | re_lo | im_hi | im_lo chunks of 8 floats (tf32.cu). Expressed as an
 // ordinary strided permutation: the leading summed modes tile the group of 8 (the mode that completes it is split
 // into (need, e/need) with destination strides (kstride, 32)); later summed modes get 4*kstride, row modes
 // rows*4K, batch modes beyond.
-bool build_pack_params(const Plan &p, int which, PermuteParams &q, int64_t &rows) {
+bool build_pack_params(const Plan &p, int which, bool mixed, PermuteParams &q, int64_t &rows) {
     struct Md { int64_t ext, ss, ds; };
     std::vector<Md> v;
     const int64_t K = p.K;
@@ -238,7 +245,7 @@ bool build_pack_params(const Plan &p, int which, PermuteParams &q, int64_t &rows
         q.dst_stride[i] = v[i].ds;
         q.total *= v[i].ext;
     }
-    q.split = 1;
+    q.split = mixed ? 2 + which : 1;
     return true;
 }
 
@@ -330,8 +337,8 @@ int contract_device(mb200_handle_t h, void *C, TensorDesc &dC, const int64_t *st
         else
             e = launch_direct(p.dtype, cp->dp, R, Q, C, s);
         h->stats.launches_direct++;
-    } else if (p.path == MB200_PATH_TCGEN05_TF32 && tf32_available() && build_pack_params(p, 0, qa, rows_a) &&
-               build_pack_params(p, 1, qb, rows_b)) {
+    } else if (p.path == MB200_PATH_TCGEN05_TF32 && tf32_available() && build_pack_params(p, 0, tf32_mixed(), qa, rows_a) &&
+               build_pack_params(p, 1, tf32_mixed(), qb, rows_b)) {
         // pack A, pack B (K1 with the tf32 hi/lo split writer), then the tcgen05 GEMM with the permuting epilogue
         void *pa = nullptr, *pb = nullptr;
         const size_t W = p.dtype == MB200_F32 ? 2 : 4;
@@ -346,7 +353,7 @@ int contract_device(mb200_handle_t h, void *C, TensorDesc &dC, const int64_t *st
             GettParams g = cp->gp;
             g.C = C;
             if (sc) g.sc = *sc;
-            e = launch_tf32_gemm(p.dtype, pa, pb, g, s);
+            e = launch_tf32_gemm(p.dtype, pa, pb, g, tf32_mixed(), s);
             h->stats.launches_tcgen05++;
         }
         cudaFreeAsync(pa, s);

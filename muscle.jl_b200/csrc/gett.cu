@@ -604,7 +604,7 @@ using Z_128x16 = CoreZ<128, 16, 16, 16, 8, 4>;   // skinny N
 using Z_128x16s = CoreZ<128, 16, 32, 16, 8, 2>;  // skinny N and short K (MPS-MPO middle step: N = K = 16): 4 warps, 2 stages -> 4-5 CTAs/SM
 using Z_64x16t = CoreZ<64, 16, 16, 16, 8, 2>;    // streaming kernel tile: 4 warps x (16 x 16), ~42 KB smem -> 5 CTAs/SM
 using Z_16x128 = CoreZ<16, 128, 16, 16, 8, 4>;   // skinny M
-using D_128x128 = CoreD<128, 128, 64, 32, 16, 3>; // Float64: 8 warps x (64 x 32)
+using D_128x128 = CoreD<128, 128, 64, 32, 16, 3>; // Float64: 8 warps x (64 x 32); BK = 32 x 2 stages measured slower (28.1 vs 31.5 TFLOP/s at 8192^3)
 using D_128x16 = CoreD<128, 16, 16, 16, 8, 4>;
 using D_16x128 = CoreD<16, 128, 16, 16, 8, 4>;
 using C_128x64 = CoreF<float2, 128, 64, 16, 3>;  // ComplexF32 FFMA: thread tile 8 x 4

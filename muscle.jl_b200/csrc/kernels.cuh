@@ -120,14 +120,16 @@ struct PermuteParams {
     int64_t dst_stride[MB200_MAX_MODES]; // stride of each source mode in the destination (elements)
     int64_t total;
     int64_t plane_stride;                // != 0: complex dst written planar, im plane at +plane_stride
-    int split;                           // 1: ComplexF32 -> tf32 hi/lo chunks (re_hi, re_lo, im_hi, im_lo at +0,+8,+16,+24
-                                         //    floats), Float32 -> (hi, lo at +0,+8): the operand formats of the tcgen05
-                                         //    kernel (tf32.cu)
+    int split;                           // != 0: write an operand of the tcgen05 kernel (tf32.cu) — per 8 k, ComplexF32 -> four chunks of 8
+                                         //    words (re_hi, re_x, im_hi, im_x at +0,+8,+16,+24), Float32 -> two (hi, x at +0,+8).
+                                         //    1: 3xTF32 format (x = fp32 remainder); 2 / 3: mixed TF32 + BF16 format of the row / column
+                                         //    operand (x = bf16 pair carrying both cross terms)
 };
 cudaError_t launch_permute(int dtype, const PermuteParams &p, const void *src, void *dst, cudaStream_t s);
 
 // ---- K3: tcgen05 / TMEM 3xTF32 ComplexF32 GEMM on packed operands (tf32.cu) ---------------------------------
 bool tf32_available();
-cudaError_t launch_tf32_gemm(int dtype, const void *packA, const void *packB, const GettParams &g, cudaStream_t s);
+// mixed: operands are in the TF32 + BF16 format (split 2 / 3), else 3xTF32 (split 1)
+cudaError_t launch_tf32_gemm(int dtype, const void *packA, const void *packB, const GettParams &g, bool mixed, cudaStream_t s);
 
 }  // namespace mb200

@@ -46,7 +46,7 @@ struct PermK {
     unsigned v_chunks, x_chunks, y_chunks;
     int pitch;               // smem elements per y
     int direct;              // 1: no transposition needed, global → global
-    int64_t plane_stride;    // planar: im plane offset in scalars
+    int64_t plane_stride;    // planar: im plane offset in scalars; split writers: operand format / side (see put)
 };
 
 // digits of idx over `ext` (32-bit divisions), accumulated into 64-bit offsets
@@ -62,27 +62,61 @@ __device__ __forceinline__ void digits_off(unsigned idx, int n, const unsigned *
 }
 
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+// round-to-nearest tf32 (x - tf32_rn(x) is exact in fp32 and half the size of the truncation remainder)
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+// one 32-bit word holding two bf16 values: `lo` in bits [0,16) (the even k position of a K-major bf16 operand), `hi` in [16,32)
+__device__ __forceinline__ float bf16_pair(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return __uint_as_float(r);
+}
+// The "x" chunk of the mixed TF32 + BF16 operand format (tf32.cu): for the row operand (side 1) the pair (bf16(x), bf16(x_lo)),
+// for the column operand (side 2) the pair (bf16(x_lo), bf16(x)), so that one K = 16 bf16 MMA over a chunk pair
+// yields sum_k x*y_lo + x_lo*y — both cross terms of the split product.
+__device__ __forceinline__ float cross_word(float x, float lo, int side) {
+    return side == 1 ? bf16_pair(x, lo) : bf16_pair(lo, x);
+}
 
-// PLANAR: 0 = interleaved (plain), 1 = two planes, 2 = ComplexF32 tf32 hi/lo split into four 8-float chunks,
-//         3 = Float32 tf32 hi/lo split into two 8-float chunks
+// PLANAR: 0 = interleaved (plain), 1 = two planes, 2 = ComplexF32 hi/lo split into four 8-word chunks,
+//         3 = Float32 hi/lo split into two 8-word chunks.
+// aux: PLANAR 1 -> offset of the imaginary plane (scalars); PLANAR 2/3 -> 0: 3xTF32 format (hi = truncated tf32, second chunk = the
+//      fp32 remainder), 1 / 2: mixed TF32 + BF16 format of the row / column operand (hi = rounded tf32, second chunk = cross_word)
 template <typename E, typename S, int PLANAR>
-__device__ __forceinline__ void put(void *dstv, int64_t off, const E &val, int64_t plane_stride) {
+__device__ __forceinline__ void put(void *dstv, int64_t off, const E &val, int64_t aux) {
     if constexpr (PLANAR == 1) {
         S *d = reinterpret_cast<S *>(dstv);
         d[off] = val.x;
-        d[off + plane_stride] = val.y;
+        d[off + aux] = val.y;
     } else if constexpr (PLANAR == 2) {
         S *d = reinterpret_cast<S *>(dstv);
-        const float rh = tf32_hi(val.x), ih = tf32_hi(val.y);
-        d[off] = rh;
-        d[off + 8] = val.x - rh;
-        d[off + 16] = ih;
-        d[off + 24] = val.y - ih;
+        if (aux == 0) {
+            const float rh = tf32_hi(val.x), ih = tf32_hi(val.y);
+            d[off] = rh;
+            d[off + 8] = val.x - rh;
+            d[off + 16] = ih;
+            d[off + 24] = val.y - ih;
+        } else {
+            const float rh = tf32_rn(val.x), ih = tf32_rn(val.y);
+            d[off] = rh;
+            d[off + 8] = cross_word(val.x, val.x - rh, (int)aux);
+            d[off + 16] = ih;
+            d[off + 24] = cross_word(val.y, val.y - ih, (int)aux);
+        }
     } else if constexpr (PLANAR == 3) {
         S *d = reinterpret_cast<S *>(dstv);
-        const float h = tf32_hi(val);
-        d[off] = h;
-        d[off + 8] = val - h;
+        if (aux == 0) {
+            const float h = tf32_hi(val);
+            d[off] = h;
+            d[off + 8] = val - h;
+        } else {
+            const float h = tf32_rn(val);
+            d[off] = h;
+            d[off + 8] = cross_word(val, val - h, (int)aux);
+        }
     } else {
         reinterpret_cast<E *>(dstv)[off] = val;
     }
@@ -386,7 +420,7 @@ bool build_tile(const PermuteParams &q, size_t esz, int cap, int ltile_bump, Per
         for (int i = 0; i < n; i++) { sstride[i] = st; st *= q.ext[i]; }
     }
     k = PermK{};
-    k.plane_stride = q.plane_stride;
+    k.plane_stride = q.split ? q.split - 1 : q.plane_stride;
     std::vector<int> role(n, 0);  // 0 outer, 1 v, 2 x, 3 y
     k.v_ext = 1;
     int xs = 0;

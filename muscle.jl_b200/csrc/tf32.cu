@@ -1,21 +1,30 @@
-// K3 — ComplexF32 GEMM on 5th-gen tensor cores: tcgen05.mma kind::tf32, accumulators in TMEM, operands
-// fed by TMA, 3xTF32 error compensation, 4M complex decomposition, fused permuting epilogue.
+// K3 — ComplexF32 / Float32 GEMM on 5th-gen tensor cores: tcgen05.mma with accumulators in TMEM, operands fed by TMA,
+// split-operand error compensation, 4M complex decomposition, fused permuting epilogue.
 //
-// Operand format (written by the K1 pack pass with the SPLIT4 writer, permute.cu): a K-major matrix
-// [rows][4*K] of float where every group of 8 k-values is stored as four consecutive 32 B chunks
-//     | re_hi(k0..k7) | re_lo(k0..k7) | im_hi(k0..k7) | im_lo(k0..k7) |        (128 B per row per group)
-// with x_hi = x & 0xFFFFE000 (exact tf32) and x_lo = x - x_hi (exact in fp32). One TMA box row is one
-// 128 B swizzle-128B line; each 32 B chunk is exactly one K=8 tf32 MMA operand, so the MMA descriptor
-// for chunk p is the tile descriptor advanced by 32*p bytes.
+// Operand format (written by the K1 pack pass with the split writers, permute.cu): a K-major matrix [rows][4*K] of
+// 32-bit words where every group of 8 k-values is stored as four consecutive 32 B chunks
+//     | re_hi(k0..k7) | re_x(k0..k7) | im_hi(k0..k7) | im_x(k0..k7) |        (128 B per row per group)
+// One TMA box row is one 128 B swizzle-128B line; each 32 B chunk is exactly one MMA operand (K = 8 tf32 or K = 16 bf16),
+// so the MMA descriptor for chunk p is the tile descriptor advanced by 32*p bytes.
 //
-// Float32 (REAL) operands use the same 128 B lines with two 8-k groups per line: | hi(k0..7) | lo(k0..7) | hi(k8..15) |
-// lo(k8..15) | (SPLIT2 writer), 6 MMAs per line (3xTF32 for each 8-k group) into ONE accumulator, and a 128 x 256
-// tile (N = 256 keeps the smem operand traffic per MMA at 12 KB / 128 cycles, under the 128 B/clk limit).
+// Two split schemes (Tf32Params::mixed):
+//   * mixed TF32 + BF16 (default). x_hi = tf32_rn(x); the x chunk holds bf16 PAIRS: (bf16(x), bf16(x - x_hi)) for the row
+//     operand and (bf16(y - y_hi), bf16(y)) for the column operand. x*y = x_hi*y_hi (one kind::tf32 MMA, K = 8) +
+//     [x*y_lo + x_lo*y] (ONE kind::f16 bf16 MMA, K = 16, same tensor cycles and smem bytes as a K = 8 tf32 MMA) + O(2^-22):
+//     2 MMAs per real product instead of 3. The cross terms are ~2^-11 of the product, so bf16's 2^-9 rounding leaves
+//     ~5e-7 relative error (simulated in fp64; measured with the TMEM accumulation: see DESIGN 3.4).
+//     Per group of 8 k the MMA warp issues 8 MMAs (2 x 4M) into two TMEM accumulators:
+//         D_re += rh*rh' + rx.rx' - (ih*ih' + ix.ix')      (minus = a_negate in the idesc)
+//         D_im += rh*ih' + rx.ix' +  ih*rh' + ix.rx'
+//   * 3xTF32 (MB200_SPLIT_SCHEME=3xtf32): x_hi = x & 0xFFFFE000, the x chunk is the fp32 remainder x_lo; 12 MMAs:
+//         D_re += rh*rh' + rh*rl' + rl*rh' - (ih*ih' + ih*il' + il*ih')
+//         D_im += rh*ih' + rh*il' + rl*ih' +  ih*rh' + ih*rl' + il*rh'
+// Effective ceiling in complex-flop terms: TF32 dense peak / 2 (mixed: 8 tf32-equivalent MACs per complex MAC = 8 flops)
+// or / 3 (3xTF32).
 //
-// Per group of 8 k the MMA warp issues 12 MMAs (3xTF32 x 4M) into two TMEM accumulators:
-//     D_re += rh*rh' + rh*rl' + rl*rh' - (ih*ih' + ih*il' + il*ih')      (minus = a_negate in the idesc)
-//     D_im += rh*ih' + rh*il' + rl*ih' +  ih*rh' + ih*rl' + il*rh'
-// Effective ceiling: TF32 dense peak / 3 in complex-flop terms (8 flops per complex MAC = 12 tf32 MACs).
+// Float32 (REAL) operands use the same 128 B lines with two 8-k groups per line: | hi(k0..7) | x(k0..7) | hi(k8..15) |
+// x(k8..15) |, 4 (mixed) or 6 (3xTF32) MMAs per line into ONE accumulator, and a 128 x 256 tile (N = 256 keeps the smem
+// operand traffic per MMA at 12 KB / 128 cycles, under the 128 B/clk limit).
 //
 // Roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
 // warps 2..9 = epilogue (tcgen05.ld 32 lanes x BN/2 columns each -> running sums in registers ->
@@ -106,6 +115,14 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -129,10 +146,11 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @4, a/b_format TF32 = 2 @7/@10,
-// a_negate @13, a/b K-major (0) @15/@16, N >> 3 @17, M >> 4 @24
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool neg_a) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((neg_a ? 1u : 0u) << 13) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @4, a/b_format @7/@10 (TF32 = 2 for kind::tf32,
+// BF16 = 1 for kind::f16), a_negate @13, a/b K-major (0) @15/@16, N >> 3 @17, M >> 4 @24
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool neg_a, bool bf16 = false) {
+    const uint32_t fmt = bf16 ? 1u : 2u;
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((neg_a ? 1u : 0u) << 13) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 struct Tf32Params {
@@ -147,6 +165,7 @@ struct Tf32Params {
     // tf32_splitk_reduce_kernel adds the slices in order and scatters through the C tables.
     int nsplit;
     void *ws;
+    int mixed;   // 1: TF32 + BF16 operand format (8 / 4 MMAs per line), 0: 3xTF32 (12 / 6)
 };
 
 template <int BN, bool REAL>
@@ -236,6 +255,8 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     } else if (warp == 1) {
         if (lane == 0) {   // ---- MMA issuer
             constexpr uint32_t IDESC = make_idesc(TBM, BN, false), IDESC_NEG = make_idesc(TBM, BN, true);
+            constexpr uint32_t IDESC_X = make_idesc(TBM, BN, false, true), IDESC_XNEG = make_idesc(TBM, BN, true, true);
+            const bool mixed = p.mixed != 0;
             uint32_t it = 0, ch = 0;   // running stage / chunk counters
             for (int64_t unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
                 const int64_t sp = unit / ntiles;
@@ -258,13 +279,32 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         const uint64_t a_rh = da, a_rl = da + 2, a_ih = da + 4, a_il = da + 6;
                         const uint64_t b_rh = db, b_rl = db + 2, b_ih = db + 4, b_il = db + 6;
                         const uint32_t acc = first ? 0u : 1u;
-                        if constexpr (REAL) {   // line = hi0 | lo0 | hi1 | lo1: 3xTF32 for each 8-k group
+                        if constexpr (REAL) {   // line = hi0 | x0 | hi1 | x1: two 8-k groups
+                            if (mixed) {
+                                umma_tf32(d_re, a_rh, b_rh, IDESC, acc);
+                                umma_bf16(d_re, a_rl, b_rl, IDESC_X, 1u);
+                                umma_tf32(d_re, a_ih, b_ih, IDESC, 1u);
+                                umma_bf16(d_re, a_il, b_il, IDESC_X, 1u);
+                            } else {
+                                umma_tf32(d_re, a_rh, b_rh, IDESC, acc);
+                                umma_tf32(d_re, a_rh, b_rl, IDESC, 1u);
+                                umma_tf32(d_re, a_rl, b_rh, IDESC, 1u);
+                                umma_tf32(d_re, a_ih, b_ih, IDESC, 1u);
+                                umma_tf32(d_re, a_ih, b_il, IDESC, 1u);
+                                umma_tf32(d_re, a_il, b_ih, IDESC, 1u);
+                            }
+                            umma_commit(&empty[s]);
+                            continue;
+                        }
+                        if (mixed) {            // chunks 1 / 3 are the bf16 cross-term pairs
                             umma_tf32(d_re, a_rh, b_rh, IDESC, acc);
-                            umma_tf32(d_re, a_rh, b_rl, IDESC, 1u);
-                            umma_tf32(d_re, a_rl, b_rh, IDESC, 1u);
-                            umma_tf32(d_re, a_ih, b_ih, IDESC, 1u);
-                            umma_tf32(d_re, a_ih, b_il, IDESC, 1u);
-                            umma_tf32(d_re, a_il, b_ih, IDESC, 1u);
+                            umma_tf32(d_im, a_rh, b_ih, IDESC, acc);
+                            umma_bf16(d_re, a_rl, b_rl, IDESC_X, 1u);
+                            umma_bf16(d_im, a_rl, b_il, IDESC_X, 1u);
+                            umma_tf32(d_re, a_ih, b_ih, IDESC_NEG, 1u);
+                            umma_tf32(d_im, a_ih, b_rh, IDESC, 1u);
+                            umma_bf16(d_re, a_il, b_il, IDESC_XNEG, 1u);
+                            umma_bf16(d_im, a_il, b_rl, IDESC_X, 1u);
                             umma_commit(&empty[s]);
                             continue;
                         }
@@ -414,7 +454,7 @@ bool make_map(CUtensorMap *map, const void *base, int64_t K, int W, int64_t rows
 }
 
 template <int BN, bool REAL>
-cudaError_t launch_bn(const void *packA, const void *packB, const GettParams &g, cudaStream_t s) {
+cudaError_t launch_bn(const void *packA, const void *packB, const GettParams &g, bool mixed, cudaStream_t s) {
     CUtensorMap mapA, mapB;
     constexpr int W = REAL ? 2 : 4;
     if (!make_map(&mapA, packA, g.K, W, g.M, g.L, TBM) || !make_map(&mapB, packB, g.K, W, g.N, g.L, BN))
@@ -424,6 +464,7 @@ cudaError_t launch_bn(const void *packA, const void *packB, const GettParams &g,
     p.C = g.C;
     p.rowC = g.rowC; p.colC = g.colC; p.batC = g.batC;
     p.M = g.M; p.N = g.N; p.L = g.L;
+    p.mixed = mixed ? 1 : 0;
     p.KG = REAL ? (int)((g.K + 15) / 16) : (int)(g.K / 8);   // a half-filled last line reads zeros (TMA out-of-bounds fill)
     const int64_t ntiles = ((g.M + TBM - 1) / TBM) * ((g.N + BN - 1) / BN) * g.L;
     if (ntiles <= 0) return cudaSuccess;
@@ -467,14 +508,14 @@ cudaError_t tf32_configure() {
 
 // C (scattered through rowC/colC/batC) = packA [L][M][W*K] x packB [L][N][W*K]^T, K % 8 == 0;
 // dtype ComplexF32 (W = 4) or Float32 (W = 2)
-cudaError_t launch_tf32_gemm(int dtype, const void *packA, const void *packB, const GettParams &g, cudaStream_t s) {
+cudaError_t launch_tf32_gemm(int dtype, const void *packA, const void *packB, const GettParams &g, bool mixed, cudaStream_t s) {
     if (g.K % 8 != 0 || g.K < 8) return cudaErrorInvalidValue;
     if (dtype == MB200_F32) {
-        if (g.N > 128) return launch_bn<256, true>(packA, packB, g, s);
-        return launch_bn<128, true>(packA, packB, g, s);
+        if (g.N > 128) return launch_bn<256, true>(packA, packB, g, mixed, s);
+        return launch_bn<128, true>(packA, packB, g, mixed, s);
     }
-    if (g.N > 64) return launch_bn<128, false>(packA, packB, g, s);
-    return launch_bn<64, false>(packA, packB, g, s);
+    if (g.N > 64) return launch_bn<128, false>(packA, packB, g, mixed, s);
+    return launch_bn<64, false>(packA, packB, g, mixed, s);
 }
 
 }  // namespace mb200
