@@ -248,6 +248,7 @@ typedef struct {
     uint64_t launches_permute, launches_table, launches_convert, launches_reduce;
     uint64_t plans_built, plans_hit;
     uint64_t launches_unary, launches_hadamard, graph_launches, launches_svd;
+    uint64_t launches_tcgen05_pair;   /* of launches_tcgen05: run by the CTA-pair (cta_group::2) kernel */
 } mb200_stats_t;
 int mb200_get_stats(mb200_handle_t handle, mb200_stats_t *stats);
 int mb200_reset_stats(mb200_handle_t handle);

@@ -65,7 +65,7 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "launches_total", "launches_direct", "launches_gett_f64", "launches_simt_f32", "launches_tcgen05",
         "launches_permute", "launches_table", "launches_convert", "launches_reduce", "plans_built", "plans_hit",
-        "launches_unary", "launches_hadamard", "graph_launches", "launches_svd")]
+        "launches_unary", "launches_hadamard", "graph_launches", "launches_svd", "launches_tcgen05_pair")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

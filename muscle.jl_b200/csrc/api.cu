@@ -353,8 +353,10 @@ int contract_device(mb200_handle_t h, void *C, TensorDesc &dC, const int64_t *st
             GettParams g = cp->gp;
             g.C = C;
             if (sc) g.sc = *sc;
-            e = launch_tf32_gemm(p.dtype, pa, pb, g, tf32_mixed(), s);
+            bool pair = false;
+            e = launch_tf32_gemm(p.dtype, pa, pb, g, tf32_mixed(), s, &pair);
             h->stats.launches_tcgen05++;
+            if (pair) h->stats.launches_tcgen05_pair++;
         }
         cudaFreeAsync(pa, s);
         cudaFreeAsync(pb, s);

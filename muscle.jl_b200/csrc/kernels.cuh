@@ -129,7 +129,9 @@ cudaError_t launch_permute(int dtype, const PermuteParams &p, const void *src, v
 
 // ---- K3: tcgen05 / TMEM 3xTF32 ComplexF32 GEMM on packed operands (tf32.cu) ---------------------------------
 bool tf32_available();
-// mixed: operands are in the TF32 + BF16 format (split 2 / 3), else 3xTF32 (split 1)
-cudaError_t launch_tf32_gemm(int dtype, const void *packA, const void *packB, const GettParams &g, bool mixed, cudaStream_t s);
+// mixed: operands are in the TF32 + BF16 format (split 2 / 3), else 3xTF32 (split 1); *pair (optional) reports whether the
+// CTA-pair kernel (cta_group::2, 256-row tiles) was launched
+cudaError_t launch_tf32_gemm(int dtype, const void *packA, const void *packB, const GettParams &g, bool mixed, cudaStream_t s,
+                             bool *pair = nullptr);
 
 }  // namespace mb200

@@ -98,33 +98,74 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
-__device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+// CTA-pair form: executed by both CTAs of the pair, each into its own shared memory; the transaction bytes are
+// counted on the LEADER CTA's mbarrier (peer bit of the shared::cluster address cleared, as cute::SM100_TMA_2SM_LOAD does)
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_3d_pair(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
 }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t *bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(smem_u32(bar)), "r"(rank)
+        : "memory");
+}
+template <bool CTA2>
+__device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t ncols) {
+    if constexpr (CTA2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+}
+template <bool CTA2>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+    if constexpr (CTA2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+// D[tmem] (+)= A[smem] * B[smem]^T. BF16 = false: kind::tf32 (K = 8); true: kind::f16 with bf16 operands (K = 16).
+// CTA2: issued by the leader CTA of a pair for both tensor cores (M = 256: 128 rows per CTA, each CTA holds N / 2 rows of B).
+template <bool CTA2, bool BF16>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (CTA2 && BF16)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    else if constexpr (CTA2)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    else if constexpr (BF16)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
+// mbarrier arrive once all MMAs issued so far by this thread have completed; CTA2: on the barrier at this offset in BOTH CTAs
+template <bool CTA2>
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    if constexpr (CTA2)
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+    else
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -149,7 +190,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @4, a/b_format @7/@10 (TF32 = 2 for kind::tf32,
 // BF16 = 1 for kind::f16), a_negate @13, a/b K-major (0) @15/@16, N >> 3 @17, M >> 4 @24
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool neg_a, bool bf16 = false) {
-    const uint32_t fmt = bf16 ? 1u : 2u;
+    const uint32_t fmt = bf16 ? 1u : 2u;   // M = 256 only with cta_group::2
     return (1u << 4) | (fmt << 7) | (fmt << 10) | ((neg_a ? 1u : 0u) << 13) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
@@ -168,12 +209,13 @@ struct Tf32Params {
     int mixed;   // 1: TF32 + BF16 operand format (8 / 4 MMAs per line), 0: 3xTF32 (12 / 6)
 };
 
-template <int BN, bool REAL>
+template <int BN, bool REAL, bool CTA2>
 struct Tf32Smem {
-    static constexpr int TSTAGES = BN == 256 ? 4 : 6;
+    static constexpr int B_ROWS = CTA2 ? BN / 2 : BN;   // CTA pair: each CTA holds half of the column operand's rows
     static constexpr int A_BYTES = TBM * GROUP_BYTES;   // 16 KB
-    static constexpr int B_BYTES = BN * GROUP_BYTES;
+    static constexpr int B_BYTES = B_ROWS * GROUP_BYTES;
     static constexpr int STAGE = A_BYTES + B_BYTES;
+    static constexpr int TSTAGES = (192 * 1024) / STAGE;   // 6 x 32 KB, 4 x 48 KB; pair: 8 x 24 KB, 6 x 32 KB
     static constexpr int TOTAL = TSTAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/ + 2 * BN * 8 /*colC, two tiles*/;
 };
 
@@ -184,15 +226,15 @@ struct Tf32Smem {
 // added with ordinary round-to-nearest FADDs.
 // tile id -> (m0, n0, batch): grouped rasterisation, 8 row-tiles share a B column panel in L2
 struct TileCoord { int m0, n0, l; };
-template <int BN>
+template <int BN, int PM = TBM>   // PM = rows per tile: 128, or 256 for a CTA pair
 __device__ __forceinline__ TileCoord tile_coord(const Tf32Params &p, int64_t tile) {
-    const int64_t tiles_m = (p.M + TBM - 1) / TBM, tiles_n = (p.N + BN - 1) / BN;
+    const int64_t tiles_m = (p.M + PM - 1) / PM, tiles_n = (p.N + BN - 1) / BN;
     const int64_t per = tiles_m * tiles_n;
     const int64_t l = tile / per, t = tile % per;
     const int64_t gsz_full = 8, pg = gsz_full * tiles_n, g = t / pg, gm0 = g * gsz_full;
     const int64_t gsz = (tiles_m - gm0) < gsz_full ? (tiles_m - gm0) : gsz_full;
     const int64_t tm = gm0 + (t % pg) % gsz, tn = (t % pg) / gsz;
-    return TileCoord{(int)(tm * TBM), (int)(tn * BN), (int)l};
+    return TileCoord{(int)(tm * PM), (int)(tn * BN), (int)l};
 }
 
 // Persistent: CTA b walks tiles b, b + gridDim.x, ... The three roles keep running counters (smem stage / TMEM
@@ -200,12 +242,23 @@ __device__ __forceinline__ TileCoord tile_coord(const Tf32Params &p, int64_t til
 // stages while the MMA warp is still on the current tile's tail, and the MMA warp starts the next tile's first
 // chunk while the epilogue warps are still storing the previous tile: per-tile prologue and epilogue are hidden
 // (K = 512 slices: 0.362 -> 0.317 ms).
-template <int BN, bool REAL>
+//
+// CTA2 (cluster of two CTAs = one TPC, tcgen05 cta_group::2): the pair owns a 256 x BN tile. Each CTA loads its own 128
+// rows of the row operand and HALF of the column operand's rows (BN / 2), the leader CTA (rank 0) issues M = 256 MMAs
+// that drive both tensor cores, each CTA's accumulators sit in its own TMEM and are drained by its own epilogue warps.
+// Why: the 1-CTA kernel is bound by the shared-memory data pipe — ncu (mixed scheme, config 3): MMA operand reads 59.6 %
+// + TMA fill 29.8 % of the pipe's peak, tensor pipe 61.6 % active. With the pair every MMA reads 6 KB instead of 8 KB per
+// CTA and a stage is 24 KB instead of 32 KB. Barriers: full[] lives in the leader (its expect_tx covers both CTAs'
+// bytes; the peer's TMA completes on it through the cleared peer bit), empty[] and tmem_full[] exist in both CTAs and are
+// signalled by multicast commits, tmem_empty[] lives in the leader and counts the epilogue warps of both CTAs.
+template <int BN, bool REAL, bool CTA2>
 __global__ void __launch_bounds__(TTHREADS, 1)
 tf32_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const __grid_constant__ Tf32Params p) {
-    using SM = Tf32Smem<BN, REAL>;
+    using SM = Tf32Smem<BN, REAL, CTA2>;
     constexpr int TSTAGES = SM::TSTAGES;
+    constexpr int NCTA = CTA2 ? 2 : 1;
+    constexpr int PM = TBM * NCTA;                // rows per (pair) tile
     constexpr int CHUNK_GROUPS = CHUNK_K / (REAL ? 16 : 8);   // smem lines per TMEM chunk
     constexpr int HALF = BN / 2;                  // columns per epilogue thread
     constexpr uint32_t BUF_COLS = REAL ? BN : 2 * BN;   // D (real) or D_re | D_im
@@ -221,44 +274,53 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t ntiles = p.ntiles, nunits = p.ntiles * p.nsplit;
+    const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;          // 0 = leader
+    const int64_t walker = CTA2 ? blockIdx.x / 2 : blockIdx.x;    // persistent walker id (CTA or CTA pair)
+    const int64_t nwalkers = CTA2 ? gridDim.x / 2 : gridDim.x;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
         for (int s = 0; s < TSTAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; b++) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 8); }
+        for (int b = 0; b < 2; b++) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 8 * NCTA); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == 1) tmem_alloc<CTA2>(tmem_slot, TMEM_COLS);
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CTA2) cluster_sync_all(); else __syncthreads();   // pair: both CTAs' barriers and TMEM exist before any remote use
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {   // ---- TMA producer
+        if (lane == 0) {   // ---- TMA producer (every CTA: its rows of A, its share of B)
             uint32_t it = 0;   // running stage counter
-            for (int64_t unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+            for (int64_t unit = walker; unit < nunits; unit += nwalkers) {
                 const int64_t tile = unit % ntiles, sp = unit / ntiles;
-                const TileCoord tc = tile_coord<BN>(p, tile);
+                const TileCoord tc = tile_coord<BN, PM>(p, tile);
                 const int kg0 = (int)((int64_t)p.KG * sp / p.nsplit), kg1 = (int)((int64_t)p.KG * (sp + 1) / p.nsplit);
                 for (int kg = kg0; kg < kg1; kg++, it++) {
                     const int s = it % TSTAGES;
                     mbar_wait(&empty[s], ((it / TSTAGES) & 1) ^ 1);
-                    mbar_expect_tx(&full[s], SM::STAGE);
                     unsigned char *a = tiles + s * SM::STAGE;
-                    tma_load_3d(a, &mapA, &full[s], kg * 32, tc.m0, tc.l);
-                    tma_load_3d(a + SM::A_BYTES, &mapB, &full[s], kg * 32, tc.n0, tc.l);
+                    if constexpr (CTA2) {
+                        if (rank == 0) mbar_expect_tx(&full[s], 2 * SM::STAGE);
+                        tma_load_3d_pair(a, &mapA, &full[s], kg * 32, tc.m0 + (int)rank * TBM, tc.l);
+                        tma_load_3d_pair(a + SM::A_BYTES, &mapB, &full[s], kg * 32, tc.n0 + (int)rank * SM::B_ROWS, tc.l);
+                    } else {
+                        mbar_expect_tx(&full[s], SM::STAGE);
+                        tma_load_3d(a, &mapA, &full[s], kg * 32, tc.m0, tc.l);
+                        tma_load_3d(a + SM::A_BYTES, &mapB, &full[s], kg * 32, tc.n0, tc.l);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {   // ---- MMA issuer
-            constexpr uint32_t IDESC = make_idesc(TBM, BN, false), IDESC_NEG = make_idesc(TBM, BN, true);
-            constexpr uint32_t IDESC_X = make_idesc(TBM, BN, false, true), IDESC_XNEG = make_idesc(TBM, BN, true, true);
+        if (lane == 0 && rank == 0) {   // ---- MMA issuer (pair: the leader CTA only)
+            constexpr uint32_t IDESC = make_idesc(PM, BN, false), IDESC_NEG = make_idesc(PM, BN, true);
+            constexpr uint32_t IDESC_X = make_idesc(PM, BN, false, true), IDESC_XNEG = make_idesc(PM, BN, true, true);
             const bool mixed = p.mixed != 0;
             uint32_t it = 0, ch = 0;   // running stage / chunk counters
-            for (int64_t unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+            for (int64_t unit = walker; unit < nunits; unit += nwalkers) {
                 const int64_t sp = unit / ntiles;
                 const int kg0 = (int)((int64_t)p.KG * sp / p.nsplit), kg1 = (int)((int64_t)p.KG * (sp + 1) / p.nsplit);
                 const int nchunks = (kg1 - kg0 + CHUNK_GROUPS - 1) / CHUNK_GROUPS;
@@ -279,50 +341,47 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         const uint64_t a_rh = da, a_rl = da + 2, a_ih = da + 4, a_il = da + 6;
                         const uint64_t b_rh = db, b_rl = db + 2, b_ih = db + 4, b_il = db + 6;
                         const uint32_t acc = first ? 0u : 1u;
+                        constexpr bool T = false, X = true;   // MMA kind: tf32 / bf16
                         if constexpr (REAL) {   // line = hi0 | x0 | hi1 | x1: two 8-k groups
                             if (mixed) {
-                                umma_tf32(d_re, a_rh, b_rh, IDESC, acc);
-                                umma_bf16(d_re, a_rl, b_rl, IDESC_X, 1u);
-                                umma_tf32(d_re, a_ih, b_ih, IDESC, 1u);
-                                umma_bf16(d_re, a_il, b_il, IDESC_X, 1u);
+                                umma<CTA2, T>(d_re, a_rh, b_rh, IDESC, acc);
+                                umma<CTA2, X>(d_re, a_rl, b_rl, IDESC_X, 1u);
+                                umma<CTA2, T>(d_re, a_ih, b_ih, IDESC, 1u);
+                                umma<CTA2, X>(d_re, a_il, b_il, IDESC_X, 1u);
                             } else {
-                                umma_tf32(d_re, a_rh, b_rh, IDESC, acc);
-                                umma_tf32(d_re, a_rh, b_rl, IDESC, 1u);
-                                umma_tf32(d_re, a_rl, b_rh, IDESC, 1u);
-                                umma_tf32(d_re, a_ih, b_ih, IDESC, 1u);
-                                umma_tf32(d_re, a_ih, b_il, IDESC, 1u);
-                                umma_tf32(d_re, a_il, b_ih, IDESC, 1u);
+                                umma<CTA2, T>(d_re, a_rh, b_rh, IDESC, acc);
+                                umma<CTA2, T>(d_re, a_rh, b_rl, IDESC, 1u);
+                                umma<CTA2, T>(d_re, a_rl, b_rh, IDESC, 1u);
+                                umma<CTA2, T>(d_re, a_ih, b_ih, IDESC, 1u);
+                                umma<CTA2, T>(d_re, a_ih, b_il, IDESC, 1u);
+                                umma<CTA2, T>(d_re, a_il, b_ih, IDESC, 1u);
                             }
-                            umma_commit(&empty[s]);
-                            continue;
+                        } else if (mixed) {     // chunks 1 / 3 are the bf16 cross-term pairs
+                            umma<CTA2, T>(d_re, a_rh, b_rh, IDESC, acc);
+                            umma<CTA2, T>(d_im, a_rh, b_ih, IDESC, acc);
+                            umma<CTA2, X>(d_re, a_rl, b_rl, IDESC_X, 1u);
+                            umma<CTA2, X>(d_im, a_rl, b_il, IDESC_X, 1u);
+                            umma<CTA2, T>(d_re, a_ih, b_ih, IDESC_NEG, 1u);
+                            umma<CTA2, T>(d_im, a_ih, b_rh, IDESC, 1u);
+                            umma<CTA2, X>(d_re, a_il, b_il, IDESC_XNEG, 1u);
+                            umma<CTA2, X>(d_im, a_il, b_rl, IDESC_X, 1u);
+                        } else {
+                            umma<CTA2, T>(d_re, a_rh, b_rh, IDESC, acc);
+                            umma<CTA2, T>(d_im, a_rh, b_ih, IDESC, acc);
+                            umma<CTA2, T>(d_re, a_rh, b_rl, IDESC, 1u);
+                            umma<CTA2, T>(d_im, a_rh, b_il, IDESC, 1u);
+                            umma<CTA2, T>(d_re, a_rl, b_rh, IDESC, 1u);
+                            umma<CTA2, T>(d_im, a_rl, b_ih, IDESC, 1u);
+                            umma<CTA2, T>(d_re, a_ih, b_ih, IDESC_NEG, 1u);
+                            umma<CTA2, T>(d_im, a_ih, b_rh, IDESC, 1u);
+                            umma<CTA2, T>(d_re, a_ih, b_il, IDESC_NEG, 1u);
+                            umma<CTA2, T>(d_im, a_ih, b_rl, IDESC, 1u);
+                            umma<CTA2, T>(d_re, a_il, b_ih, IDESC_NEG, 1u);
+                            umma<CTA2, T>(d_im, a_il, b_rh, IDESC, 1u);
                         }
-                        if (mixed) {            // chunks 1 / 3 are the bf16 cross-term pairs
-                            umma_tf32(d_re, a_rh, b_rh, IDESC, acc);
-                            umma_tf32(d_im, a_rh, b_ih, IDESC, acc);
-                            umma_bf16(d_re, a_rl, b_rl, IDESC_X, 1u);
-                            umma_bf16(d_im, a_rl, b_il, IDESC_X, 1u);
-                            umma_tf32(d_re, a_ih, b_ih, IDESC_NEG, 1u);
-                            umma_tf32(d_im, a_ih, b_rh, IDESC, 1u);
-                            umma_bf16(d_re, a_il, b_il, IDESC_XNEG, 1u);
-                            umma_bf16(d_im, a_il, b_rl, IDESC_X, 1u);
-                            umma_commit(&empty[s]);
-                            continue;
-                        }
-                        umma_tf32(d_re, a_rh, b_rh, IDESC, acc);
-                        umma_tf32(d_im, a_rh, b_ih, IDESC, acc);
-                        umma_tf32(d_re, a_rh, b_rl, IDESC, 1u);
-                        umma_tf32(d_im, a_rh, b_il, IDESC, 1u);
-                        umma_tf32(d_re, a_rl, b_rh, IDESC, 1u);
-                        umma_tf32(d_im, a_rl, b_ih, IDESC, 1u);
-                        umma_tf32(d_re, a_ih, b_ih, IDESC_NEG, 1u);
-                        umma_tf32(d_im, a_ih, b_rh, IDESC, 1u);
-                        umma_tf32(d_re, a_ih, b_il, IDESC_NEG, 1u);
-                        umma_tf32(d_im, a_ih, b_rl, IDESC, 1u);
-                        umma_tf32(d_re, a_il, b_ih, IDESC_NEG, 1u);
-                        umma_tf32(d_im, a_il, b_rh, IDESC, 1u);
-                        umma_commit(&empty[s]);          // frees the smem stage when these MMAs have read it
+                        umma_commit<CTA2>(&empty[s]);          // frees the smem stage (in both CTAs) when these MMAs have read it
                     }
-                    umma_commit(&tmem_full[buf]);        // this chunk's accumulators are complete
+                    umma_commit<CTA2>(&tmem_full[buf]);        // this chunk's accumulators are complete
                 }
             }
         }
@@ -331,14 +390,14 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         const int row = q * 32 + lane;
         const int et = threadIdx.x - 64;   // 0..255 among the epilogue threads
         uint32_t ch = 0, tcount = 0;
-        for (int64_t unit = blockIdx.x; unit < nunits; unit += gridDim.x, tcount++) {
+        for (int64_t unit = walker; unit < nunits; unit += nwalkers, tcount++) {
             const int64_t tile = unit % ntiles, sp = unit / ntiles;
             const int kg0 = (int)((int64_t)p.KG * sp / p.nsplit), kg1 = (int)((int64_t)p.KG * (sp + 1) / p.nsplit);
             const int nchunks = (kg1 - kg0 + CHUNK_GROUPS - 1) / CHUNK_GROUPS;
-            const TileCoord tc = tile_coord<BN>(p, tile);
+            const TileCoord tc = tile_coord<BN, PM>(p, tile);
             int64_t *cols = sColC + (tcount & 1) * BN;
             for (int i = et; i < BN; i += TTHREADS - 64) cols[i] = (tc.n0 + i < p.N) ? p.colC[tc.n0 + i] : 0;
-            const int64_t m = (int64_t)tc.m0 + row;
+            const int64_t m = (int64_t)tc.m0 + (int64_t)rank * TBM + row;
             const bool row_ok = m < p.M;
             const int64_t crow = (row_ok ? p.rowC[m] : 0) + p.batC[tc.l];
             float accr[HALF], acci[REAL ? 1 : HALF];
@@ -367,9 +426,12 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                if (lane == 0) {
+                    if constexpr (CTA2) mbar_arrive_cluster(&tmem_empty[buf], 0);   // the leader's MMA warp waits for both CTAs
+                    else mbar_arrive(&tmem_empty[buf]);
+                }
             }
-            if (p.nsplit > 1) {   // partial tile -> workspace, row fastest (coalesced), every row / column of the tile
+            if (p.nsplit > 1) {   // partial tile -> workspace, row fastest (coalesced), every row / column of the tile (1-CTA only)
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 const size_t base = (size_t)unit * (TBM * BN) + row;
 #pragma unroll
@@ -396,8 +458,8 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         if (p.sc.nranks) __threadfence_system();   // peer stores must be visible before the cross-rank barrier
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (CTA2) cluster_sync_all(); else __syncthreads();   // pair: no CTA frees TMEM / exits while the other still uses it
+    if (warp == 1) tmem_dealloc<CTA2>(tmem_base, TMEM_COLS);
 }
 
 // C[rowC[m] + colC[n] + batC[l]] = sum over slices of ws[(s * ntiles + tile) * 128 * BN + col * 128 + row]
@@ -453,12 +515,16 @@ bool make_map(CUtensorMap *map, const void *base, int64_t K, int W, int64_t rows
     return r == CUDA_SUCCESS;
 }
 
+// CTA-pair policy: MB200_CTA_PAIR=0 disables, 2 forces the pair kernel whenever the shape allows it (tests, A/B)
+int pair_mode() {
+    static const int m = [] { const char *e = getenv("MB200_CTA_PAIR"); return e ? atoi(e) : 1; }();
+    return m;
+}
+
 template <int BN, bool REAL>
-cudaError_t launch_bn(const void *packA, const void *packB, const GettParams &g, bool mixed, cudaStream_t s) {
+cudaError_t launch_bn(const void *packA, const void *packB, const GettParams &g, bool mixed, cudaStream_t s, bool *pair) {
     CUtensorMap mapA, mapB;
     constexpr int W = REAL ? 2 : 4;
-    if (!make_map(&mapA, packA, g.K, W, g.M, g.L, TBM) || !make_map(&mapB, packB, g.K, W, g.N, g.L, BN))
-        return cudaErrorInvalidValue;
     Tf32Params p{};
     p.sc = g.sc;
     p.C = g.C;
@@ -468,8 +534,34 @@ cudaError_t launch_bn(const void *packA, const void *packB, const GettParams &g,
     p.KG = REAL ? (int)((g.K + 15) / 16) : (int)(g.K / 8);   // a half-filled last line reads zeros (TMA out-of-bounds fill)
     const int64_t ntiles = ((g.M + TBM - 1) / TBM) * ((g.N + BN - 1) / BN) * g.L;
     if (ntiles <= 0) return cudaSuccess;
-    p.ntiles = ntiles;
     p.nsplit = 1;
+    // CTA pairs (256 x BN tiles, cta_group::2) for the wide tile shapes once there is work for every SM
+    constexpr bool PAIR_OK = (REAL && BN == 256) || (!REAL && BN == 128);
+    if constexpr (PAIR_OK) {
+        const int64_t ptiles = ((g.M + 2 * TBM - 1) / (2 * TBM)) * ((g.N + BN - 1) / BN) * g.L;
+        const bool want = pair_mode() == 2 ? g.M > TBM : (pair_mode() == 1 && g.M >= 2 * TBM && ptiles >= 148);
+        if (want) {
+            if (!make_map(&mapA, packA, g.K, W, g.M, g.L, TBM) || !make_map(&mapB, packB, g.K, W, g.N, g.L, BN / 2))
+                return cudaErrorInvalidValue;
+            p.ntiles = ptiles;
+            if (pair) *pair = true;
+            cudaLaunchConfig_t cfg{};
+            const int64_t pairs = ptiles < 74 ? ptiles : 74;   // persistent: one CTA pair per TPC
+            cfg.gridDim = dim3((unsigned)(2 * pairs));
+            cfg.blockDim = dim3(TTHREADS);
+            cfg.dynamicSmemBytes = Tf32Smem<BN, REAL, true>::TOTAL;
+            cfg.stream = s;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            return cudaLaunchKernelEx(&cfg, tf32_gemm_kernel<BN, REAL, true>, mapA, mapB, p);
+        }
+    }
+    if (!make_map(&mapA, packA, g.K, W, g.M, g.L, TBM) || !make_map(&mapB, packB, g.K, W, g.N, g.L, BN))
+        return cudaErrorInvalidValue;
+    p.ntiles = ntiles;
     // split-K when the tiles cannot fill the SMs: at most one slice per 128-k TMEM chunk
     const int64_t chunks = (g.K + CHUNK_K - 1) / CHUNK_K;
     static const int sk_mode = [] { const char *e = getenv("MB200_SPLITK"); return e ? atoi(e) : 1; }();
@@ -483,7 +575,7 @@ cudaError_t launch_bn(const void *packA, const void *packB, const GettParams &g,
     }
     const int64_t nunits = ntiles * p.nsplit;
     const int64_t grid = nunits < 148 ? nunits : 148;   // persistent: one CTA per SM
-    tf32_gemm_kernel<BN, REAL><<<(unsigned)grid, TTHREADS, Tf32Smem<BN, REAL>::TOTAL, s>>>(mapA, mapB, p);
+    tf32_gemm_kernel<BN, REAL, false><<<(unsigned)grid, TTHREADS, Tf32Smem<BN, REAL, false>::TOTAL, s>>>(mapA, mapB, p);
     if (p.nsplit > 1) {
         const int64_t threads = ntiles * TBM * BN;
         tf32_splitk_reduce_kernel<BN, REAL><<<(unsigned)std::min<int64_t>((threads + 255) / 256, 148 * 16), 256, 0, s>>>(p);
@@ -499,23 +591,27 @@ bool tf32_available() { return encode_fn() != nullptr; }
 
 // opt-in shared memory sizes; called once per device from mb200_create
 cudaError_t tf32_configure() {
-    cudaError_t e = cudaFuncSetAttribute(tf32_gemm_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tf32Smem<128, false>::TOTAL);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tf32_gemm_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tf32Smem<64, false>::TOTAL);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tf32_gemm_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tf32Smem<256, true>::TOTAL);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tf32_gemm_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tf32Smem<128, true>::TOTAL);
+    cudaError_t e = cudaSuccess;
+#define MB200_TCFG(BN, REAL, CTA2)                                                                                          \
+    if (e == cudaSuccess)                                                                                                   \
+        e = cudaFuncSetAttribute(tf32_gemm_kernel<BN, REAL, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tf32Smem<BN, REAL, CTA2>::TOTAL)
+    MB200_TCFG(128, false, false); MB200_TCFG(64, false, false); MB200_TCFG(256, true, false); MB200_TCFG(128, true, false);
+    MB200_TCFG(128, false, true); MB200_TCFG(256, true, true);
+#undef MB200_TCFG
     return e;
 }
 
 // C (scattered through rowC/colC/batC) = packA [L][M][W*K] x packB [L][N][W*K]^T, K % 8 == 0;
 // dtype ComplexF32 (W = 4) or Float32 (W = 2)
-cudaError_t launch_tf32_gemm(int dtype, const void *packA, const void *packB, const GettParams &g, bool mixed, cudaStream_t s) {
+cudaError_t launch_tf32_gemm(int dtype, const void *packA, const void *packB, const GettParams &g, bool mixed, cudaStream_t s, bool *pair) {
+    if (pair) *pair = false;
     if (g.K % 8 != 0 || g.K < 8) return cudaErrorInvalidValue;
     if (dtype == MB200_F32) {
-        if (g.N > 128) return launch_bn<256, true>(packA, packB, g, mixed, s);
-        return launch_bn<128, true>(packA, packB, g, mixed, s);
+        if (g.N > 128) return launch_bn<256, true>(packA, packB, g, mixed, s, pair);
+        return launch_bn<128, true>(packA, packB, g, mixed, s, pair);
     }
-    if (g.N > 64) return launch_bn<128, false>(packA, packB, g, mixed, s);
-    return launch_bn<64, false>(packA, packB, g, mixed, s);
+    if (g.N > 64) return launch_bn<128, false>(packA, packB, g, mixed, s, pair);
+    return launch_bn<64, false>(packA, packB, g, mixed, s, pair);
 }
 
 }  // namespace mb200

@@ -479,6 +479,40 @@ def test_tcgen05_split_k(m, n, k, l, dt):
     assert rel_frobenius(got.astype(wide), refr) <= 1e-5
 
 
+@pytest.mark.parametrize("dt,m,n,k,l", [("complex64", 4096, 4736, 264, 1), ("complex64", 1100, 2100, 520, 9), ("float32", 4608, 8448, 392, 1),
+                                        ("float32", 3000, 1400, 136, 12)])
+def test_tcgen05_cta_pair(dt, m, n, k, l):
+    """Shapes with work for every SM take the CTA-pair kernel (cluster of 2, tcgen05 cta_group::2, 256-row tiles, each CTA
+    holding half of the column operand): bit-exact on integer-valued inputs (ragged M / N edges, odd 128-row tile counts
+    so that a pair's second CTA is entirely out of range, batches), 1e-5 on random ones."""
+    rng = np.random.default_rng(12)
+    a = integer_array(rng, (k, m, l), dt, lo=-2, hi=3)
+    b = integer_array(rng, (k, n, l), dt, lo=-2, hi=3)
+    wide = np.complex128 if dt == "complex64" else np.float64
+    ref = np.einsum("kml,knl->nml", a.astype(wide), b.astype(wide)).astype(dt)
+    h = _lib.Handle.get()
+    h.reset_stats()
+    got = contract(a, "kml", b, "knl", "nml", device=True, path=mb.PATH_TCGEN05_TF32)
+    st = h.stats()
+    assert st["launches_tcgen05"] == 1 and st["launches_tcgen05_pair"] == 1, st
+    assert np.array_equal(got, ref)
+    ar, br = random_array(rng, (k, m, l), dt), random_array(rng, (k, n, l), dt)
+    refr = np.einsum("kml,knl->nml", ar.astype(wide), br.astype(wide))
+    got = contract(ar, "kml", br, "knl", "mnl", device=True, path=mb.PATH_TCGEN05_TF32)
+    assert rel_frobenius(got.astype(wide), refr.transpose(1, 0, 2)) <= 1e-5
+
+
+def test_tcgen05_suite_with_cta_pairs_forced():
+    """The whole tcgen05 parity battery once more with MB200_CTA_PAIR=2 (pair kernel for every shape with M > 128,
+    however few tiles) — in a child process, the policy is read once per process."""
+    import subprocess, sys
+    env = dict(os.environ, MB200_CTA_PAIR="2")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k",
+                        "tcgen05_tf32x3_parity or tcgen05_ragged or tcgen05_accuracy or qubit"],
+                       env=env, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 def test_tcgen05_auto_selected_for_large_c64():
     info = mb.plan_describe(_lib.C64, [0, 2, 4, 5, 6], _lib.C64, [0, 1, 2, 3, 6], [256, 8, 8, 256, 8],
                             _lib.C64, [3, 1, 4, 5, 6], [256, 8, 8, 256, 8])
