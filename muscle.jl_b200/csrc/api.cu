@@ -337,24 +337,36 @@ int contract_device(mb200_handle_t h, void *C, TensorDesc &dC, const int64_t *st
         else
             e = launch_direct(p.dtype, cp->dp, R, Q, C, s);
         h->stats.launches_direct++;
-    } else if (p.path == MB200_PATH_TCGEN05_TF32 && tf32_available() && build_pack_params(p, 0, tf32_mixed(), qa, rows_a) &&
-               build_pack_params(p, 1, tf32_mixed(), qb, rows_b)) {
-        // pack A, pack B (K1 with the tf32 hi/lo split writer), then the tcgen05 GEMM with the permuting epilogue
+    } else if (p.path == MB200_PATH_TCGEN05_TF32 && tf32_available()) {
+        // pack A, pack B (K1 with the split writer: a strided permutation when the layout allows it, else the table-driven
+        // gather pack with K zero-padded to a multiple of 8), then the tcgen05 GEMM with the permuting epilogue
+        const bool mixed = tf32_mixed();
+        const bool by_permute = p.tc_permute_pack && build_pack_params(p, 0, mixed, qa, rows_a) && build_pack_params(p, 1, mixed, qb, rows_b);
+        if (!by_permute) { rows_a = p.M; rows_b = p.N; }
+        const int64_t Kp = by_permute ? p.K : (p.K + 7) / 8 * 8;
         void *pa = nullptr, *pb = nullptr;
         const size_t W = p.dtype == MB200_F32 ? 2 : 4;
-        const size_t ba = (size_t)p.L * rows_a * W * p.K * sizeof(float), bb = (size_t)p.L * rows_b * W * p.K * sizeof(float);
+        const size_t ba = (size_t)p.L * rows_a * W * Kp * sizeof(float), bb = (size_t)p.L * rows_b * W * Kp * sizeof(float);
         MB200_CUDA(cudaMallocAsync(&pa, ba, s));
         MB200_CUDA(cudaMallocAsync(&pb, bb, s));
-        e = launch_permute(p.dtype, qa, R, pa, s);
-        if (e == cudaSuccess) e = launch_permute(p.dtype, qb, Q, pb, s);
+        const GettParams &t = cp->gp;
+        if (by_permute) {
+            e = launch_permute(p.dtype, qa, R, pa, s);
+            if (e == cudaSuccess) e = launch_permute(p.dtype, qb, Q, pb, s);
+        } else {
+            e = launch_pack_gather(p.dtype, R, t.rowA, t.kA, t.batA, p.M, p.K, Kp, p.L, p.a_kmajor, mixed ? 2 : 1, (float *)pa, s);
+            if (e == cudaSuccess)
+                e = launch_pack_gather(p.dtype, Q, t.colB, t.kB, t.batB, p.N, p.K, Kp, p.L, p.b_kmajor, mixed ? 3 : 1, (float *)pb, s);
+        }
         h->stats.launches_permute += 2;
         h->stats.launches_total += 2;
         if (e == cudaSuccess) {
             GettParams g = cp->gp;
             g.C = C;
+            g.K = Kp;
             if (sc) g.sc = *sc;
             bool pair = false;
-            e = launch_tf32_gemm(p.dtype, pa, pb, g, tf32_mixed(), s, &pair);
+            e = launch_tf32_gemm(p.dtype, pa, pb, g, mixed, s, &pair);
             h->stats.launches_tcgen05++;
             if (pair) h->stats.launches_tcgen05_pair++;
         }

@@ -126,6 +126,10 @@ struct PermuteParams {
                                          //    operand (x = bf16 pair carrying both cross terms)
 };
 cudaError_t launch_permute(int dtype, const PermuteParams &p, const void *src, void *dst, cudaStream_t s);
+// Table-driven pack of one operand into the tcgen05 operand format, any strides and any K (zero-padded to Kp, a multiple of 8):
+// dst[l][row][W * Kp] <- src[row_tab[row] + k_tab[k] + bat_tab[l]]; split = PermuteParams::split (1, 2 or 3)
+cudaError_t launch_pack_gather(int dtype, const void *src, const int64_t *row_tab, const int64_t *k_tab, const int64_t *bat_tab,
+                               int64_t rows, int64_t K, int64_t Kp, int64_t L, int kmajor, int split, float *dst, cudaStream_t s);
 
 // ---- K3: tcgen05 / TMEM 3xTF32 ComplexF32 GEMM on packed operands (tf32.cu) ---------------------------------
 bool tf32_available();

@@ -397,6 +397,63 @@ __global__ void __launch_bounds__(PT_THREADS) permute_regT_kernel(const __grid_c
     }
 }
 
+// Table-driven pack into the tcgen05 operand format (tf32.cu) for operands the strided-permutation pack cannot express: summed
+// extents that do not tile groups of 8 k (K = 100, bond dimensions 3, 5, 6, 10 ...; K is zero-padded to Kp = 8 * ceil(K / 8)) and
+// strided (non-dense) operands. dst[l][row][group(k)] <- src[row_tab[row] + k_tab[k] + bat_tab[l]] through a 32 x 32 tile:
+// the gather runs with lanes along k (K-major source) or along rows, the writes always with lanes along k (32-byte runs).
+struct PackGather {
+    const int64_t *row_tab, *k_tab, *bat_tab;
+    int64_t rows, K, Kp, L;
+    int kmajor, aux;   // aux: split writer format / side (see put)
+};
+template <bool REAL>
+__global__ void __launch_bounds__(256) pack_gather_kernel(const __grid_constant__ PackGather q, const void *__restrict__ srcv,
+                                                          float *__restrict__ dst) {
+    using E = typename std::conditional<REAL, float, float2>::type;
+    constexpr int W = REAL ? 2 : 4;
+    __shared__ E tile[32][33];
+    const E *src = reinterpret_cast<const E *>(srcv);
+    const int64_t tiles_k = (q.Kp + 31) / 32, tiles_r = (q.rows + 31) / 32;
+    int64_t b = blockIdx.x;
+    const int64_t k0 = (b % tiles_k) * 32; b /= tiles_k;
+    const int64_t r0 = (b % tiles_r) * 32;
+    const int64_t l = b / tiles_r;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t bat = q.bat_tab[l];
+    if (q.kmajor) {
+        const int64_t k = k0 + tx;
+        const bool kok = k < q.K;
+        const int64_t koff = kok ? q.k_tab[k] : 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int r = ty + 8 * i;
+            E v{};
+            if (kok && r0 + r < q.rows) v = src[q.row_tab[r0 + r] + koff + bat];
+            tile[r][tx] = v;
+        }
+    } else {
+        const bool rok = r0 + tx < q.rows;
+        const int64_t roff = rok ? q.row_tab[r0 + tx] : 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int kk = ty + 8 * i;
+            E v{};
+            if (rok && k0 + kk < q.K) v = src[roff + q.k_tab[k0 + kk] + bat];
+            tile[tx][kk] = v;
+        }
+    }
+    __syncthreads();
+    const int64_t k = k0 + tx;
+    if (k >= q.Kp) return;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int r = ty + 8 * i;
+        const int64_t row = r0 + r;
+        if (row < q.rows)
+            put<E, float, REAL ? 3 : 2>(dst, (l * q.rows + row) * (W * q.Kp) + (k >> 3) * (8 * W) + (k & 7), tile[r][tx], q.aux);
+    }
+}
+
 inline int floor_log2(int64_t v) { int l = 0; while ((int64_t)2 << l <= v) l++; return l; }
 inline int ceil_log2(int64_t v) { int l = 0; while (((int64_t)1 << l) < v) l++; return l; }
 
@@ -594,6 +651,18 @@ cudaError_t launch_permute(int dtype, const PermuteParams &q_in, const void *src
         return cudaErrorInvalidValue;   // planar / split need a complex dtype
     }
 #undef MB200_PERM
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_gather(int dtype, const void *src, const int64_t *row_tab, const int64_t *k_tab, const int64_t *bat_tab,
+                               int64_t rows, int64_t K, int64_t Kp, int64_t L, int kmajor, int split, float *dst, cudaStream_t s) {
+    if (rows <= 0 || L <= 0 || Kp <= 0) return cudaSuccess;
+    if (split < 1 || (dtype != MB200_C64 && dtype != MB200_F32)) return cudaErrorInvalidValue;
+    PackGather q{row_tab, k_tab, bat_tab, rows, K, Kp, L, kmajor, split - 1};
+    const int64_t grid = ((Kp + 31) / 32) * ((rows + 31) / 32) * L;
+    if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    if (dtype == MB200_F32) pack_gather_kernel<true><<<(unsigned)grid, 256, 0, s>>>(q, src, dst);
+    else pack_gather_kernel<false><<<(unsigned)grid, 256, 0, s>>>(q, src, dst);
     return cudaGetLastError();
 }
 

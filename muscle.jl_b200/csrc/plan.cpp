@@ -224,8 +224,10 @@ int make_plan(const TensorDesc &A, const TensorDesc &B, TensorDesc &C, const int
     plan.bytes = (double)dtype_size(plan.dtype) *
                  ((double)A.numel() + (double)B.numel() + (double)plan.M * plan.N * plan.L);
 
-    // ---- tcgen05 eligibility: both operands dense in memory (the pack pass is a K1 permute of a dense
-    // tensor) and the fastest summed mode a multiple of 8 (one 8-k group = one 128 B TMA row)
+    // ---- tcgen05 eligibility: ComplexF32 / Float32 with enough rows, columns and k to fill 128-row tiles and 128-k chunks.
+    // Operands that are dense in memory with leading summed modes tiling groups of 8 k are packed by a K1 permutation
+    // (tc_permute_pack); everything else (K = 100, bond dimensions 3, 5, 6 ..., strided operands) by the table-driven gather
+    // pack with K zero-padded to a multiple of 8.
     auto dense = [](const TensorDesc &T) {
         std::vector<std::pair<int64_t, int64_t>> v;
         for (int i = 0; i < T.n; i++)
@@ -238,9 +240,10 @@ int make_plan(const TensorDesc &A, const TensorDesc &B, TensorDesc &C, const int
         }
         return true;
     };
-    plan.tc_ok = (plan.dtype == MB200_C64 || plan.dtype == MB200_F32) && k8_groupable(plan.sum) && dense(A) && dense(B) &&
-                 plan.M >= 64 && plan.N >= 32 && plan.K >= 64 && plan.M < ((int64_t)1 << 31) &&
-                 plan.N < ((int64_t)1 << 31) && plan.L < ((int64_t)1 << 31) && plan.K < ((int64_t)1 << 27);
+    plan.tc_ok = (plan.dtype == MB200_C64 || plan.dtype == MB200_F32) && plan.M >= 64 && plan.N >= 32 && plan.K >= 64 &&
+                 plan.M < ((int64_t)1 << 31) && plan.N < ((int64_t)1 << 31) && plan.L < ((int64_t)1 << 31) &&
+                 plan.K < ((int64_t)1 << 27);
+    plan.tc_permute_pack = plan.tc_ok && k8_groupable(plan.sum) && dense(A) && dense(B);
 
     // ---- kernel family ---------------------------------------------------------------------------
     const int64_t TABLE_LIMIT = (int64_t)1 << 26;

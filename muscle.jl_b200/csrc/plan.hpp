@@ -51,7 +51,9 @@ struct Plan {
     int path = MB200_PATH_DIRECT;
     bool empty_output = false;  // some C extent is 0
     bool apply_like = false;    // K <= 8 and one free side <= 8, no batch: the direct path uses its streaming apply kernel
-    bool tc_ok = false;         // eligible for the tcgen05 3xTF32 path (dense ComplexF32 operands, leading summed modes tile groups of 8 k)
+    bool tc_ok = false;         // eligible for the tcgen05 path (ComplexF32 / Float32, M >= 64, N >= 32, K >= 64)
+    bool tc_permute_pack = false;   // ... with operands a K1 permutation can pack (dense, leading summed modes tile groups of 8 k);
+                                    // otherwise the table-driven gather pack is used (any strides, K zero-padded to 8)
     double flops = 0, bytes = 0;
     std::string key;  // cache key (all integers of the three descriptors + dtypes + forced path)
 };

@@ -519,9 +519,70 @@ def test_tcgen05_auto_selected_for_large_c64():
     assert info.path == mb.PATH_TCGEN05_TF32
     info = mb.plan_describe(_lib.F32, [0, 2], _lib.F32, [0, 1], [4096, 4096], _lib.F32, [1, 2], [4096, 4096])
     assert info.path == mb.PATH_TCGEN05_TF32      # Float32 takes the tensor cores too (3xTF32, 128 x 256 tiles)
-    # strided operand or first summed extent not a multiple of 8 -> FFMA path
+    # summed extent not a multiple of 8: still the tensor cores (gather pack, K zero-padded) once the contraction is big enough
+    info = mb.plan_describe(_lib.C64, [0, 2], _lib.C64, [1, 0], [100, 2048], _lib.C64, [1, 2], [100, 2048])
+    assert info.path == mb.PATH_TCGEN05_TF32
     info = mb.plan_describe(_lib.C64, [0, 2], _lib.C64, [1, 0], [100, 512], _lib.C64, [1, 2], [100, 512])
-    assert info.path == mb.PATH_SIMT_F32
+    assert info.path == mb.PATH_SIMT_F32          # 2.6e7 MACs: below the tcgen05 size floor
+
+
+TC_GATHER_CASES = [
+    ("k100_kmajor", dict(i=300, j=200, k=100), "ki", "kj", "ij"),                    # K = 100 -> padded to 104
+    ("k100_mmajor", dict(i=300, j=200, k=100), "ik", "jk", "ji"),                    # rows fastest in both operands
+    ("bond_3_5_7", dict(a=3, b=5, c=7, i=130, j=70), "aibc", "cjba", "ji"),          # K = 105, three odd summed modes
+    ("peps_d3", dict(l=27, k=9, b=3, m=27, q=9, r=27, z=3), "lkbmz", "mkqrz", "lbqrz"),   # D = 3 PEPS-like, batch z
+    ("mixed_order", dict(a=6, b=10, i=96, j=40, l=4), "aibl", "bjla", "ijl"),       # K = 60 < 64 -> not eligible, FFMA fallback
+]
+
+
+@pytest.mark.parametrize("dt", ["complex64", "float32"])
+@pytest.mark.parametrize("integer", [False, True], ids=["random", "integer_exact"])
+@pytest.mark.parametrize("case", TC_GATHER_CASES, ids=[c[0] for c in TC_GATHER_CASES])
+def test_tcgen05_gather_pack_parity(case, integer, dt):
+    """Summed extents that do not tile groups of 8 k (K = 100, odd bond dimensions) take the table-driven gather pack (K
+    zero-padded to a multiple of 8) and the same tcgen05 GEMM: <= 1e-5 against the oracle, bit-exact on integer inputs."""
+    wide = np.complex128 if dt == "complex64" else np.float64
+    a, ia, b, ib, ic = build_case(case, dt, seed=37, integer=integer)
+    ref = binary_einsum_general(ic, a.astype(wide), ia, b.astype(wide), ib).astype(dt)
+    h = _lib.Handle.get()
+    h.reset_stats()
+    got = contract(a, ia, b, ib, ic, device=True, path=mb.PATH_TCGEN05_TF32)
+    s = h.stats()
+    if case[0] == "mixed_order":
+        assert s["launches_tcgen05"] == 0 and s["launches_simt_f32"] == 1, s
+    else:
+        assert s["launches_tcgen05"] == 1 and s["launches_permute"] == 2, s
+    if integer:
+        assert np.array_equal(got, ref), case[0]
+    else:
+        assert rel_frobenius(got, ref) <= 1e-5, (case[0], rel_frobenius(got, ref))
+
+
+@pytest.mark.parametrize("dt", ["complex64", "float32"])
+def test_tcgen05_strided_operands(dt):
+    """Strided (non-dense) operands through the C ABI on the tcgen05 path: a slab of a larger array as the row operand
+    (free-index shard) and every other row of a wider buffer as the column operand, strides passed explicitly."""
+    rng = np.random.default_rng(41)
+    a_full = random_array(rng, (192, 160, 6), dt)          # [i, k, s]; use i in 32:160, s in 2:5
+    b_full = random_array(rng, (320, 96), dt)              # [2k, j]; use rows 0::2
+    dA, dB = B200Array.from_host(a_full), B200Array.from_host(b_full)
+    dC = B200Array((128, 96, 3), dt)
+    h = _lib.Handle.get()
+    h.set_path(mb.PATH_TCGEN05_TF32)
+    h.reset_stats()
+    esz = np.dtype(dt).itemsize
+    en = _lib.dtype_enum(dt)
+    try:
+        _lib.check(mb.lib().mb200_binary_einsum(
+            h.ptr, C.c_void_p(dC.ptr), en, 3, _lib.i32([0, 2, 3]), None,
+            C.c_void_p(dA.ptr + (2 * 192 * 160 + 32) * esz), en, 3, _lib.i32([0, 1, 3]), _lib.i64([128, 160, 3]), _lib.i64([1, 192, 192 * 160]),
+            C.c_void_p(dB.ptr), en, 2, _lib.i32([1, 2]), _lib.i64([160, 96]), _lib.i64([2, 320])))
+    finally:
+        h.set_path(mb.PATH_AUTO)
+    assert h.stats()["launches_tcgen05"] == 1, h.stats()
+    wide = np.complex128 if dt == "complex64" else np.float64
+    ref = np.einsum("iks,kj->ijs", a_full[32:160, :, 2:5].astype(wide), b_full[0::2].astype(wide))
+    assert rel_frobenius(dC.to_host().astype(wide), ref) <= 1e-5
 
 
 # ---- fused contraction + reduce-scatter epilogue (single GPU: the "peers" are local buffers) -----------------
