@@ -54,7 +54,7 @@ typedef enum {
     MB200_PATH_DIRECT = 1,   /* K5: single-kernel direct contraction (launch-bound / skinny sizes) */
     MB200_PATH_GETT_F64 = 2, /* K2: FP64 DMMA (mma.sync m8n8k4 f64) gather-GEMM, C128 4M / F64    */
     MB200_PATH_SIMT_F32 = 3, /* FP32 FFMA gather-GEMM (C64 / F32; shapes the tcgen05 path rejects) */
-    MB200_PATH_TCGEN05_TF32 = 4 /* K3: tcgen05/TMEM 3xTF32 GEMM on TMA-fed planar operands         */
+    MB200_PATH_TCGEN05_TF32 = 4 /* K3: tcgen05/TMEM split-operand (TF32 + BF16) GEMM on TMA-fed operands */
 } mb200_path_t;
 
 typedef struct mb200_handle_s *mb200_handle_t;

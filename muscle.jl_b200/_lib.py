@@ -29,7 +29,7 @@ OK, INVALID_ARGUMENT, NOT_SUPPORTED, DIMENSION_MISMATCH, CUDA_ERROR, OUT_OF_MEMO
 # kernel families (mb200_path_t)
 PATH_AUTO, PATH_DIRECT, PATH_GETT_F64, PATH_SIMT_F32, PATH_TCGEN05_TF32 = range(5)
 PATH_NAMES = {PATH_AUTO: "auto", PATH_DIRECT: "direct", PATH_GETT_F64: "gett_f64_dmma",
-              PATH_SIMT_F32: "simt_f32", PATH_TCGEN05_TF32: "tcgen05_tf32x3"}
+              PATH_SIMT_F32: "simt_f32", PATH_TCGEN05_TF32: "tcgen05_split"}
 
 SHARD_NONE, SHARD_FREE, SHARD_BATCH, SHARD_SUM = range(4)
 

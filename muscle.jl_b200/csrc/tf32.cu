@@ -32,17 +32,16 @@
 // tmem_full/tmem_empty over two TMEM chunk buffers (MMA <-> epilogue). Persistent: one CTA per SM walks the
 // 128 x BN output tiles.
 //
-// Measured limits (ncu, config 3): the SM clock sits at ~1.57 GHz under this kernel (power), tensor sub-pipes 81 %
-// active; at N = 128 a K=8 tf32 MMA reads 8 KB of smem operands per 64 tensor cycles = all 128 B/clk of shared
-// memory (forcing BN = 64 makes the GEMM 1.77x slower). A variant issuing six N = 256 MMAs over concatenated
-// [re;im] column-operand planes (25 % fewer smem bytes) was built and verified: GEMM 2.21 -> 2.13 ms but the pack
-// and DRAM traffic grow by the same amount, so it was not kept.
-// Stream-K (balanced (tile, 128-k chunk) unit ranges per CTA, tiles cut between two CTAs finished through a
-// flag-ordered workspace hand-over) was also built and verified bit-exact: for 256 tiles on 148 SMs (one 2048^3
-// batch of config 3) it gained 2.6 % instead of the 13 % the wave arithmetic promises, and contiguous unit ranges
-// lost up to 18 % elsewhere (CTAs walk distant tiles concurrently, the packed panels stop hitting in L2). The kernel
-// is POWER-bound (1.57 GHz of 1.965): SMs idle in a ragged last wave let the busy ones clock higher, so balancing
-// the waves buys almost nothing. Not kept.
+// Measured limits (config 3): the path runs at the 1000 W board power cap (tools/power_probe.py: 982 W, sw_power_cap,
+// SM clock 1.67-1.70 GHz), so sustained throughput is set by energy per flop. ncu on the 1-CTA kernel: tensor sub-pipes 61.6 %
+// active, shared-memory data pipe 89 % busy (MMA operand reads 59.6 % + TMA fill 29.8 %: at N = 128 a K=8 tf32 MMA reads 8 KB of
+// operands per 64 tensor cycles = all 128 B/clk of shared memory; forcing BN = 64 makes the GEMM 1.77x slower) -> CTA pairs.
+// Tried and not kept: six N = 256 MMAs over concatenated [re;im] column-operand planes (25 % fewer smem bytes, GEMM 2.21 -> 2.13 ms
+// but the pack and DRAM traffic grow by the same amount); same-kind grouping of the mixed scheme's MMAs (slower than interleaved);
+// stream-K (balanced (tile, 128-k chunk) unit ranges per CTA, tiles cut between two CTAs finished through a flag-ordered workspace
+// hand-over; verified bit-exact): for 256 tiles on 148 SMs (one 2048^3 batch of config 3) it gained 2.6 % instead of the 13 % the
+// wave arithmetic promises, and contiguous unit ranges lost up to 18 % elsewhere (CTAs walk distant tiles concurrently, the packed
+// panels stop hitting in L2) - under a power cap SMs idle in a ragged last wave let the busy ones clock higher.
 #include <cuda.h>
 #include <cuda_runtime.h>
 

@@ -25,6 +25,9 @@ METRICS = [
     "launch__registers_per_thread", "launch__shared_mem_per_block_allocated", "launch__waves_per_multiprocessor",
     "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum",
+    "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum.pct_of_peak_sustained_elapsed",
     "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
