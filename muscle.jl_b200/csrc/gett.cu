@@ -270,7 +270,7 @@ constexpr int GROUP_M = 8;
 // coalesced) and splitk_reduce_kernel adds the slices in order and scatters to C through the tables (deterministic).
 template <class Core>
 __global__ void __launch_bounds__(Core::NTHREADS, Core::NTHREADS <= 128 ? 4 : 1) gett_kernel(const __grid_constant__ GettParams p,
-                                                                                            typename Core::Elem *ws) {
+                                                                                            typename Core::Elem *ws, int64_t tile0) {
     using E = typename Core::Elem;
     constexpr int BM = Core::BM, BN = Core::BN, BK = Core::BK, S = Core::STAGES;
     constexpr int LDA = Core::LDA, LDB = Core::LDB, NT = Core::NTHREADS;
@@ -286,8 +286,9 @@ __global__ void __launch_bounds__(Core::NTHREADS, Core::NTHREADS <= 128 ? 4 : 1)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
     const int64_t tiles = tiles_m * tiles_n;
-    const int64_t l = blockIdx.x / tiles;
-    const int64_t t = blockIdx.x % tiles;
+    const int64_t bid = tile0 + blockIdx.x;   // tile0 > 0: the split tail launch of a ragged last wave
+    const int64_t l = bid / tiles;
+    const int64_t t = bid % tiles;
     // grouped rasterisation
     const int64_t per_group = GROUP_M * tiles_n;
     const int64_t g = t / per_group;
@@ -429,7 +430,7 @@ template <> __device__ __forceinline__ double2 add_e(double2 a, double2 b) { ret
 // C[rowC[m] + colC[n] + batC[l]] = sum over slices of ws[(s * ntiles + tile) * BM * BN + c * BM + r]
 template <typename E, int BM, int BN>
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const __grid_constant__ GettParams p, const E *__restrict__ ws, int nsplit,
-                                                            int64_t ntiles) {
+                                                            int64_t ntiles, int64_t tile0) {
     // one thread per output element (tile-linear index: consecutive threads read consecutive workspace elements and,
     // rows being C's fastest mode, write consecutive C elements); slices added in order, four loads in flight
     const int64_t tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
@@ -439,7 +440,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const __grid_constan
         const int64_t tile = idx / (BM * BN);
         const int e = (int)(idx - tile * (BM * BN));
         const int r = e % BM, c = e / BM;
-        const int64_t l = tile / tiles, t = tile % tiles;
+        const int64_t l = (tile0 + tile) / tiles, t = (tile0 + tile) % tiles;
         const int64_t per_group = GROUP_M * tiles_n, g = t / per_group, gm0 = g * GROUP_M;
         const int64_t gsz = (tiles_m - gm0) < GROUP_M ? (tiles_m - gm0) : GROUP_M;
         const int64_t m0 = (gm0 + (t % per_group) % gsz) * BM, n0 = ((t % per_group) / gsz) * BN;
@@ -582,13 +583,28 @@ cudaError_t launch(const GettParams &p, cudaStream_t s) {
         E *ws = nullptr;
         cudaError_t e = cudaMallocAsync((void **)&ws, (size_t)nsplit * grid * Core::BM * Core::BN * sizeof(E), s);
         if (e != cudaSuccess) return e;
-        gett_kernel<Core><<<dim3((unsigned)grid, (unsigned)nsplit), Core::NTHREADS, gett_smem_bytes<Core>(), s>>>(p, ws);
-        splitk_reduce_kernel<E, Core::BM, Core::BN><<<(unsigned)std::min<int64_t>((grid * Core::BM * Core::BN + 255) / 256, 148 * 16), 256, 0, s>>>(p, ws, (int)nsplit, grid);
+        gett_kernel<Core><<<dim3((unsigned)grid, (unsigned)nsplit), Core::NTHREADS, gett_smem_bytes<Core>(), s>>>(p, ws, 0);
+        splitk_reduce_kernel<E, Core::BM, Core::BN><<<(unsigned)std::min<int64_t>((grid * Core::BM * Core::BN + 255) / 256, 148 * 16), 256, 0, s>>>(p, ws, (int)nsplit, grid, 0);
         e = cudaGetLastError();
         cudaFreeAsync(ws, s);
         return e;
     }
-    gett_kernel<Core><<<(unsigned)grid, Core::NTHREADS, gett_smem_bytes<Core>(), s>>>(p, nullptr);
+    // Ragged last wave: the tiles beyond the last full wave (at most half a wave of them) run as a second launch with their
+    // k-range split so that they fill the SMs once more for 1 / nsplit of a tile time (512 tiles on 148 SMs: 4 -> 3.5 tile times).
+    const int64_t tail = grid % slots, full = grid - tail;
+    if (sk_mode == 1 && p.sc.nranks == 0 && full > 0 && tail > 0 && tail * 2 <= slots && KB >= 8) {   // MB200_SPLITK=2: A/B without it
+        const int64_t tsplit = std::min<int64_t>(KB / 2, slots / tail);
+        E *ws = nullptr;
+        cudaError_t e = cudaMallocAsync((void **)&ws, (size_t)tsplit * tail * Core::BM * Core::BN * sizeof(E), s);
+        if (e != cudaSuccess) return e;
+        gett_kernel<Core><<<(unsigned)full, Core::NTHREADS, gett_smem_bytes<Core>(), s>>>(p, nullptr, 0);
+        gett_kernel<Core><<<dim3((unsigned)tail, (unsigned)tsplit), Core::NTHREADS, gett_smem_bytes<Core>(), s>>>(p, ws, full);
+        splitk_reduce_kernel<E, Core::BM, Core::BN><<<(unsigned)std::min<int64_t>((tail * Core::BM * Core::BN + 255) / 256, 148 * 16), 256, 0, s>>>(p, ws, (int)tsplit, tail, full);
+        e = cudaGetLastError();
+        cudaFreeAsync(ws, s);
+        return e;
+    }
+    gett_kernel<Core><<<(unsigned)grid, Core::NTHREADS, gett_smem_bytes<Core>(), s>>>(p, nullptr, 0);
     return cudaGetLastError();
 }
 template <class Core>

@@ -555,7 +555,15 @@ cudaError_t launch_bn(const void *packA, const void *packB, const GettParams &g,
             attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr;
             cfg.numAttrs = 1;
-            return cudaLaunchKernelEx(&cfg, tf32_gemm_kernel<BN, REAL, true>, mapA, mapB, p);
+            const cudaError_t le = cudaLaunchKernelEx(&cfg, tf32_gemm_kernel<BN, REAL, true>, mapA, mapB, p);
+            if (le == cudaSuccess) return le;
+            // a device that cannot place the cluster (partitioned GPU, shared-memory carve-out): clear the launch-configuration
+            // error and run the single-CTA kernel below
+            if (le != cudaErrorInvalidConfiguration && le != cudaErrorLaunchOutOfResources && le != cudaErrorInvalidValue &&
+                le != cudaErrorNotSupported)
+                return le;
+            (void)cudaGetLastError();
+            if (pair) *pair = false;
         }
     }
     if (!make_map(&mapA, packA, g.K, W, g.M, g.L, TBM) || !make_map(&mapB, packB, g.K, W, g.N, g.L, BN))

@@ -586,12 +586,16 @@ def test_tcgen05_strided_operands(dt):
 
 
 # ---- fused contraction + reduce-scatter epilogue (single GPU: the "peers" are local buffers) -----------------
-@pytest.mark.parametrize("dt,path,tol", [("complex128", "gett", 1e-12), ("complex64", "tcgen05", 1e-5)])
-def test_fused_scatter_epilogue_and_slot_reduce(dt, path, tol):
+@pytest.mark.parametrize("dt,path,tol,dims", [("complex128", "gett", 1e-12, (256, 128, 1024)), ("complex64", "tcgen05", 1e-5, (256, 128, 1024)),
+                                              ("complex64", "tcgen05_pair", 1e-5, (4096, 2048, 1024))])
+def test_fused_scatter_epilogue_and_slot_reduce(dt, path, tol, dims):
     """mb200_binary_einsum_scatter + mb200_reduce_slots with 4 emulated ranks on one GPU: every rank contracts its
     K-slice, the epilogue routes each element to the owner's staging slot, the owners sum their slots. The union
-    of the slabs must equal the unsliced contraction (what all_reduce(SUM) of the partials would give)."""
-    nranks, Mx, Nx, Kx = 4, 256, 128, 1024
+    of the slabs must equal the unsliced contraction (what all_reduce(SUM) of the partials would give). The third case is
+    large enough for the CTA-pair tcgen05 kernel (both CTAs of a pair scatter their half of the 256-row tile)."""
+    nranks, (Mx, Nx, Kx) = 4, dims
+    pair = path == "tcgen05_pair"
+    path = "tcgen05" if pair else path
     rng = np.random.default_rng(17)
     a = random_array(rng, (Kx, Mx), dt)          # [k, i]
     b = random_array(rng, (Kx, Nx), dt)          # [k, j]
@@ -618,6 +622,7 @@ def test_fused_scatter_epilogue_and_slot_reduce(dt, path, tol):
             arr, nranks, r, slab.bit_length() - 1))
     st = h.stats()
     assert (st["launches_tcgen05"] if path == "tcgen05" else st["launches_gett_f64"]) == nranks, st
+    assert st["launches_tcgen05_pair"] == (nranks if pair else 0), st
     out = np.empty(numel, dtype=dt)
     for o in range(nranks):
         d = B200Array((slab,), dt)
