@@ -62,16 +62,21 @@ __device__ __forceinline__ void digits_off(unsigned idx, int n, const unsigned *
 }
 
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
-// round-to-nearest tf32 (x - tf32_rn(x) is exact in fp32 and half the size of the truncation remainder)
+// round-to-nearest tf32 (x - tf32_rn(x) is exact in fp32 and half the size of the truncation remainder); a finite x within
+// 2^-12 of FLT_MAX would round up to infinity: truncate those
 __device__ __forceinline__ float tf32_rn(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    if ((r & 0x7F800000u) == 0x7F800000u) r = __float_as_uint(x) & 0xFFFFE000u;   // inf / nan stay what they were
     return __uint_as_float(r);
 }
-// one 32-bit word holding two bf16 values: `lo` in bits [0,16) (the even k position of a K-major bf16 operand), `hi` in [16,32)
+// one 32-bit word holding two bf16 values: `lo` in bits [0,16) (the even k position of a K-major bf16 operand), `hi` in [16,32).
+// Round to nearest, except that a finite value may not round up to infinity (inf * 0 in the cross terms would poison the sum).
 __device__ __forceinline__ float bf16_pair(float lo, float hi) {
     uint32_t r;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    if ((r & 0x7F800000u) == 0x7F800000u || (r & 0x00007F80u) == 0x00007F80u)
+        asm("cvt.rz.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));      // rz keeps inf / nan inputs as they are
     return __uint_as_float(r);
 }
 // The "x" chunk of the mixed TF32 + BF16 operand format (tf32.cu): for the row operand (side 1) the pair (bf16(x), bf16(x_lo)),

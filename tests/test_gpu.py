@@ -417,6 +417,27 @@ def test_tcgen05_accuracy_beats_plain_tf32():
     assert errr <= 5e-6, errr
 
 
+@pytest.mark.parametrize("dt", ["complex64", "float32"])
+def test_tcgen05_extreme_magnitudes(dt):
+    """Operand values up to FLT_MAX (where rounding the hi / bf16 parts to nearest would overflow to infinity) against
+    tiny ones, and a wide dynamic range inside one row: finite results within 1e-5 of the fp64 product."""
+    rng = np.random.default_rng(23)
+    K, M, N = 256, 128, 64
+    a = random_array(rng, (K, M), dt)
+    b = random_array(rng, (K, N), dt)
+    scale_a = np.float32(2.0) ** rng.integers(100, 127, size=(K, 1)).astype(np.float32)    # up to ~1.7e38
+    a = (a * scale_a).astype(dt)
+    flat = a.reshape(-1).view(np.float32)
+    flat[::97] = np.finfo(np.float32).max                                                 # FLT_MAX itself, both signs
+    flat[5::193] = -np.finfo(np.float32).max
+    b = (b * np.float32(2.0) ** -100).astype(dt)                                           # tiny partner: products stay finite
+    wide = np.complex128 if dt == "complex64" else np.float64
+    ref = a.astype(wide).T @ b.astype(wide)
+    got = contract(np.asfortranarray(a), "ki", np.asfortranarray(b), "kj", "ij", path=mb.PATH_TCGEN05_TF32)
+    assert np.isfinite(got).all()
+    assert rel_frobenius(got.astype(wide), ref) <= 1e-5, rel_frobenius(got.astype(wide), ref)
+
+
 @pytest.mark.parametrize("dt,m,n,k", [("complex64", 2048, 2048, 520), ("complex64", 1920, 2304, 264), ("float32", 2304, 2560, 392),
                                       ("float32", 4096, 4096, 128 * 3), ("complex64", 1300, 2000, 1032)])
 def test_tcgen05_ragged_waves(dt, m, n, k):
