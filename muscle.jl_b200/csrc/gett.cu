@@ -261,6 +261,11 @@ constexpr size_t gett_smem_bytes() {
            (size_t)(Core::BM + Core::BN) * 2 * sizeof(int64_t) + (size_t)4 * Core::BK * sizeof(int64_t);
 }
 
+template <class Core>
+constexpr size_t gett_persistent_smem_bytes() {   // two sets of offset tables
+    return gett_smem_bytes<Core>() + (size_t)(Core::BM + Core::BN) * 2 * sizeof(int64_t);
+}
+
 // Tile order: groups of GROUP_M row tiles, walked column by column inside a group, so the CTAs of a
 // wave share a few A row-panels (kept in the 126 MB L2) while B column-panels stream through.
 constexpr int GROUP_M = 8;
@@ -419,6 +424,161 @@ __global__ void __launch_bounds__(Core::NTHREADS, Core::NTHREADS <= 128 ? 4 : 1)
     } else {
         Core::store(acc, reinterpret_cast<E *>(p.C), sRowC, sColC, cb, mrem, nrem, warp, lane, p.sc);
     }
+}
+
+// Persistent form of gett_kernel for contractions with several tiles per SM: CTA b walks tiles b, b + gridDim.x, ... and the
+// (tile, k-block) pairs form ONE software pipeline — during the last k-block of a tile the gather units already fetch the first
+// k-block of the next tile (their row pointers are rebuilt from the next tile's offset tables, which arrived by cp.async many
+// k-blocks earlier), and the epilogue stores of a tile run while that gather is in flight. What a tile no longer pays: the CTA
+// launch, the table loads, the exposed first gather (98 KB per CTA) and the drain before the stores. Pays off for short sums
+// (K <= 512: 8192 x 8192 x 256 30.6 -> 32.1 TFLOP/s); for K >= 1024 the plain kernel is ~1 % faster and stays in use.
+// No split-K, no scatter epilogue.
+template <class Core>
+__global__ void __launch_bounds__(Core::NTHREADS, 1) gett_persistent_kernel(const __grid_constant__ GettParams p, int64_t ntiles_run) {
+    using E = typename Core::Elem;
+    constexpr int BM = Core::BM, BN = Core::BN, BK = Core::BK, S = Core::STAGES;
+    constexpr int LDA = Core::LDA, LDB = Core::LDB, NT = Core::NTHREADS;
+    static_assert(S == 2, "the cross-tile pipeline below assumes a prefetch distance of one k-block");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    E *sA = reinterpret_cast<E *>(smem_raw);
+    E *sB = sA + (size_t)S * BK * LDA;
+    int64_t *sTab = reinterpret_cast<int64_t *>(sB + (size_t)S * BK * LDB);   // [2][rowA BM | colB BN | rowC BM | colC BN]
+    constexpr int TABN = 2 * (BM + BN);
+    int64_t *sK = sTab + 2 * TABN;                                            // [2][2][BK]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+    const int64_t tiles = tiles_m * tiles_n;
+    const int64_t KB = (p.K + BK - 1) / BK;
+
+    struct Tile { int64_t m0, n0, l; int mrem, nrem; };
+    auto tile_of = [&](int64_t bid) {
+        Tile t;
+        t.l = bid / tiles;
+        const int64_t r = bid % tiles;
+        const int64_t per_group = GROUP_M * tiles_n, g = r / per_group, gm0 = g * GROUP_M;
+        const int64_t gsz = (tiles_m - gm0) < GROUP_M ? (tiles_m - gm0) : GROUP_M;
+        t.m0 = (gm0 + (r % per_group) % gsz) * BM;
+        t.n0 = ((r % per_group) / gsz) * BN;
+        t.mrem = (int)((p.M - t.m0) < BM ? (p.M - t.m0) : BM);
+        t.nrem = (int)((p.N - t.n0) < BN ? (p.N - t.n0) : BN);
+        return t;
+    };
+    // offset tables of a tile -> smem set `buf`, by 8-byte cp.async (rows / columns past the edge read entry 0: never used)
+    auto issue_tables = [&](const Tile &t, int buf) {
+        int64_t *d = sTab + buf * TABN;
+        for (int i = tid; i < BM; i += NT) {
+            const int64_t m = t.m0 + (i < t.mrem ? i : 0);
+            cp_async<8>(d + i, p.rowA + m);
+            cp_async<8>(d + BM + BN + i, p.rowC + m);
+        }
+        for (int i = tid; i < BN; i += NT) {
+            const int64_t n = t.n0 + (i < t.nrem ? i : 0);
+            cp_async<8>(d + BM + i, p.colB + n);
+            cp_async<8>(d + 2 * BM + BN + i, p.colC + n);
+        }
+    };
+
+    constexpr int UA = (BM * BK + NT - 1) / NT, UB = (BN * BK + NT - 1) / NT, UNITS = UA + UB;
+    static_assert((BM * BK) % NT == 0 && (BN * BK) % NT == 0, "full tiles of units only");
+    const char *u_ptr[UNITS];   // global row base (bytes) of the tile being GATHERED; nullptr = row outside the tile / no tile
+    int u_dst[UNITS], u_k[UNITS];
+    constexpr int STAGE_A = BK * LDA * (int)sizeof(E), STAGE_B = BK * LDB * (int)sizeof(E);
+#pragma unroll
+    for (int u = 0; u < UNITS; u++) {   // the (row, k) slot of a unit never changes
+        const int i = tid + (u < UA ? u : u - UA) * NT;
+        int r, k;
+        if (u < UA) { if (p.a_kmajor) { k = i % BK; r = i / BK; } else { r = i % BM; k = i / BM; } u_dst[u] = (k * LDA + r) * (int)sizeof(E); u_k[u] = k; }
+        else { if (p.b_kmajor) { k = i % BK; r = i / BK; } else { r = i % BN; k = i / BN; } u_dst[u] = (k * LDB + r) * (int)sizeof(E); u_k[u] = BK + k; }
+    }
+    auto build_units = [&](const Tile &t, int buf, bool exists) {
+        const int64_t *d = sTab + buf * TABN;
+        const E *gA = reinterpret_cast<const E *>(p.A) + (exists ? p.batA[t.l] : 0);
+        const E *gB = reinterpret_cast<const E *>(p.B) + (exists ? p.batB[t.l] : 0);
+#pragma unroll
+        for (int u = 0; u < UNITS; u++) {
+            const int i = tid + (u < UA ? u : u - UA) * NT;
+            if (u < UA) {
+                const int m = p.a_kmajor ? i / BK : i % BM;
+                u_ptr[u] = (exists && m < t.mrem) ? reinterpret_cast<const char *>(gA + d[m]) : nullptr;
+            } else {
+                const int n = p.b_kmajor ? i / BK : i % BN;
+                u_ptr[u] = (exists && n < t.nrem) ? reinterpret_cast<const char *>(gB + d[BM + n]) : nullptr;
+            }
+        }
+    };
+    const unsigned sA_u32 = (unsigned)__cvta_generic_to_shared(sA), sB_u32 = (unsigned)__cvta_generic_to_shared(sB);
+    auto issue_unit = [&](int stage, int u, const int64_t *koff) {
+        const int64_t ko = koff[u_k[u]];
+        const bool v = u_ptr[u] != nullptr && ko >= 0;
+        const char *src = v ? u_ptr[u] + ko : reinterpret_cast<const char *>(p.A);
+        const unsigned dst = (u < UA ? sA_u32 + stage * STAGE_A : sB_u32 + stage * STAGE_B) + u_dst[u];
+        const int bytes = v ? (int)sizeof(E) : 0;
+        static_assert(sizeof(E) == 16, "ComplexF64 tiles");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes));
+    };
+    // byte offsets of k-block `kblock` (of any tile: they depend on k only) -> sK slot
+    auto stage_koff = [&](int64_t kblock, int slot) {
+        if (tid < 2 * BK) {
+            const int64_t kg = kblock * BK + tid % BK;
+            int64_t v = -1;
+            if (kg < p.K) v = ((tid < BK) ? p.kA[kg] : p.kB[kg]) * (int64_t)sizeof(E);
+            sK[slot * 2 * BK + tid] = v;
+        }
+    };
+
+    int64_t bid = blockIdx.x;
+    if (bid >= ntiles_run) return;
+    Tile cur = tile_of(bid);
+    issue_tables(cur, 0);
+    cp_async_commit();
+    stage_koff(0, 0);
+    cp_async_wait<0>();
+    __syncthreads();
+    build_units(cur, 0, true);
+#pragma unroll
+    for (int u = 0; u < UNITS; u++) issue_unit(0, u, sK);
+    cp_async_commit();
+    __syncthreads();
+    stage_koff(1 % KB, 1);   // offsets of global block 1 (gathered during block 0)
+
+    typename Core::Acc acc;
+    Core::init(acc);
+    int buf = 0;
+    int64_t g = 0;   // global k-block counter of this CTA: stage g & 1 is computed, stage (g + 1) & 1 is gathered
+    for (;;) {
+        const int64_t nbid = bid + gridDim.x;
+        const bool has_next = nbid < ntiles_run;
+        const Tile nxt = has_next ? tile_of(nbid) : cur;
+        for (int64_t kb = 0; kb < KB; kb++, g++) {
+            cp_async_wait<0>();
+            __syncthreads();     // block g landed; sK[(g + 1) & 1] (written one iteration ago) visible; previous epilogue finished
+            if (kb == 0 && has_next) issue_tables(nxt, buf ^ 1);                  // lands long before the last block of this tile
+            if (kb == KB - 1) build_units(nxt, buf ^ 1, has_next);                // from here on the gather belongs to the next tile
+            const int64_t *koff = sK + ((g + 1) & 1) * 2 * BK;
+            stage_koff((kb + 2) % KB, (int)(g & 1));                              // block g + 2, for the next iteration's gather
+            const int st = (int)(g & 1), nstage = st ^ 1;
+            Core::compute(acc, sA + (size_t)st * BK * LDA, sB + (size_t)st * BK * LDB, warp, lane, [&](int slot) {
+                constexpr int SLOTS = Core::SLOTS;
+                constexpr int PER = (UNITS + SLOTS - 1) / SLOTS;
+#pragma unroll
+                for (int q = 0; q < PER; q++) {
+                    const int u = slot * PER + q;
+                    if (u < UNITS) issue_unit(nstage, u, koff);
+                }
+                if (slot == SLOTS - 1) cp_async_commit();
+            });
+        }
+        // epilogue of this tile; the first k-block of the next one is in flight
+        const int64_t *d = sTab + buf * TABN;
+        Core::store(acc, reinterpret_cast<E *>(p.C), d + BM + BN, d + 2 * BM + BN, p.batC[cur.l], cur.mrem, cur.nrem, warp, lane, p.sc);
+        if (!has_next) break;
+        Core::init(acc);
+        cur = nxt;
+        bid = nbid;
+        buf ^= 1;
+    }
+    cp_async_wait<0>();
 }
 
 template <typename E> __device__ __forceinline__ E add_e(E a, E b);
@@ -592,23 +752,42 @@ cudaError_t launch(const GettParams &p, cudaStream_t s) {
     // Ragged last wave: the tiles beyond the last full wave (at most half a wave of them) run as a second launch with their
     // k-range split so that they fill the SMs once more for 1 / nsplit of a tile time (512 tiles on 148 SMs: 4 -> 3.5 tile times).
     const int64_t tail = grid % slots, full = grid - tail;
-    if (sk_mode == 1 && p.sc.nranks == 0 && full > 0 && tail > 0 && tail * 2 <= slots && KB >= 8) {   // MB200_SPLITK=2: A/B without it
+    const bool split_tail = sk_mode == 1 && p.sc.nranks == 0 && full > 0 && tail > 0 && tail * 2 <= slots && KB >= 8;   // MB200_SPLITK=2: A/B without it
+    const int64_t run = split_tail ? full : grid;   // tiles of the main launch
+    // main launch: persistent (cross-tile pipeline) for the ComplexF64 main tile when every SM gets several tiles
+    static const int persist_mode = [] { const char *e = getenv("MB200_PERSIST"); return e ? atoi(e) : 1; }();
+    bool launched = false;
+    if constexpr (Core::STAGES == 2 && sizeof(E) == 16 && (Core::BM * Core::BK) % Core::NTHREADS == 0 &&
+                  (Core::BN * Core::BK) % Core::NTHREADS == 0 && (Core::NTHREADS > 128)) {
+        // measured (tools/ab_tail.py): 8192 x 8192 x 256 30.6 -> 32.1 TFLOP/s, but K >= 1024 loses ~1 % (the extra control flow in the
+        // k loop costs more than the hidden prologue / epilogue gains once a tile runs for 32+ k-blocks) -> short-K shapes only
+        if (persist_mode && p.sc.nranks == 0 && KB >= 4 && (KB <= 16 || persist_mode == 2) && run >= 2 * 148) {
+            gett_persistent_kernel<Core><<<148, Core::NTHREADS, gett_persistent_smem_bytes<Core>(), s>>>(p, run);
+            launched = true;
+        }
+    }
+    if (!launched) gett_kernel<Core><<<(unsigned)run, Core::NTHREADS, gett_smem_bytes<Core>(), s>>>(p, nullptr, 0);
+    if (split_tail) {
         const int64_t tsplit = std::min<int64_t>(KB / 2, slots / tail);
         E *ws = nullptr;
         cudaError_t e = cudaMallocAsync((void **)&ws, (size_t)tsplit * tail * Core::BM * Core::BN * sizeof(E), s);
         if (e != cudaSuccess) return e;
-        gett_kernel<Core><<<(unsigned)full, Core::NTHREADS, gett_smem_bytes<Core>(), s>>>(p, nullptr, 0);
         gett_kernel<Core><<<dim3((unsigned)tail, (unsigned)tsplit), Core::NTHREADS, gett_smem_bytes<Core>(), s>>>(p, ws, full);
         splitk_reduce_kernel<E, Core::BM, Core::BN><<<(unsigned)std::min<int64_t>((tail * Core::BM * Core::BN + 255) / 256, 148 * 16), 256, 0, s>>>(p, ws, (int)tsplit, tail, full);
         e = cudaGetLastError();
         cudaFreeAsync(ws, s);
         return e;
     }
-    gett_kernel<Core><<<(unsigned)grid, Core::NTHREADS, gett_smem_bytes<Core>(), s>>>(p, nullptr, 0);
     return cudaGetLastError();
 }
 template <class Core>
 cudaError_t configure() {
+    if constexpr (Core::STAGES == 2 && sizeof(typename Core::Elem) == 16 && (Core::BM * Core::BK) % Core::NTHREADS == 0 &&
+                  (Core::BN * Core::BK) % Core::NTHREADS == 0 && (Core::NTHREADS > 128)) {
+        cudaError_t e = cudaFuncSetAttribute(gett_persistent_kernel<Core>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)gett_persistent_smem_bytes<Core>());
+        if (e != cudaSuccess) return e;
+    }
     return cudaFuncSetAttribute(gett_kernel<Core>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)gett_smem_bytes<Core>());
 }

@@ -479,6 +479,23 @@ def test_gather_gemm_split_k(m, n, k, l, dt):
     assert rel_frobenius(got.astype(wide), refr) <= (1e-12 if dt in ("complex128", "float64") else 1e-5)
 
 
+@pytest.mark.parametrize("m,n,k,l", [(2500, 1000, 160, 1), (1300, 700, 300, 3), (4096, 1200, 512, 1), (2500, 1000, 2048, 1)])
+def test_gather_gemm_persistent_and_split_tail(m, n, k, l):
+    """ComplexF64 shapes with several tiles per SM: short sums (K <= 512) take the persistent kernel (one software pipeline
+    across tiles: the next tile's first k-block is gathered during the current tile's last one), a ragged last wave runs as
+    a split tail launch (the K = 2048 case: 320 tiles = 296 + 24). Ragged M / N edges, batches; bit-exact on integer inputs."""
+    dt = "complex128"
+    rng = np.random.default_rng(10)
+    a = integer_array(rng, (k, m, l), dt, lo=-2, hi=3)
+    b = integer_array(rng, (n, l, k), dt, lo=-2, hi=3)
+    ref = np.einsum("kml,nlk->nml", a, b)
+    got = contract(a, "kml", b, "nlk", "nml", device=True, path=mb.PATH_GETT_F64)
+    assert np.array_equal(got, ref)
+    ar, br = random_array(rng, (k, m, l), dt), random_array(rng, (n, l, k), dt)
+    got = contract(ar, "kml", br, "nlk", "mnl", device=True, path=mb.PATH_GETT_F64)
+    assert rel_frobenius(got, np.einsum("kml,nlk->mnl", ar, br)) <= 1e-12
+
+
 @pytest.mark.parametrize("dt", ["complex64", "float32"])
 @pytest.mark.parametrize("m,n,k,l", [(256, 256, 4096, 1), (64, 64, 8192, 1), (130, 70, 1032, 1), (512, 512, 1024, 1), (96, 96, 520, 3)])
 def test_tcgen05_split_k(m, n, k, l, dt):
