@@ -7,7 +7,7 @@ Import it as `muscle_b200` (the repo-root shim maps the dotted directory name to
 """
 from ._lib import (ArgumentError, B200Error, DimensionMismatch, Handle, LIB_PATH, PATH_AUTO, PATH_DIRECT,
                    PATH_GETT_F64, PATH_NAMES, PATH_SIMT_F32, PATH_TCGEN05_TF32, lib, plan_describe, shard_plan)
-from .backend import (Backend, BackendB200, BackendBase, BackendOMEinsum, Domain, DomainB200, DomainHost, choose_backend,
+from .backend import (Backend, BackendB200, BackendBase, BackendBlocks, BackendOMEinsum, Domain, DomainB200, DomainBlocks, DomainHost, choose_backend,
                       choose_backend_rule, domain, with_backend)
 from .einsum import binary_einsum, binary_einsum_, binary_einsum_inplace, flatten_labels, frontend_inds_c
 from .factorize import (AbsorbEqually, AbsorbU, AbsorbV, DontAbsorb, factorinds, simple_update,
@@ -15,6 +15,7 @@ from .factorize import (AbsorbEqually, AbsorbU, AbsorbV, DontAbsorb, factorinds,
 from .family import hadamard, hadamard_, unary_einsum, unary_einsum_, unary_frontend_inds_y
 from .network import CapturedProgram, ContractionProgram, contract, find_path
 from .tensor import B200Array, Index, Tensor, findperm
+from .blocks import BlockArray, Blocks, blocked_binary_einsum, distribute
 from . import dist
 
 __all__ = [
@@ -27,4 +28,5 @@ __all__ = [
     "choose_backend_rule", "domain", "with_backend",
     "binary_einsum", "binary_einsum_", "binary_einsum_inplace", "flatten_labels", "frontend_inds_c",
     "B200Array", "Index", "Tensor", "findperm",
+    "BackendBlocks", "DomainBlocks", "BlockArray", "Blocks", "blocked_binary_einsum", "distribute",
 ]

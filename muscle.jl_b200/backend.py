@@ -35,6 +35,11 @@ class BackendOMEinsum(Backend):
     ext/MuscleOMEinsumExt.jl). Like BackendBase it lives in Muscle.jl, not here."""
 
 
+class BackendBlocks(Backend):
+    """Stand-in for `BackendDagger` (src/Backend.jl:6-14, ext/MuscleDaggerExt): blocked operands, one `binary_einsum` per
+    chunk pair (each re-enters the dispatch, so device chunks run on BackendB200) and an add-reduce over summed blocks."""
+
+
 class BackendB200(Backend):
     """The new backend: ccall/ctypes → libmuscle_b200.so (CUDA for sm_100a)."""
 
@@ -60,12 +65,18 @@ class DomainB200(Domain):
     pass
 
 
+class DomainBlocks(Domain):
+    """Stand-in for `DomainDagger` (src/Domain.jl:6-9): a `blocks.BlockArray`."""
+
+
 def domain(x) -> Domain:
     """`Domain(array)` (src/Domain.jl:11-14): numpy → host, B200Array → B200; Tensors are unwrapped."""
     if isinstance(x, Tensor):
         x = x.parent
     if isinstance(x, B200Array):
         return DomainB200()
+    if getattr(x, "_is_block_array", False):
+        return DomainBlocks()
     if isinstance(x, np.ndarray):
         return DomainHost()
     raise ArgumentError(f"no Domain for {type(x).__name__}")
@@ -116,6 +127,10 @@ register_rule("binary_einsum", (DomainHost, DomainHost), BackendBase())
 register_rule("binary_einsum", (DomainB200, DomainB200), BackendB200())
 register_rule("binary_einsum", (DomainB200, DomainHost), BackendB200())
 register_rule("binary_einsum", (DomainHost, DomainB200), BackendB200())
+# blocked operands, also mixed with a plain array (binary_einsum.jl:25-31: Dagger rules incl. mixed-with-Host)
+for _d in (DomainBlocks, DomainHost, DomainB200):
+    register_rule("binary_einsum", (DomainBlocks, _d), BackendBlocks())
+    register_rule("binary_einsum", (_d, DomainBlocks), BackendBlocks())
 register_rule("binary_einsum!", (DomainHost, DomainHost, DomainHost), BackendBase())
 register_rule("binary_einsum!", (DomainB200, DomainB200, DomainB200), BackendB200())
 

@@ -217,6 +217,17 @@ __global__ void __launch_bounds__(256) reduce_slots_kernel(T *__restrict__ out, 
     }
 }
 
+// the same on scalars, for slabs whose byte count is not a multiple of 32 (small blocks of the blocked-tensor bridge)
+template <typename T>
+__global__ void __launch_bounds__(256) reduce_slots_scalar_kernel(T *__restrict__ out, const T *__restrict__ in, int64_t n, int nslots) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        T acc = in[i];
+        for (int s = 1; s < nslots; s++) acc += in[(int64_t)s * n + i];
+        out[i] = acc;
+    }
+}
+
 // Cross-rank barrier of the fused reduce-scatter, without a collective: after its contraction every rank stores the
 // call's epoch into ITS entry of every rank's flag array (peer mappings, system scope); the owner's slot-sum kernel
 // spins until all nslots entries carry the epoch. The GEMM epilogue ended with __threadfence_system() and the kernel
@@ -331,7 +342,16 @@ cudaError_t launch_apply(int dtype, const ApplyParams &p, const void *X, const v
 cudaError_t launch_reduce_slots(int dtype, void *out, const void *staging, int64_t slab_elems, int nslots, cudaStream_t s) {
     const int64_t bytes = slab_elems * (int64_t)dtype_size(dtype);
     if (bytes <= 0) return cudaSuccess;
-    if (bytes % 32 != 0) return cudaErrorInvalidValue;
+    if (bytes % 32 != 0 || (((uintptr_t)out | (uintptr_t)staging) & 31)) {   // odd slab size / unaligned base: scalar form
+        if (dtype_is_double(dtype)) {
+            const int64_t n = bytes / 8;
+            reduce_slots_scalar_kernel<double><<<grid_for(n, 256), 256, 0, s>>>((double *)out, (const double *)staging, n, nslots);
+        } else {
+            const int64_t n = bytes / 4;
+            reduce_slots_scalar_kernel<float><<<grid_for(n, 256), 256, 0, s>>>((float *)out, (const float *)staging, n, nslots);
+        }
+        return cudaGetLastError();
+    }
     if (dtype_is_double(dtype)) {
         const int64_t n = bytes / 32;   // double4
         reduce_slots_kernel<double4><<<grid_for(n, 256), 256, 0, s>>>((double4 *)out, (const double4 *)staging, n, nslots);

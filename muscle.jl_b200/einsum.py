@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import ArgumentError
-from .backend import Backend, BackendB200, choose_backend
+from .backend import Backend, BackendB200, BackendBlocks, choose_backend
 from .tensor import B200Array, Index, Tensor, _as_index_list
 
 
@@ -156,6 +156,9 @@ def binary_einsum(*args, dims=None, out=None) -> Tensor:
         raise ArgumentError("binary_einsum(a, b; dims, out) or binary_einsum(backend, inds_c, a, b)")
     if isinstance(backend, BackendB200):
         return _b200_out_of_place(inds_c, a, b)
+    if isinstance(backend, BackendBlocks):
+        from .blocks import blocked_binary_einsum
+        return blocked_binary_einsum(inds_c, a, b)
     # binary_einsum.jl:53-55
     raise ArgumentError(f"`binary_einsum` not implemented or not loaded for backend {backend!r} "
                         "(this package provides BackendB200 only; use with_backend(f, BackendB200()) "

@@ -148,7 +148,7 @@ class Tensor:
     `data` is a numpy array (host; shape = Julia `size`) or a `B200Array`."""
 
     def __init__(self, data, inds=()):
-        if not isinstance(data, B200Array):
+        if not isinstance(data, B200Array) and not getattr(data, "_is_block_array", False):   # blocks.BlockArray: the DArray stand-in
             data = np.asarray(data)
         inds = _as_index_list(inds)
         if len(inds) != data.ndim:  # src/Tensor.jl:16-18

@@ -18,6 +18,7 @@ from .muscle_oracle import (  # noqa: F401
 )
 from .family_oracle import (  # noqa: F401
     contract_path_oracle,
+    dagger_stage_oracle,
     simple_update_theta,
     tensor_svd_thin_base,
     hadamard_base,

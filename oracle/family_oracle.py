@@ -152,3 +152,47 @@ def simple_update_theta(a, inds_a, b, inds_b, g, inds_g, ind_pa, ind_pb, ind_bon
     th, ith = binary_einsum(ab, iab, g, list(inds_g), dims=[ind_pa, ind_pb])
     ren = {ind_ga: ind_pa, ind_gb: ind_pb}
     return th, [ren.get(i, i) for i in ith]
+
+
+def dagger_stage_oracle(inds_c, a: np.ndarray, inds_a, blocks_a, b: np.ndarray, inds_b, blocks_b):
+    """Restatement of `Dagger.stage(::BinaryEinsum)` (ext/MuscleDaggerExt/binary_einsum.jl:64-119) on plain numpy blocks:
+    output block sizes from a, else b (:47-58); grid = size ÷ blocksize (:68-69); per output block the add-tree reduction
+    (`treereduce(AddComputeOp)`, :107-115) over the summed-index blocks of one chunk contraction each
+    (`task_binary_einsum`, :60-62). Returns (dense result, block sizes of the result, list of chunk shapes).
+    Pinned on the reference's own test (test/integration/dagger.jl:12-31: 2 x 2 Float64 in 1 x 1 blocks,
+    `collect(block_c) ≈ c`, every chunk of size (1, 1))."""
+    from .muscle_oracle import binary_einsum_general
+    ia, ib, ic = list(inds_a), list(inds_b), list(inds_c)
+    for ii in (ia, ib, ic):                                  # :19-21
+        if len(set(ii)) != len(ii):
+            raise ArgumentError("indices must be unique")
+    if not set(ic) <= set(ia) | set(ib):                     # :22
+        raise ArgumentError("ic must be a subset of ia ∪ ib")
+    bs = {}
+    for ii, blk, arr in ((ib, blocks_b, b), (ia, blocks_a, a)):   # a's block size wins for shared labels (:48-55)
+        for j, i in enumerate(ii):
+            if arr.shape[j] % blk[j]:
+                raise ArgumentError("extent is not a multiple of the block size")
+            bs[i] = blk[j]
+    size = {i: a.shape[j] for j, i in enumerate(ia)}
+    size.update({i: b.shape[j] for j, i in enumerate(ib) if i not in size})
+    suminds = [i for i in ia if i in ib and i not in ic]      # :82
+    out = np.zeros([size[i] for i in ic], dtype=np.result_type(a.dtype, b.dtype), order="F")
+    chunk_shapes = []
+    grid = [size[i] // bs[i] for i in ic]
+    for oidx in np.ndindex(*grid):
+        pos = dict(zip(ic, oidx))
+        parts = []
+        for sidx in np.ndindex(*[size[i] // bs[i] for i in suminds]):
+            pos.update(zip(suminds, sidx))
+            ca = a[tuple(slice(pos[i] * bs[i], (pos[i] + 1) * bs[i]) for i in ia)]
+            cb = b[tuple(slice(pos[i] * bs[i], (pos[i] + 1) * bs[i]) for i in ib)]
+            parts.append(binary_einsum_general(ic, _fortran(ca), ia, _fortran(cb), ib))
+        while len(parts) > 1:                                 # treereduce: pairwise add tree
+            nxt = [parts[k] + parts[k + 1] for k in range(0, len(parts) - 1, 2)]
+            if len(parts) % 2:
+                nxt.append(parts[-1])
+            parts = nxt
+        out[tuple(slice(o * bs[i], (o + 1) * bs[i]) for o, i in zip(oidx, ic))] = parts[0]
+        chunk_shapes.append(parts[0].shape)
+    return out, tuple(bs[i] for i in ic), chunk_shapes
