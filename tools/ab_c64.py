@@ -12,10 +12,3 @@ for name, ext, ia, ib, ic, dt in [("cfg3 PEPS c64", dict(l=256, k=8, b=8, m=256,
                                   ("cfg1 c128 scrambled", dict(i=64, j=64, k=64, l=64, m=64, n=64), "kilj", "nlmk", "mjni", "complex128")]:
     r = bk.einsum_case(name, ext, ia, ib, ic, dt, iters=8)
     print("EINSUM %-30s %8.2f TF/s best %8.2f mean %.3f ms" % (name, r["tflops_best"], r["tflops_mean"], r["ms_mean"]))
-# summed extents that do not tile groups of 8 k: table-driven gather pack (K zero-padded) + tcgen05, against the FFMA fallback
-for name, ext, ia, ib, ic, dt in [("c64 K=100 chi=2048", dict(i=2048, j=2048, k=100), "ki", "kj", "ij", "complex64"),
-                                  ("c64 D=6 PEPS-like", dict(l=216, k=6, b=6, m=216, q=6, r=216, z=6), "lkbmz", "mkqrz", "lbqrz", "complex64"),
-                                  ("c64 chi=100 d=3 mps", dict(a=100, s=3, b=100, t=3, c=100, w=100), "asbw", "btcw", "astc", "complex64"),
-                                  ("f32 K=1000", dict(i=4096, j=4096, k=1000), "ki", "kj", "ij", "float32")]:
-    r = bk.einsum_case(name, ext, ia, ib, ic, dt, iters=8)
-    print("EINSUM %-30s %8.2f TF/s best %8.2f mean %.3f ms" % (name, r["tflops_best"], r["tflops_mean"], r["ms_mean"]))

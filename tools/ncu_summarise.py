@@ -56,7 +56,8 @@ def main():
     for rep, title in (("prof_gett.ncu-rep", "gett kernels inside one bench step (2a, 2b, 2c)"),
                        ("prof_permute.ncu-rep", "K1 permute kernels (tools/bench_kernels.py, first cases)"),
                        ("prof_tf32.ncu-rep", "K3 tcgen05 3xTF32 kernels and their K1 split-writer packs (configs 3, 5; 8192^3 Float32)"),
-                       ("prof_family.ncu-rep", "hadamard / unary_einsum streaming kernels")):
+                       ("prof_family.ncu-rep", "hadamard / unary_einsum streaming kernels"),
+                       ("prof_extra.ncu-rep", "persistent gather-GEMM (8192 x 8192 x 256), split tail + ordered reduce (2048^3), tcgen05 on the last shape of tools/run_extra_once.py")):
         path = os.path.join(OUT, rep)
         if not os.path.exists(path):
             continue
