@@ -166,6 +166,15 @@ int build_cached(mb200_handle_t h, CachedPlan &cp) {
     g.batA = batA; g.batB = batB; g.batC = batC;
     g.M = M; g.N = N; g.K = K; g.L = L;
     g.a_kmajor = p.a_kmajor; g.b_kmajor = p.b_kmajor;
+    g.k_pairs = 0;
+    if (p.dtype == MB200_F64 && !p.msum.empty() && p.msum[0].sa == 1 && p.msum[0].sb == 1 && p.msum[0].extent % 2 == 0) {
+        bool even = true;   // every other stride of A and B keeps the pairs 16-byte aligned
+        for (size_t i = 1; i < p.msum.size(); i++) even = even && p.msum[i].sa % 2 == 0 && p.msum[i].sb % 2 == 0;
+        for (const GroupMode &m : p.mleft) even = even && m.sa % 2 == 0;
+        for (const GroupMode &m : p.mright) even = even && m.sb % 2 == 0;
+        for (const GroupMode &m : p.mbatch) even = even && m.sa % 2 == 0 && m.sb % 2 == 0;
+        g.k_pairs = even ? 1 : 0;
+    }
     return MB200_OK;
 }
 

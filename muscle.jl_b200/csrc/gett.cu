@@ -19,6 +19,7 @@
 // Pipeline: STAGES-deep cp.async ring over k-blocks of BK, one __syncthreads per k-block.
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "kernels.cuh"
 
@@ -68,6 +69,7 @@ __device__ __forceinline__ double neg_bits(double x) {  // sign flip on the inte
 template <int BM_, int BN_, int WM_, int WN_, int BK_, int STAGES_>
 struct CoreZ {
     using Elem = double2;
+    static constexpr int KSTEP = 1;   // k values per smem element
     static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, BK = BK_, STAGES = STAGES_;
     static constexpr int NWARPS = (BM / WM) * (BN / WN), NTHREADS = 32 * NWARPS;
     static constexpr int LDA = BM + 2, LDB = BN + 2;  // == 2 (mod 8) in 16 B units: conflict-free LDS.128
@@ -143,6 +145,7 @@ struct CoreZ {
 template <int BM_, int BN_, int WM_, int WN_, int BK_, int STAGES_>
 struct CoreD {
     using Elem = double;
+    static constexpr int KSTEP = 1;   // k values per smem element
     static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, BK = BK_, STAGES = STAGES_;
     static constexpr int NWARPS = (BM / WM) * (BN / WN), NTHREADS = 32 * NWARPS;
     static constexpr int LDA = BM + 4, LDB = BN + 4;  // == 4 (mod 16) in 8 B units: conflict-free LDS.64
@@ -194,11 +197,76 @@ struct CoreD {
     }
 };
 
+// Float64 on DMMA for operands that are both K-major with the unit-stride summed mode of even extent: an smem element is a PAIR
+// of consecutive k (16 bytes, like a ComplexF64 element), so one cp.async moves two k and one LDS.128 feeds two DMMAs
+// (x with x, y with y: CoreZ without the imaginary passes). Half the gather instructions and fragment loads per flop of CoreD
+// and twice the DMMAs per CTA barrier. BK counts pairs; GettParams::K and the k-offset tables are walked in pairs (KSTEP = 2).
+template <int BM_, int BN_, int WM_, int WN_, int BK_, int STAGES_>
+struct CoreD2 {
+    using Elem = double2;
+    static constexpr int KSTEP = 2;
+    static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, BK = BK_, STAGES = STAGES_;
+    static constexpr int NWARPS = (BM / WM) * (BN / WN), NTHREADS = 32 * NWARPS;
+    static constexpr int LDA = BM + 2, LDB = BN + 2;  // == 2 (mod 8) in 16 B units: conflict-free LDS.128
+    static constexpr int MT = WM / 8, NT = WN / 8;
+    struct Acc { double c[MT][NT][2]; };
+    __device__ static void init(Acc &a) {
+#pragma unroll
+        for (int i = 0; i < MT; i++)
+#pragma unroll
+            for (int j = 0; j < NT; j++) a.c[i][j][0] = a.c[i][j][1] = 0.0;
+    }
+    static constexpr int SLOTS = (BK / 4) * 2;
+    template <class Hook>
+    __device__ static void compute(Acc &acc, const Elem *sa, const Elem *sb, int warp, int lane, Hook &&hook) {
+        const int wm = (warp % (BM / WM)) * WM, wn = (warp / (BM / WM)) * WN;
+        const int fr = lane >> 2, fk = lane & 3;
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; kk++) {
+            double2 af[MT], bf[NT];
+#pragma unroll
+            for (int i = 0; i < MT; i++) af[i] = sa[(kk * 4 + fk) * LDA + wm + i * 8 + fr];
+#pragma unroll
+            for (int j = 0; j < NT; j++) bf[j] = sb[(kk * 4 + fk) * LDB + wn + j * 8 + fr];
+#pragma unroll
+            for (int i = 0; i < MT; i++)
+#pragma unroll
+                for (int j = 0; j < NT; j++) dmma(acc.c[i][j][0], acc.c[i][j][1], af[i].x, bf[j].x);   // even k of the pairs
+            hook(kk * 2 + 0);
+#pragma unroll
+            for (int i = 0; i < MT; i++)
+#pragma unroll
+                for (int j = 0; j < NT; j++) dmma(acc.c[i][j][0], acc.c[i][j][1], af[i].y, bf[j].y);   // odd k
+            hook(kk * 2 + 1);
+        }
+    }
+    __device__ static void store(const Acc &acc, Elem *Cv, const int64_t *sRowC, const int64_t *sColC,
+                                 int64_t cb, int mrem, int nrem, int warp, int lane, const ScatterDesc &) {
+        double *C = reinterpret_cast<double *>(Cv);   // C offsets are in doubles
+        const int wm = (warp % (BM / WM)) * WM, wn = (warp / (BM / WM)) * WN;
+        const int fr = lane >> 2, fc = (lane & 3) * 2;
+#pragma unroll
+        for (int j = 0; j < NT; j++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                int c = wn + j * 8 + fc + h;
+                if (c >= nrem) continue;
+                int64_t co = sColC[c] + cb;
+#pragma unroll
+                for (int i = 0; i < MT; i++) {
+                    int r = wm + i * 8 + fr;
+                    if (r < mrem) C[sRowC[r] + co] = acc.c[i][j][h];
+                }
+            }
+    }
+};
+
 // ComplexF32 / Float32 on FFMA. 256 threads as 16 x 16; thread (tx, ty) owns rows tx + 16 i and
 // columns ty + 16 j, so a warp's smem reads are 16 consecutive elements (A) or 2 broadcasts (B).
 template <typename E, int BM_, int BN_, int BK_, int STAGES_>
 struct CoreF {
     using Elem = E;
+    static constexpr int KSTEP = 1;
     static constexpr int BM = BM_, BN = BN_, BK = BK_, STAGES = STAGES_;
     static constexpr int NTHREADS = 256;
     static constexpr int LDA = BM, LDB = BN;
@@ -320,8 +388,9 @@ __global__ void __launch_bounds__(Core::NTHREADS, Core::NTHREADS <= 128 ? 4 : 1)
     const int64_t cb = split ? ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * (BM * BN) : p.batC[l];
     __syncthreads();
 
-    const E *gA = reinterpret_cast<const E *>(p.A) + ab;
-    const E *gB = reinterpret_cast<const E *>(p.B) + bb;
+    constexpr int64_t OFFB = (int64_t)sizeof(E) / Core::KSTEP;   // bytes per table offset unit (one scalar element of the tensor)
+    const char *gA = reinterpret_cast<const char *>(p.A) + ab * OFFB;
+    const char *gB = reinterpret_cast<const char *>(p.B) + bb * OFFB;
     // this slice's k-blocks [kb0, kb0 + KB); k beyond the slice (or beyond K) is zero-filled
     const int64_t KB_all = (p.K + BK - 1) / BK;
     const int64_t kb0 = KB_all * blockIdx.y / gridDim.y, kb1 = KB_all * (blockIdx.y + 1) / gridDim.y;
@@ -344,7 +413,7 @@ __global__ void __launch_bounds__(Core::NTHREADS, Core::NTHREADS <= 128 ? 4 : 1)
             int m, k;
             if (p.a_kmajor) { k = i % BK; m = i / BK; } else { m = i % BM; k = i / BM; }
             const bool ok = i < BM * BK && m < mrem;
-            u_ptr[u] = ok ? reinterpret_cast<const char *>(gA + sRowA[m]) : nullptr;
+            u_ptr[u] = ok ? gA + sRowA[m] * OFFB : nullptr;
             u_dst[u] = (i < BM * BK) ? (k * LDA + m) * (int)sizeof(E) : -1;
             u_k[u] = k;
         } else {
@@ -352,7 +421,7 @@ __global__ void __launch_bounds__(Core::NTHREADS, Core::NTHREADS <= 128 ? 4 : 1)
             int n, k;
             if (p.b_kmajor) { k = i % BK; n = i / BK; } else { n = i % BN; k = i / BN; }
             const bool ok = i < BN * BK && n < nrem;
-            u_ptr[u] = ok ? reinterpret_cast<const char *>(gB + sColB[n]) : nullptr;
+            u_ptr[u] = ok ? gB + sColB[n] * OFFB : nullptr;
             u_dst[u] = (i < BN * BK) ? (k * LDB + n) * (int)sizeof(E) : -1;
             u_k[u] = BK + k;
         }
@@ -383,7 +452,7 @@ __global__ void __launch_bounds__(Core::NTHREADS, Core::NTHREADS <= 128 ? 4 : 1)
             const int k = tid % BK;
             const int64_t kg = (kb0 + kblock) * BK + k;
             int64_t v = -1;
-            if (kg < k_limit) v = ((tid < BK) ? p.kA[kg] : p.kB[kg]) * (int64_t)sizeof(E);
+            if (kg < k_limit) v = ((tid < BK) ? p.kA[kg * Core::KSTEP] : p.kB[kg * Core::KSTEP]) * OFFB;
             sK[slot * 2 * BK + tid] = v;
         }
     };
@@ -732,6 +801,7 @@ cudaError_t launch(const GettParams &p, cudaStream_t s) {
     if (grid <= 0) return cudaSuccess;
     if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     using E = typename Core::Elem;
+    using RE = typename std::conditional<Core::KSTEP == 2, double, E>::type;   // element type of C and of the split-K partial tiles
     // split-K when the tiles cannot fill the GPU: slices = how many times the tile set fits into the resident CTA
     // slots, at most one slice per k-block (a k-block of work per CTA is the granularity of the pipeline)
     static const int sk_mode = [] { const char *e = getenv("MB200_SPLITK"); return e ? atoi(e) : 1; }();
@@ -744,7 +814,7 @@ cudaError_t launch(const GettParams &p, cudaStream_t s) {
         cudaError_t e = cudaMallocAsync((void **)&ws, (size_t)nsplit * grid * Core::BM * Core::BN * sizeof(E), s);
         if (e != cudaSuccess) return e;
         gett_kernel<Core><<<dim3((unsigned)grid, (unsigned)nsplit), Core::NTHREADS, gett_smem_bytes<Core>(), s>>>(p, ws, 0);
-        splitk_reduce_kernel<E, Core::BM, Core::BN><<<(unsigned)std::min<int64_t>((grid * Core::BM * Core::BN + 255) / 256, 148 * 16), 256, 0, s>>>(p, ws, (int)nsplit, grid, 0);
+        splitk_reduce_kernel<RE, Core::BM, Core::BN><<<(unsigned)std::min<int64_t>((grid * Core::BM * Core::BN + 255) / 256, 148 * 16), 256, 0, s>>>(p, (const RE *)ws, (int)nsplit, grid, 0);
         e = cudaGetLastError();
         cudaFreeAsync(ws, s);
         return e;
@@ -757,7 +827,7 @@ cudaError_t launch(const GettParams &p, cudaStream_t s) {
     // main launch: persistent (cross-tile pipeline) for the ComplexF64 main tile when every SM gets several tiles
     static const int persist_mode = [] { const char *e = getenv("MB200_PERSIST"); return e ? atoi(e) : 1; }();
     bool launched = false;
-    if constexpr (Core::STAGES == 2 && sizeof(E) == 16 && (Core::BM * Core::BK) % Core::NTHREADS == 0 &&
+    if constexpr (Core::STAGES == 2 && Core::KSTEP == 1 && sizeof(E) == 16 && (Core::BM * Core::BK) % Core::NTHREADS == 0 &&
                   (Core::BN * Core::BK) % Core::NTHREADS == 0 && (Core::NTHREADS > 128)) {
         // measured (tools/ab_tail.py): 8192 x 8192 x 256 30.6 -> 32.1 TFLOP/s, but K >= 1024 loses ~1 % (the extra control flow in the
         // k loop costs more than the hidden prologue / epilogue gains once a tile runs for 32+ k-blocks) -> short-K shapes only
@@ -773,7 +843,7 @@ cudaError_t launch(const GettParams &p, cudaStream_t s) {
         cudaError_t e = cudaMallocAsync((void **)&ws, (size_t)tsplit * tail * Core::BM * Core::BN * sizeof(E), s);
         if (e != cudaSuccess) return e;
         gett_kernel<Core><<<dim3((unsigned)tail, (unsigned)tsplit), Core::NTHREADS, gett_smem_bytes<Core>(), s>>>(p, ws, full);
-        splitk_reduce_kernel<E, Core::BM, Core::BN><<<(unsigned)std::min<int64_t>((tail * Core::BM * Core::BN + 255) / 256, 148 * 16), 256, 0, s>>>(p, ws, (int)tsplit, tail, full);
+        splitk_reduce_kernel<RE, Core::BM, Core::BN><<<(unsigned)std::min<int64_t>((tail * Core::BM * Core::BN + 255) / 256, 148 * 16), 256, 0, s>>>(p, (const RE *)ws, (int)tsplit, tail, full);
         e = cudaGetLastError();
         cudaFreeAsync(ws, s);
         return e;
@@ -782,7 +852,7 @@ cudaError_t launch(const GettParams &p, cudaStream_t s) {
 }
 template <class Core>
 cudaError_t configure() {
-    if constexpr (Core::STAGES == 2 && sizeof(typename Core::Elem) == 16 && (Core::BM * Core::BK) % Core::NTHREADS == 0 &&
+    if constexpr (Core::STAGES == 2 && Core::KSTEP == 1 && sizeof(typename Core::Elem) == 16 && (Core::BM * Core::BK) % Core::NTHREADS == 0 &&
                   (Core::BN * Core::BK) % Core::NTHREADS == 0 && (Core::NTHREADS > 128)) {
         cudaError_t e = cudaFuncSetAttribute(gett_persistent_kernel<Core>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)gett_persistent_smem_bytes<Core>());
@@ -800,6 +870,7 @@ using Z_128x16s = CoreZ<128, 16, 32, 16, 8, 2>;  // skinny N and short K (MPS-MP
 using Z_64x16t = CoreZ<64, 16, 16, 16, 8, 2>;    // streaming kernel tile: 4 warps x (16 x 16), ~42 KB smem -> 5 CTAs/SM
 using Z_16x128 = CoreZ<16, 128, 16, 16, 8, 4>;   // skinny M
 using D_128x128 = CoreD<128, 128, 64, 32, 16, 3>; // Float64: 8 warps x (64 x 32); BK = 32 x 2 stages measured slower (28.1 vs 31.5 TFLOP/s at 8192^3)
+using D2_128x128 = CoreD2<128, 128, 64, 32, 16, 3>; // Float64, K-major pairs: 8 warps x (64 x 32), 32 k per k-block
 using D_128x16 = CoreD<128, 16, 16, 16, 8, 4>;
 using D_16x128 = CoreD<16, 128, 16, 16, 8, 4>;
 using C_128x64 = CoreF<float2, 128, 64, 16, 3>;  // ComplexF32 FFMA: thread tile 8 x 4
@@ -816,7 +887,7 @@ cudaError_t gett_configure() {
 #define MB200_CFG(C) if ((e = configure<C>()) != cudaSuccess) return e
     if ((e = configure_stream<Z_64x16t>()) != cudaSuccess) return e;
     MB200_CFG(Z_128x64); MB200_CFG(Z_128x64k8); MB200_CFG(Z_128x16); MB200_CFG(Z_128x16s); MB200_CFG(Z_16x128);
-    MB200_CFG(D_128x128); MB200_CFG(D_128x16); MB200_CFG(D_16x128);
+    MB200_CFG(D_128x128); MB200_CFG(D2_128x128); MB200_CFG(D_128x16); MB200_CFG(D_16x128);
     MB200_CFG(C_128x64); MB200_CFG(C_128x16); MB200_CFG(C_16x128);
     MB200_CFG(S_128x128); MB200_CFG(S_128x16); MB200_CFG(S_16x128);
 #undef MB200_CFG
@@ -832,6 +903,12 @@ cudaError_t launch_gett_f64(int dtype, const GettParams &p, cudaStream_t s) {
     }
     if (p.N <= 16 && p.M > 16) return launch<D_128x16>(p, s);
     if (p.M <= 16 && p.N > 16) return launch<D_16x128>(p, s);
+    static const int pairs_mode = [] { const char *e = getenv("MB200_F64_PAIRS"); return e ? atoi(e) : 1; }();
+    if (pairs_mode && p.k_pairs && p.K >= 64 && p.K % 2 == 0 && ((((uintptr_t)p.A) | ((uintptr_t)p.B)) & 15) == 0) {
+        GettParams q = p;
+        q.K = p.K / 2;   // k is walked in pairs
+        return launch<D2_128x128>(q, s);   // 8192^3: 31.4 -> 32.9 TFLOP/s; a 128 x 64 / BK = 32 pair tile measured slower (31.0)
+    }
     return launch<D_128x128>(p, s);
 }
 

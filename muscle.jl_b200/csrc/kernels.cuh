@@ -64,6 +64,8 @@ struct GettParams {
     const int64_t *rowC, *colC, *batC;
     int64_t M, N, K, L;
     int a_kmajor, b_kmajor;
+    int k_pairs;   // Float64 only: both operands are K-major with a unit-stride summed mode of even extent and every other stride
+                   // even, so consecutive k pairs are 16-byte elements in both tensors (gett.cu CoreD2)
 };
 cudaError_t launch_gett_f64(int dtype, const GettParams &p, cudaStream_t s);   // F64 / C128, DMMA
 cudaError_t launch_simt_f32(int dtype, const GettParams &p, cudaStream_t s);   // F32 / C64, FFMA

@@ -479,6 +479,30 @@ def test_gather_gemm_split_k(m, n, k, l, dt):
     assert rel_frobenius(got.astype(wide), refr) <= (1e-12 if dt in ("complex128", "float64") else 1e-5)
 
 
+F64_PAIR_CASES = [
+    ("kmajor_matmul", dict(i=300, j=260, k=128), "ki", "kj", "ij"),                 # eligible: pairs of k are 16-byte elements
+    ("kmajor_two_summed", dict(k=6, l=20, i=70, j=90), "klij", "klj", "ji"),         # k*l merged (120), C transposed (operands swap)
+    ("kmajor_batch", dict(k=64, i=130, j=70, z=3), "kiz", "kjz", "ijz"),
+    ("kmajor_split_k", dict(i=256, j=256, k=4096), "ki", "kj", "ij"),                # few tiles: split-K partial tiles in doubles
+    ("k_odd_fallback", dict(i=200, j=136, k=129), "ki", "kj", "ij"),                 # odd K: plain Float64 core
+    ("row_stride_odd_fallback", dict(k=64, i=131, j=70, z=3), "kiz", "jkz", "ijz"),  # B is not K-major
+]
+
+
+@pytest.mark.parametrize("integer", [False, True], ids=["random", "integer_exact"])
+@pytest.mark.parametrize("case", F64_PAIR_CASES, ids=[c[0] for c in F64_PAIR_CASES])
+def test_float64_k_pair_core(case, integer):
+    """Float64 with both operands K-major takes the k-pair DMMA core (a 16-byte smem element = two consecutive k); odd K or a
+    non-K-major operand fall back to the plain core. 1e-12 against the oracle, bit-exact on integer inputs."""
+    a, ia, b, ib, ic = build_case(case, "float64", seed=43, integer=integer)
+    ref = binary_einsum_general(ic, a, ia, b, ib)
+    got = contract(a, ia, b, ib, ic, device=True, path=mb.PATH_GETT_F64)
+    if integer:
+        assert np.array_equal(got, ref), case[0]
+    else:
+        assert rel_frobenius(got, ref) <= 1e-12, (case[0], rel_frobenius(got, ref))
+
+
 @pytest.mark.parametrize("m,n,k,l", [(2500, 1000, 160, 1), (1300, 700, 300, 3), (4096, 1200, 512, 1), (2500, 1000, 2048, 1)])
 def test_gather_gemm_persistent_and_split_tail(m, n, k, l):
     """ComplexF64 shapes with several tiles per SM: short sums (K <= 512) take the persistent kernel (one software pipeline
