@@ -122,6 +122,9 @@ typedef struct {
     int32_t a_kmajor, b_kmajor;  /* 1: the operand's unit-stride mode is a summed mode           */
     double flops;                /* 8*M*N*K*L complex, 2*M*N*K*L real                            */
     double bytes;                /* sizeof(T)*(|A|+|B|+|C|)                                      */
+    int32_t tc_eligible;         /* 1: ComplexF32 / Float32 shape the tcgen05 path accepts (M >= 64, N >= 32, K >= 64) */
+    int32_t tc_permute_pack;     /* 1: its operands are packed by a K1 permutation; 0 with tc_eligible: by the
+                                    table-driven gather pack (summed extents not tiling groups of 8 k, strided operands) */
 } mb200_plan_info_t;
 
 int mb200_plan_describe(int dtypeC, int nmodeC, const int32_t *modesC, const int64_t *stridesC,

@@ -53,7 +53,8 @@ class PlanInfo(C.Structure):
                 ("left", C.c_int32 * MAX_MODES), ("right", C.c_int32 * MAX_MODES),
                 ("sum", C.c_int32 * MAX_MODES), ("batch", C.c_int32 * MAX_MODES),
                 ("a_kmajor", C.c_int32), ("b_kmajor", C.c_int32),
-                ("flops", C.c_double), ("bytes", C.c_double)]
+                ("flops", C.c_double), ("bytes", C.c_double),
+                ("tc_eligible", C.c_int32), ("tc_permute_pack", C.c_int32)]
 
 
 class ShardInfo(C.Structure):

@@ -306,6 +306,8 @@ void fill_info(const Plan &p, mb200_plan_info_t *info) {
     info->b_kmajor = p.b_kmajor;
     info->flops = p.flops;
     info->bytes = p.bytes;
+    info->tc_eligible = p.tc_ok;
+    info->tc_permute_pack = p.tc_permute_pack;
 }
 
 }  // namespace mb200

@@ -206,3 +206,28 @@ def test_shard_plan():
     # nothing shardable → replicas only
     s = mb.shard_plan([0], [0, 1], [2, 3], [1], [3], 8, 0)
     assert s.kind == _lib.SHARD_NONE
+
+
+def test_planner_tcgen05_eligibility_and_pack_kind():
+    """ComplexF32 / Float32 shapes with M >= 64, N >= 32, K >= 64 are tcgen05-eligible whatever the summed extents and strides;
+    the operands are packed by a K1 permutation when the leading summed modes tile groups of 8 k and both tensors are dense,
+    by the table-driven gather pack otherwise (host-only planner facts, no device needed)."""
+    C64, F32, C128 = _lib.C64, _lib.F32, _lib.C128
+    # config 3 (PEPS, D = 8): permutation pack
+    i = mb.plan_describe(C64, [0, 2, 4, 5, 6], C64, [0, 1, 2, 3, 6], [256, 8, 8, 256, 8], C64, [3, 1, 4, 5, 6], [256, 8, 8, 256, 8])
+    assert i.path == mb.PATH_TCGEN05_TF32 and i.tc_eligible == 1 and i.tc_permute_pack == 1
+    # K = 100 (4 | 100 but 8 does not): eligible, gather pack; big enough -> tcgen05 picked
+    i = mb.plan_describe(C64, [1, 2], C64, [0, 1], [100, 2048], C64, [0, 2], [100, 2048])
+    assert i.tc_eligible == 1 and i.tc_permute_pack == 0 and i.path == mb.PATH_TCGEN05_TF32
+    # odd bond dimensions 3 x 5 x 7 = 105
+    i = mb.plan_describe(F32, [3, 4], F32, [0, 3, 1, 2], [3, 1300, 5, 7], F32, [2, 4, 1, 0], [7, 1100, 5, 3])
+    assert i.K == 105 and i.tc_eligible == 1 and i.tc_permute_pack == 0 and i.path == mb.PATH_TCGEN05_TF32
+    # a strided operand (every other row of a wider buffer): gather pack
+    i = mb.plan_describe(C64, [1, 2], C64, [0, 1], [512, 2048], C64, [0, 2], [512, 1024], strides_b=[2, 1024])
+    assert i.tc_eligible == 1 and i.tc_permute_pack == 0
+    i = mb.plan_describe(C64, [1, 2], C64, [0, 1], [512, 2048], C64, [0, 2], [512, 1024])
+    assert i.tc_eligible == 1 and i.tc_permute_pack == 1
+    # K < 64, a skinny side, or a double-precision dtype: not eligible
+    assert mb.plan_describe(C64, [1, 2], C64, [0, 1], [60, 2048], C64, [0, 2], [60, 2048]).tc_eligible == 0
+    assert mb.plan_describe(C64, [1, 2], C64, [0, 1], [512, 2048], C64, [0, 2], [512, 16]).tc_eligible == 0
+    assert mb.plan_describe(C128, [1, 2], C128, [0, 1], [512, 2048], C128, [0, 2], [512, 2048]).tc_eligible == 0
