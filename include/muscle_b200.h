@@ -57,6 +57,24 @@ typedef enum {
     MB200_PATH_TCGEN05_TF32 = 4 /* K3: tcgen05/TMEM split-operand (TF32 + BF16) GEMM on TMA-fed operands */
 } mb200_path_t;
 
+/* Arithmetic of Float32 / ComplexF32 contractions (per handle, mb200_set_compute_type). Float64 / ComplexF64 always run
+ * native FP64 FMAs (DMMA) and are not affected.
+ *   DEFAULT  the north-star scheme: shapes with M >= 64, N >= 32, K >= 64 and >= 2^27 MACs run on tcgen05 tensor cores with
+ *            split-operand error compensation, x = tf32_rn(x) + lo: hi*hi in TF32 plus both cross terms in ONE bf16 MMA
+ *            (lo*lo is dropped, the cross terms carry bf16's 8-bit significand), chunked FP32 accumulation. Accuracy contract:
+ *            relative Frobenius error <= 1e-5 against an FP64 reference (measured 1.3e-6 ComplexF32 / 0.9e-6 Float32, flat in
+ *            K up to 16384) - about 10x the error of FP32 FMAs. Integer-valued operands are reproduced exactly only while
+ *            every operand fits TF32's 11-bit significand (|x| <= 2048); smaller / skinnier shapes use FP32 FMAs, so the
+ *            accuracy changes at the eligibility threshold.
+ *   FP32     strict: every product and sum is an FP32 FMA on every shape (what cuTENSOR's default COMPUTE_32F and Muscle's
+ *            BackendBase give); the tensor-core path is never taken.
+ *   3XTF32   the classic three-pass split (hi*hi + hi*lo + lo*hi, all TF32) on the same tensor-core path. */
+typedef enum {
+    MB200_COMPUTE_DEFAULT = 0,
+    MB200_COMPUTE_FP32 = 1,
+    MB200_COMPUTE_3XTF32 = 2
+} mb200_compute_type_t;
+
 typedef struct mb200_handle_s *mb200_handle_t;
 
 /* ---- library / handle ------------------------------------------------------------------ */
@@ -71,6 +89,9 @@ int mb200_set_stream(mb200_handle_t handle, void *cuda_stream);
 int mb200_stream_sync(mb200_handle_t handle);
 /* force a kernel family (testing / benchmarking); MB200_PATH_AUTO restores the planner's choice */
 int mb200_set_path(mb200_handle_t handle, int path);
+/* mb200_compute_type_t for Float32 / ComplexF32 contractions on this handle (default MB200_COMPUTE_DEFAULT) */
+int mb200_set_compute_type(mb200_handle_t handle, int compute_type);
+int mb200_get_compute_type(mb200_handle_t handle, int *compute_type);
 
 /* ---- device / pinned-host memory helpers (Julia has no CUDA.jl on this path) -------------- */
 int mb200_malloc(mb200_handle_t handle, void **dptr, size_t bytes);
@@ -84,8 +105,12 @@ int mb200_memset(mb200_handle_t handle, void *dptr, int value, size_t bytes);
 /* ---- the hot path ------------------------------------------------------------------------
  * C[modesC] = sum over modes absent from C of A[modesA] * B[modesB]        (alpha = 1, beta = 0)
  * Mode classes: batch/hyper = in A, B and C; summed = in A and B, not C; free = in one operand and C.
+ * A mode carried by ONE operand and absent from C ("dangling") is summed over, as cuTENSOR.contract! and OMEinsum do
+ * (ext/MuscleCUDAExt.jl:30-38, ext/MuscleOMEinsumExt.jl:40-59; BackendBase rejects it, binary_einsum.jl:83): launch-bound
+ * sizes fold the sum into the contraction kernel (the other operand is broadcast along it), larger operands are
+ * pre-reduced by one unary_einsum pass.
  * Rejected (INVALID_ARGUMENT): a mode repeated inside one tensor, a C mode found in neither
- * operand, a mode of a single operand missing from C, nmodes > MB200_MAX_MODES.
+ * operand, nmodes > MB200_MAX_MODES.
  * DIMENSION_MISMATCH: a shared mode with different extents in A and B.
  * dtypes may differ between A and B (Float64 x ComplexF64 ...): the result dtype must be the
  * promotion of the two (Base.promote_eltype, ext/MuscleCUDAExt.jl:16).
@@ -222,12 +247,51 @@ int mb200_binary_einsum_scatter(mb200_handle_t handle,
 int mb200_reduce_slots(mb200_handle_t handle, void *out, const void *staging_local, int dtype,
                        int64_t slab_elems, int nslots);
 
+/* ---- summed-index slice with the all-reduce FUSED into the contraction ("cross-GPU split-K") -------------
+ * One process per GPU. Dagger contracts every pair of summed-index blocks and add-reduces the partial outputs
+ * (treereduce(AddComputeOp), ext/MuscleDaggerExt/binary_einsum.jl:107-115); the NCCL baseline here is contraction then
+ * ncclAllReduce. This entry overlaps the two: every rank contracts its K-slice into partial 128 x BN sub-tiles ("units") kept
+ * in its own workspace and raises a flag in the unit's owner (unit % nranks); the owner's reducer kernel runs CONCURRENTLY on
+ * a side stream, adds the nranks partials of each unit as soon as all of them exist (peer loads over NVLink, or one
+ * multimem.ld_reduce when an NVLS multicast mapping is given) and stores the finished unit into the C of every rank (peer
+ * stores or multimem.st) through C's offset tables, i.e. in any requested index order. Every rank ends with the same bits.
+ * Buffers (comm): ws / c / flags of EVERY rank as pointers valid on this device (own + IPC or VMM peer mappings); flags must
+ * be zero-initialised once; `epoch` starts at 1 and increases with every call on the same buffers. A call may reuse the
+ * buffers of the previous call as soon as that call's DIST_WAIT phase has been enqueued (stream order) on every rank.
+ * phases: CONTRACT | REDUCE | WAIT (7) is the production call. The separate bits exist so that a single GPU can emulate
+ * several ranks in tests (all contractions first, then all reducers, then the waits).
+ * Supported on the ComplexF32 / Float32 tcgen05 path; NOT_SUPPORTED otherwise (use an NCCL all-reduce). */
+#define MB200_DIST_CONTRACT 1
+#define MB200_DIST_REDUCE 2
+#define MB200_DIST_WAIT 4
+typedef struct {
+    int32_t nranks, rank, epoch;
+    void *ws[MB200_MAX_PEERS];    /* partial-unit workspace of every rank, ws_bytes each                     */
+    void *c[MB200_MAX_PEERS];     /* output C of every rank (dense column-major in modesC order)              */
+    void *flags[MB200_MAX_PEERS]; /* flag array of every rank, flag_bytes each, zeroed once                   */
+    void *mc_ws, *mc_c;           /* NVLS multicast mappings of ws and c over all ranks, or both NULL          */
+    size_t ws_bytes, flag_bytes;  /* sizes of the buffers above (checked against mb200_allreduce_workspace)    */
+} mb200_comm_t;
+/* sizes of the per-rank workspace and flag array for this contraction (host only; dense operands) */
+int mb200_allreduce_workspace(mb200_handle_t handle, int dtypeC, int nmodeC, const int32_t *modesC,
+                              int dtypeA, int nmodeA, const int32_t *modesA, const int64_t *extentsA,
+                              int dtypeB, int nmodeB, const int32_t *modesB, const int64_t *extentsB,
+                              int nranks, size_t *ws_bytes, size_t *flag_bytes);
+int mb200_binary_einsum_allreduce(mb200_handle_t handle, int dtypeC, int nmodeC, const int32_t *modesC,
+                                  const void *A, int dtypeA, int nmodeA, const int32_t *modesA,
+                                  const int64_t *extentsA, const int64_t *stridesA,
+                                  const void *B, int dtypeB, int nmodeB, const int32_t *modesB,
+                                  const int64_t *extentsB, const int64_t *stridesB,
+                                  const mb200_comm_t *comm, int phases);
+
 /* ---- CUDA-graph replay of a fixed sequence of calls (n-ary contraction chains) ------------
  * Everything enqueued on the handle's stream between graph_begin and graph_end (binary_einsum, unary_einsum,
  * hadamard, permute ... on fixed device pointers) is captured instead of executed and can then be replayed with one
  * launch: a launch-bound chain of small contractions costs one graph launch instead of one kernel launch (plus
  * planner work) per step. The handle's stream must not be the legacy default stream. Every plan the sequence needs
- * must already be cached (run the sequence once before capturing): a plan miss during capture is NOT_SUPPORTED. */
+ * must already be cached (run the sequence once before capturing): a plan miss during capture is NOT_SUPPORTED.
+ * A graph co-owns every cached plan its kernel nodes point into (offset tables): evicting such a plan from the handle's
+ * LRU cache, or destroying the handle, leaves the graph replayable; the tables go when mb200_graph_destroy runs. */
 typedef struct mb200_graph_s *mb200_graph_t;
 int mb200_graph_begin(mb200_handle_t handle);
 int mb200_graph_end(mb200_handle_t handle, mb200_graph_t *graph);

@@ -33,6 +33,9 @@ PATH_NAMES = {PATH_AUTO: "auto", PATH_DIRECT: "direct", PATH_GETT_F64: "gett_f64
 
 SHARD_NONE, SHARD_FREE, SHARD_BATCH, SHARD_SUM = range(4)
 
+# arithmetic of Float32 / ComplexF32 contractions (mb200_compute_type_t)
+COMPUTE_DEFAULT, COMPUTE_FP32, COMPUTE_3XTF32 = range(3)
+
 
 class ArgumentError(ValueError):
     """Julia `ArgumentError` (src/Operations/binary_einsum.jl:53-55, 82-83)."""
@@ -62,6 +65,16 @@ class ShardInfo(C.Structure):
                 ("needs_allreduce", C.c_int32)]
 
 
+class Comm(C.Structure):
+    """mb200_comm_t: the peer buffers of a fused contraction + all-reduce (include/muscle_b200.h)."""
+    _fields_ = [("nranks", C.c_int32), ("rank", C.c_int32), ("epoch", C.c_int32),
+                ("ws", C.c_void_p * 8), ("c", C.c_void_p * 8), ("flags", C.c_void_p * 8),
+                ("mc_ws", C.c_void_p), ("mc_c", C.c_void_p), ("ws_bytes", C.c_size_t), ("flag_bytes", C.c_size_t)]
+
+
+DIST_CONTRACT, DIST_REDUCE, DIST_WAIT = 1, 2, 4
+
+
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "launches_total", "launches_direct", "launches_gett_f64", "launches_simt_f32", "launches_tcgen05",
@@ -84,6 +97,8 @@ PROTOTYPES = {
     "mb200_set_stream": ([_vp, _vp], C.c_int),
     "mb200_stream_sync": ([_vp], C.c_int),
     "mb200_set_path": ([_vp, _i], C.c_int),
+    "mb200_set_compute_type": ([_vp, _i], C.c_int),
+    "mb200_get_compute_type": ([_vp, C.POINTER(_i)], C.c_int),
     "mb200_malloc": ([_vp, C.POINTER(_vp), _sz], C.c_int),
     "mb200_free": ([_vp, _vp], C.c_int),
     "mb200_host_alloc": ([C.POINTER(_vp), _sz], C.c_int),
@@ -123,6 +138,14 @@ PROTOTYPES = {
                                      _vp, _i, _i, _i32p, _i64p, _i64p,
                                      C.POINTER(_vp), _i, _i, _i], C.c_int),
     "mb200_reduce_slots": ([_vp, _vp, _vp, _i, C.c_int64, _i], C.c_int),
+    "mb200_allreduce_workspace": ([_vp, _i, _i, _i32p,
+                                   _i, _i, _i32p, _i64p,
+                                   _i, _i, _i32p, _i64p,
+                                   _i, C.POINTER(_sz), C.POINTER(_sz)], C.c_int),
+    "mb200_binary_einsum_allreduce": ([_vp, _i, _i, _i32p,
+                                       _vp, _i, _i, _i32p, _i64p, _i64p,
+                                       _vp, _i, _i, _i32p, _i64p, _i64p,
+                                       C.POINTER(Comm), _i], C.c_int),
     "mb200_graph_begin": ([_vp], C.c_int),
     "mb200_graph_end": ([_vp, C.POINTER(_vp)], C.c_int),
     "mb200_graph_launch": ([_vp, _vp], C.c_int),
@@ -201,9 +224,11 @@ def i64(seq):
 
 
 class Handle:
-    """One mb200 handle per (process, device). The stream follows torch's current stream when
-    torch is importable, so torch.cuda.Event timing and torch allocations are ordered with our
-    launches (torch is plumbing here: device memory, streams, torch.distributed)."""
+    """One mb200 handle per (device, host thread) — the header's contract. The stream follows torch's
+    current stream (which is itself per thread) when torch is importable, so torch.cuda.Event timing and
+    torch allocations are ordered with our launches (torch is plumbing here: device memory, streams,
+    torch.distributed). Two Python threads on different torch streams therefore never re-point each
+    other's handle between `set_stream` and a launch (ctypes releases the GIL during foreign calls)."""
 
     _handles: dict = {}
     _lock = threading.Lock()
@@ -218,10 +243,13 @@ class Handle:
     def get(cls, device: int | None = None) -> "Handle":
         if device is None:
             device = current_device()
-        with cls._lock:
-            h = cls._handles.get(device)
-            if h is None:
-                h = cls._handles[device] = Handle(device)
+        key = (device, threading.get_ident())
+        h = cls._handles.get(key)
+        if h is None:
+            with cls._lock:
+                h = cls._handles.get(key)
+                if h is None:
+                    h = cls._handles[key] = Handle(device)
         h.sync_stream_with_torch()
         return h
 
@@ -247,6 +275,15 @@ class Handle:
 
     def set_path(self, path: int):
         check(lib().mb200_set_path(self._h, path))
+
+    def set_compute_type(self, compute_type: int):
+        """COMPUTE_DEFAULT (tensor-core split scheme, <= 1e-5), COMPUTE_FP32 (strict FP32 FMAs), COMPUTE_3XTF32."""
+        check(lib().mb200_set_compute_type(self._h, compute_type))
+
+    def compute_type(self) -> int:
+        v = C.c_int()
+        check(lib().mb200_get_compute_type(self._h, C.byref(v)))
+        return int(v.value)
 
     def stats(self) -> dict:
         s = Stats()

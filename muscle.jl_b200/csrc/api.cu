@@ -20,14 +20,32 @@ using namespace mb200;
 
 namespace {
 
+// A cached plan is shared between the handle's LRU cache and every captured graph whose kernel nodes carry raw pointers
+// into its offset tables (GettParams rowA/rowC/... are passed by value at capture time): the tables are freed when the
+// LAST owner lets go, so evicting a plan from the cache can never pull the tables from under a graph replay.
 struct CachedPlan {
     Plan plan;
+    int device = 0;
     int64_t *tables = nullptr;  // one device allocation: rowA rowC colB colC kA kB batA batB batC
     GettParams gp{};
     DirectParams dp{};
     ApplyParams ap{};
     bool use_apply = false, apply_big_is_row = true;
     std::list<std::string>::iterator lru;
+    CachedPlan() = default;
+    CachedPlan(const CachedPlan &) = delete;
+    CachedPlan &operator=(const CachedPlan &) = delete;
+    ~CachedPlan() {
+        if (!tables) return;
+        int cur = 0;
+        cudaGetDevice(&cur);
+        cudaSetDevice(device);
+        // launches that read these tables may be in flight on ANY stream the handle has used (mb200_set_stream can
+        // change it between calls): wait for the whole device, not only the current stream
+        cudaDeviceSynchronize();
+        cudaFree(tables);
+        cudaSetDevice(cur);
+    }
 };
 
 constexpr size_t PLAN_CACHE_CAP = 128;
@@ -38,17 +56,23 @@ struct mb200_handle_s {
     int device = 0;
     cudaStream_t stream = nullptr;
     int forced_path = MB200_PATH_AUTO;
-    std::unordered_map<std::string, std::unique_ptr<CachedPlan>> cache;
+    int compute_type = MB200_COMPUTE_DEFAULT;
+    std::unordered_map<std::string, std::shared_ptr<CachedPlan>> cache;
     std::list<std::string> lru;
     mb200_stats_t stats{};
     std::mutex mu;
     bool capturing = false;
+    std::vector<std::shared_ptr<CachedPlan>> captured;   // plans touched since mb200_graph_begin
+    // cross-GPU split-K: the reducer runs on a high-priority side stream, concurrently with the GEMM on `stream`
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 struct mb200_graph_s {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     int device = 0;
+    std::vector<std::shared_ptr<CachedPlan>> plans;      // keeps the offset tables its kernel nodes point into alive
 };
 
 namespace {
@@ -183,20 +207,14 @@ void evict_one(mb200_handle_t h) {
     std::string key = h->lru.back();
     h->lru.pop_back();
     auto it = h->cache.find(key);
-    if (it != h->cache.end()) {
-        if (it->second->tables) {
-            cudaStreamSynchronize(h->stream);  // a launch using these tables may still be in flight
-            cudaFree(it->second->tables);
-        }
-        h->cache.erase(it);
-    }
+    if (it != h->cache.end()) h->cache.erase(it);   // ~CachedPlan frees the tables once no captured graph holds the plan
 }
 
 // Split scheme of the tcgen05 path: mixed TF32 + BF16 (8 MMAs per 8 k of a complex product) unless MB200_SPLIT_SCHEME=3xtf32
 // asks for the all-TF32 scheme (12 MMAs; A/B measurements, tools/ab_c64.py).
-bool tf32_mixed() {
-    static const bool mixed = [] { const char *e = getenv("MB200_SPLIT_SCHEME"); return !(e && std::string(e) == "3xtf32"); }();
-    return mixed;
+bool tf32_mixed(const mb200_handle_t h) {
+    static const bool env_mixed = [] { const char *e = getenv("MB200_SPLIT_SCHEME"); return !(e && std::string(e) == "3xtf32"); }();
+    return env_mixed && h->compute_type != MB200_COMPUTE_3XTF32;
 }
 
 // K1 pack of one operand into the tcgen05 kernel's operand format: [batch][rows][4*K] floats, K-major,
@@ -268,14 +286,42 @@ int64_t span_of(const TensorDesc &t) {
     return s;
 }
 
+int ensure_side_stream(mb200_handle_t h) {
+    if (h->side) return MB200_OK;
+    int lo = 0, hi = 0;
+    MB200_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    MB200_CUDA(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, hi));
+    MB200_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    MB200_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    return MB200_OK;
+}
+
+constexpr int DIST_CONTRACT = 1, DIST_REDUCE = 2, DIST_WAIT = 4;
+
 int contract_device(mb200_handle_t h, void *C, TensorDesc &dC, const int64_t *stridesC, const void *A,
-                    const TensorDesc &dA, const void *B, const TensorDesc &dB, const ScatterDesc *sc = nullptr) {
+                    const TensorDesc &dA, const void *B, const TensorDesc &dB, const ScatterDesc *sc = nullptr,
+                    const DistDesc *dist = nullptr, int phases = 0, size_t dist_ws_bytes = 0, size_t dist_flag_bytes = 0) {
     Plan plan;
     int st = make_plan(dA, dB, dC, stridesC, h->forced_path, plan);
     if (st != MB200_OK) return st;
+    if (h->compute_type == MB200_COMPUTE_FP32 && plan.path == MB200_PATH_TCGEN05_TF32) {
+        // strict FP32: every product and sum is an FP32 FMA (cuTENSOR COMPUTE_32F / BackendBase accuracy)
+        if ((st = make_plan(dA, dB, dC, stridesC, MB200_PATH_SIMT_F32, plan)) != MB200_OK) return st;
+    }
     if (plan.empty_output) return MB200_OK;
-    if ((!C && !sc) || (!A && dA.numel() > 0) || (!B && dB.numel() > 0))
+    if ((!C && !sc && !dist) || (!A && dA.numel() > 0) || (!B && dB.numel() > 0))
         return fail(MB200_INVALID_ARGUMENT, "NULL data pointer");
+    if (dist) {
+        if (!(plan.path == MB200_PATH_TCGEN05_TF32 && tf32_available()))
+            return fail(MB200_NOT_SUPPORTED, "the fused all-reduce runs on the ComplexF32 / Float32 tcgen05 path (this contraction is "
+                                             "planned on path %d); use an NCCL all-reduce of the partial outputs", plan.path);
+        const DistGeometry geo = tf32_dist_geometry(plan.dtype, plan.M, plan.N, plan.L);
+        const size_t need_ws = (size_t)geo.nunits * geo.unit_elems * dtype_size(plan.dtype);
+        const size_t need_fl = ((size_t)geo.nunits * dist->nranks + dist->nranks + 1) * sizeof(int);
+        if (dist_ws_bytes < need_ws || dist_flag_bytes < need_fl)
+            return fail(MB200_INVALID_ARGUMENT, "all-reduce workspace too small: %zu / %zu bytes given, %zu / %zu needed "
+                                                "(mb200_allreduce_workspace)", dist_ws_bytes, dist_flag_bytes, need_ws, need_fl);
+    }
     if (sc) {
         const bool tensor_path = (plan.path == MB200_PATH_GETT_F64 && plan.dtype == MB200_C128) ||
                                  (plan.path == MB200_PATH_TCGEN05_TF32 && tf32_available());
@@ -300,19 +346,18 @@ int contract_device(mb200_handle_t h, void *C, TensorDesc &dC, const int64_t *st
         if (h->capturing)
             return fail(MB200_NOT_SUPPORTED, "plan miss during graph capture: run the sequence once before mb200_graph_begin");
         while (h->cache.size() >= PLAN_CACHE_CAP) evict_one(h);
-        auto fresh = std::make_unique<CachedPlan>();
+        auto fresh = std::make_shared<CachedPlan>();
         fresh->plan = plan;
+        fresh->device = h->device;
         st = build_cached(h, *fresh);
-        if (st != MB200_OK) {
-            if (fresh->tables) cudaFree(fresh->tables);
-            return st;
-        }
+        if (st != MB200_OK) return st;
         h->lru.push_front(plan.key);
         fresh->lru = h->lru.begin();
         cp = fresh.get();
-        h->cache.emplace(plan.key, std::move(fresh));
+        it = h->cache.emplace(plan.key, std::move(fresh)).first;
         h->stats.plans_built++;
     }
+    if (h->capturing) h->captured.push_back(it->second);
     const Plan &p = cp->plan;
     cudaStream_t s = h->stream;
 
@@ -349,13 +394,39 @@ int contract_device(mb200_handle_t h, void *C, TensorDesc &dC, const int64_t *st
     } else if (p.path == MB200_PATH_TCGEN05_TF32 && tf32_available()) {
         // pack A, pack B (K1 with the split writer: a strided permutation when the layout allows it, else the table-driven
         // gather pack with K zero-padded to a multiple of 8), then the tcgen05 GEMM with the permuting epilogue
-        const bool mixed = tf32_mixed();
+        const bool mixed = tf32_mixed(h);
         const bool by_permute = p.tc_permute_pack && build_pack_params(p, 0, mixed, qa, rows_a) && build_pack_params(p, 1, mixed, qb, rows_b);
         if (!by_permute) { rows_a = p.M; rows_b = p.N; }
         const int64_t Kp = by_permute ? p.K : (p.K + 7) / 8 * 8;
         void *pa = nullptr, *pb = nullptr;
         const size_t W = p.dtype == MB200_F32 ? 2 : 4;
         const size_t ba = (size_t)p.L * rows_a * W * Kp * sizeof(float), bb = (size_t)p.L * rows_b * W * Kp * sizeof(float);
+        if (dist && (phases & DIST_REDUCE) && (phases & DIST_CONTRACT)) {
+            // the owner-side reducer first, on the side stream: it is resident (spinning on unit flags) before the GEMM's
+            // CTAs arrive and drains finished units while the GEMM is still producing the later ones
+            if ((st = ensure_side_stream(h)) != MB200_OK) return st;
+            MB200_CUDA(cudaEventRecord(h->ev_fork, s));
+            MB200_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+            GettParams gr = cp->gp;
+            MB200_CUDA(launch_tf32_allreduce(p.dtype, gr, *dist, h->side));
+            MB200_CUDA(cudaEventRecord(h->ev_join, h->side));
+            h->stats.launches_reduce++; h->stats.launches_total++;
+        }
+        if (dist && !(phases & DIST_CONTRACT)) {
+            e = cudaSuccess;
+            if (phases & DIST_REDUCE) {
+                e = launch_tf32_allreduce(p.dtype, cp->gp, *dist, s);
+                h->stats.launches_reduce++; h->stats.launches_total++;
+            }
+            if (e == cudaSuccess && (phases & DIST_WAIT)) {
+                e = launch_dist_wait_done(*dist, tf32_dist_geometry(p.dtype, p.M, p.N, p.L).nunits, s);
+                h->stats.launches_reduce++; h->stats.launches_total++;
+            }
+            if (tmpR) cudaFreeAsync(tmpR, s);
+            if (tmpQ) cudaFreeAsync(tmpQ, s);
+            if (e != cudaSuccess) return cuda_fail(e, "all-reduce launch");
+            return MB200_OK;
+        }
         MB200_CUDA(cudaMallocAsync(&pa, ba, s));
         MB200_CUDA(cudaMallocAsync(&pb, bb, s));
         const GettParams &t = cp->gp;
@@ -375,12 +446,19 @@ int contract_device(mb200_handle_t h, void *C, TensorDesc &dC, const int64_t *st
             g.K = Kp;
             if (sc) g.sc = *sc;
             bool pair = false;
-            e = launch_tf32_gemm(p.dtype, pa, pb, g, mixed, s, &pair);
+            e = launch_tf32_gemm(p.dtype, pa, pb, g, mixed, s, &pair, dist);
             h->stats.launches_tcgen05++;
             if (pair) h->stats.launches_tcgen05_pair++;
         }
         cudaFreeAsync(pa, s);
         cudaFreeAsync(pb, s);
+        if (dist && e == cudaSuccess) {
+            if (phases & DIST_REDUCE) e = cudaStreamWaitEvent(s, h->ev_join, 0);   // join: the reducer has drained every owned unit
+            if (e == cudaSuccess && (phases & DIST_WAIT)) {
+                e = launch_dist_wait_done(*dist, tf32_dist_geometry(p.dtype, p.M, p.N, p.L).nunits, s);
+                h->stats.launches_reduce++; h->stats.launches_total++;
+            }
+        }
     } else {
         GettParams g = cp->gp;
         g.A = R; g.B = Q; g.C = C;
@@ -413,252 +491,10 @@ int make_c_desc(TensorDesc &d, int dtype, int nmode, const int32_t *modes) {
 
 }  // namespace
 
-extern "C" {
-
-int mb200_version(void) { return 100; }
-
-const char *mb200_last_error_string(void) { return last_error().c_str(); }
-
-int mb200_device_count(int *count) {
-    if (!count) return fail(MB200_INVALID_ARGUMENT, "count is NULL");
-    *count = 0;
-    MB200_CUDA(cudaGetDeviceCount(count));
-    return MB200_OK;
-}
-
-int mb200_create(mb200_handle_t *handle, int device) {
-    if (!handle) return fail(MB200_INVALID_ARGUMENT, "handle is NULL");
-    *handle = nullptr;
-    int n = 0;
-    cudaError_t e = cudaGetDeviceCount(&n);
-    if (e != cudaSuccess || n == 0)
-        return fail(MB200_CUDA_ERROR, "no usable CUDA device (%s); libmuscle_b200 has no CPU fallback",
-                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
-    if (device < 0 || device >= n) return fail(MB200_INVALID_ARGUMENT, "device %d outside [0, %d)", device, n);
-    MB200_CUDA(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    MB200_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10)
-        return fail(MB200_NOT_SUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
-                    device, prop.major, prop.minor);
-    MB200_CUDA(gett_configure());
-    MB200_CUDA(permute_configure());
-    MB200_CUDA(tf32_configure());
-    // keep stream-ordered temporaries cached in the pool instead of returning them to the OS
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        uint64_t thr = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-    }
-    auto *h = new mb200_handle_s();
-    h->device = device;
-    *handle = h;
-    return MB200_OK;
-}
-
-int mb200_destroy(mb200_handle_t h) {
-    MB200_CHECK_HANDLE(h);
-    cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
-    for (auto &kv : h->cache)
-        if (kv.second->tables) cudaFree(kv.second->tables);
-    delete h;
-    return MB200_OK;
-}
-
-int mb200_set_stream(mb200_handle_t h, void *cuda_stream) {
-    MB200_CHECK_HANDLE(h);
-    std::lock_guard<std::mutex> lk(h->mu);
-    h->stream = (cudaStream_t)cuda_stream;
-    return MB200_OK;
-}
-
-int mb200_stream_sync(mb200_handle_t h) {
-    MB200_CHECK_HANDLE(h);
-    MB200_CUDA(cudaSetDevice(h->device));
-    MB200_CUDA(cudaStreamSynchronize(h->stream));
-    return MB200_OK;
-}
-
-int mb200_set_path(mb200_handle_t h, int path) {
-    MB200_CHECK_HANDLE(h);
-    if (path < MB200_PATH_AUTO || path > MB200_PATH_TCGEN05_TF32)
-        return fail(MB200_INVALID_ARGUMENT, "unknown path %d", path);
-    std::lock_guard<std::mutex> lk(h->mu);
-    h->forced_path = path;
-    return MB200_OK;
-}
-
-int mb200_malloc(mb200_handle_t h, void **dptr, size_t bytes) {
-    MB200_CHECK_HANDLE(h);
-    if (!dptr) return fail(MB200_INVALID_ARGUMENT, "dptr is NULL");
-    MB200_CUDA(cudaSetDevice(h->device));
-    MB200_CUDA(cudaMalloc(dptr, bytes ? bytes : 1));
-    return MB200_OK;
-}
-
-int mb200_free(mb200_handle_t h, void *dptr) {
-    MB200_CHECK_HANDLE(h);
-    MB200_CUDA(cudaSetDevice(h->device));
-    MB200_CUDA(cudaFree(dptr));
-    return MB200_OK;
-}
-
-int mb200_host_alloc(void **hptr, size_t bytes) {
-    if (!hptr) return fail(MB200_INVALID_ARGUMENT, "hptr is NULL");
-    MB200_CUDA(cudaMallocHost(hptr, bytes ? bytes : 1));
-    return MB200_OK;
-}
-
-int mb200_host_free(void *hptr) {
-    MB200_CUDA(cudaFreeHost(hptr));
-    return MB200_OK;
-}
-
-int mb200_memcpy_h2d(mb200_handle_t h, void *dst, const void *src, size_t bytes) {
-    MB200_CHECK_HANDLE(h);
-    MB200_CUDA(cudaSetDevice(h->device));
-    MB200_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
-    return MB200_OK;
-}
-
-int mb200_memcpy_d2h(mb200_handle_t h, void *dst, const void *src, size_t bytes) {
-    MB200_CHECK_HANDLE(h);
-    MB200_CUDA(cudaSetDevice(h->device));
-    MB200_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
-    return MB200_OK;
-}
-
-int mb200_memset(mb200_handle_t h, void *dptr, int value, size_t bytes) {
-    MB200_CHECK_HANDLE(h);
-    MB200_CUDA(cudaSetDevice(h->device));
-    MB200_CUDA(cudaMemsetAsync(dptr, value, bytes, h->stream));
-    return MB200_OK;
-}
-
-int mb200_binary_einsum(mb200_handle_t h, void *C, int dtypeC, int nmodeC, const int32_t *modesC,
-                        const int64_t *stridesC, const void *A, int dtypeA, int nmodeA, const int32_t *modesA,
-                        const int64_t *extentsA, const int64_t *stridesA, const void *B, int dtypeB, int nmodeB,
-                        const int32_t *modesB, const int64_t *extentsB, const int64_t *stridesB) {
-    MB200_CHECK_HANDLE(h);
-    TensorDesc dA, dB, dC;
-    int st;
-    if ((st = make_desc(dA, dtypeA, nmodeA, modesA, extentsA, stridesA, "A")) != MB200_OK) return st;
-    if ((st = make_desc(dB, dtypeB, nmodeB, modesB, extentsB, stridesB, "B")) != MB200_OK) return st;
-    if ((st = make_c_desc(dC, dtypeC, nmodeC, modesC)) != MB200_OK) return st;
-    std::lock_guard<std::mutex> lk(h->mu);
-    return contract_device(h, C, dC, stridesC, A, dA, B, dB);
-}
-
-int mb200_binary_einsum_host(mb200_handle_t h, void *C, int dtypeC, int nmodeC, const int32_t *modesC,
-                             const void *A, int dtypeA, int nmodeA, const int32_t *modesA,
-                             const int64_t *extentsA, const void *B, int dtypeB, int nmodeB,
-                             const int32_t *modesB, const int64_t *extentsB) {
-    MB200_CHECK_HANDLE(h);
-    TensorDesc dA, dB, dC;
-    int st;
-    if ((st = make_desc(dA, dtypeA, nmodeA, modesA, extentsA, nullptr, "A")) != MB200_OK) return st;
-    if ((st = make_desc(dB, dtypeB, nmodeB, modesB, extentsB, nullptr, "B")) != MB200_OK) return st;
-    if ((st = make_c_desc(dC, dtypeC, nmodeC, modesC)) != MB200_OK) return st;
-    std::lock_guard<std::mutex> lk(h->mu);
-    {   // validate before touching the device so argument errors do not depend on a GPU
-        Plan probe;
-        TensorDesc tmp = dC;
-        if ((st = make_plan(dA, dB, tmp, nullptr, h->forced_path, probe)) != MB200_OK) return st;
-        dC = tmp;
-    }
-    MB200_CUDA(cudaSetDevice(h->device));
-    cudaStream_t s = h->stream;
-    const size_t bA = (size_t)dA.numel() * dtype_size(dA.dtype);
-    const size_t bB = (size_t)dB.numel() * dtype_size(dB.dtype);
-    const size_t bC = (size_t)dC.numel() * dtype_size(dC.dtype);
-    if (bC == 0) return MB200_OK;
-    if (!C || (!A && bA) || (!B && bB)) return fail(MB200_INVALID_ARGUMENT, "NULL data pointer");
-    void *dAp = nullptr, *dBp = nullptr, *dCp = nullptr;
-    MB200_CUDA(cudaMallocAsync(&dAp, bA ? bA : 1, s));
-    MB200_CUDA(cudaMallocAsync(&dBp, bB ? bB : 1, s));
-    MB200_CUDA(cudaMallocAsync(&dCp, bC, s));
-    if (bA) MB200_CUDA(cudaMemcpyAsync(dAp, A, bA, cudaMemcpyHostToDevice, s));
-    if (bB) MB200_CUDA(cudaMemcpyAsync(dBp, B, bB, cudaMemcpyHostToDevice, s));
-    st = contract_device(h, dCp, dC, nullptr, dAp, dA, dBp, dB);
-    if (st == MB200_OK) {
-        cudaError_t e = cudaMemcpyAsync(C, dCp, bC, cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-        if (e != cudaSuccess) st = cuda_fail(e, "device-to-host copy of C");
-    }
-    cudaFreeAsync(dAp, s);
-    cudaFreeAsync(dBp, s);
-    cudaFreeAsync(dCp, s);
-    return st;
-}
-
-int mb200_plan_describe(int dtypeC, int nmodeC, const int32_t *modesC, const int64_t *stridesC, int dtypeA,
-                        int nmodeA, const int32_t *modesA, const int64_t *extentsA, const int64_t *stridesA,
-                        int dtypeB, int nmodeB, const int32_t *modesB, const int64_t *extentsB,
-                        const int64_t *stridesB, mb200_plan_info_t *info) {
-    if (!info) return fail(MB200_INVALID_ARGUMENT, "info is NULL");
-    TensorDesc dA, dB, dC;
-    int st;
-    if ((st = make_desc(dA, dtypeA, nmodeA, modesA, extentsA, stridesA, "A")) != MB200_OK) return st;
-    if ((st = make_desc(dB, dtypeB, nmodeB, modesB, extentsB, stridesB, "B")) != MB200_OK) return st;
-    if ((st = make_c_desc(dC, dtypeC, nmodeC, modesC)) != MB200_OK) return st;
-    Plan plan;
-    if ((st = make_plan(dA, dB, dC, stridesC, MB200_PATH_AUTO, plan)) != MB200_OK) return st;
-    fill_info(plan, info);
-    return MB200_OK;
-}
-
-int mb200_permute(mb200_handle_t h, void *dst, const void *src, int dtype, int nmode, const int64_t *extents,
-                  const int32_t *perm, uint32_t flags) {
-    MB200_CHECK_HANDLE(h);
-    if (!dtype_valid(dtype)) return fail(MB200_INVALID_ARGUMENT, "unknown dtype %d", dtype);
-    if (nmode < 0 || nmode > MB200_MAX_MODES) return fail(MB200_INVALID_ARGUMENT, "nmode %d out of range", nmode);
-    if (nmode > 0 && (!extents || !perm)) return fail(MB200_INVALID_ARGUMENT, "extents/perm are NULL");
-    bool seen[MB200_MAX_MODES] = {false};
-    for (int d = 0; d < nmode; d++) {
-        if (perm[d] < 0 || perm[d] >= nmode || seen[perm[d]])
-            return fail(MB200_INVALID_ARGUMENT, "perm is not a permutation of 0..%d", nmode - 1);
-        seen[perm[d]] = true;
-        if (extents[d] < 0) return fail(MB200_INVALID_ARGUMENT, "negative extent");
-    }
-    if ((flags & MB200_PERMUTE_PLANAR) && !dtype_is_complex(dtype))
-        return fail(MB200_INVALID_ARGUMENT, "planar output needs a complex dtype");
-    // destination stride of every source mode
-    int64_t dstride_src[MB200_MAX_MODES];
-    int64_t st = 1, total = 1;
-    for (int d = 0; d < nmode; d++) {
-        dstride_src[perm[d]] = st;
-        st *= extents[perm[d]];
-    }
-    for (int i = 0; i < nmode; i++) total *= extents[i];
-    if (total == 0) return MB200_OK;
-    if (!dst || !src) return fail(MB200_INVALID_ARGUMENT, "NULL data pointer");
-    // canonical form: drop extent-1 modes, merge modes adjacent in both layouts
-    PermuteParams q{};
-    for (int i = 0; i < nmode; i++) {
-        if (extents[i] == 1) continue;
-        if (q.n > 0 && dstride_src[i] == q.dst_stride[q.n - 1] * q.ext[q.n - 1]) {
-            q.ext[q.n - 1] *= extents[i];
-        } else {
-            q.ext[q.n] = extents[i];
-            q.dst_stride[q.n] = dstride_src[i];
-            q.n++;
-        }
-    }
-    q.total = total;
-    q.plane_stride = (flags & MB200_PERMUTE_PLANAR) ? total : 0;
-    std::lock_guard<std::mutex> lk(h->mu);
-    MB200_CUDA(cudaSetDevice(h->device));
-    MB200_CUDA(launch_permute(dtype, q, src, dst, h->stream));
-    h->stats.launches_permute++;
-    h->stats.launches_total++;
-    return MB200_OK;
-}
-
-int mb200_unary_einsum(mb200_handle_t h, void *Y, int dtypeY, int nmodeY, const int32_t *modesY, const int64_t *stridesY,
-                       const void *X, int dtypeX, int nmodeX, const int32_t *modesX, const int64_t *extentsX,
-                       const int64_t *stridesX) {
-    MB200_CHECK_HANDLE(h);
+// unary_einsum with the handle's mutex already held (also the pre-reduce step of binary_einsum)
+static int unary_locked(mb200_handle_t h, void *Y, int dtypeY, int nmodeY, const int32_t *modesY, const int64_t *stridesY,
+                        const void *X, int dtypeX, int nmodeX, const int32_t *modesX, const int64_t *extentsX,
+                        const int64_t *stridesX) {
     if (!dtype_valid(dtypeX) || dtypeY != dtypeX)
         return fail(MB200_INVALID_ARGUMENT, "unary_einsum: eltype(y) must equal eltype(x)");
     if (nmodeX < 0 || nmodeX > MB200_MAX_MODES || nmodeY < 0 || nmodeY > MB200_MAX_MODES)
@@ -727,7 +563,6 @@ int mb200_unary_einsum(mb200_handle_t h, void *Y, int dtypeY, int nmodeY, const 
             p.k_ext[p.nk] = l.ext; p.k_sx[p.nk] = l.sx; p.nk++;
         }
     }
-    std::lock_guard<std::mutex> lk(h->mu);
     MB200_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
     // no reduction, no diagonal, dense operands: a plain permutation -> K1
@@ -759,6 +594,350 @@ int mb200_unary_einsum(mb200_handle_t h, void *Y, int dtypeY, int nmodeY, const 
     h->stats.launches_unary += nsplit > 1 ? 2 : 1;
     h->stats.launches_total += nsplit > 1 ? 2 : 1;
     return MB200_OK;
+}
+
+// binary_einsum with modes that one operand carries and C does not ("dangling": cuTENSOR / OMEinsum semantics - they are
+// summed; ext/MuscleCUDAExt.jl:30-38, ext/MuscleOMEinsumExt.jl:40-59). Extent-1 dangling modes are dropped from the
+// descriptor. Launch-bound sizes (<= 2^20 MACs with the dangling extents counted) FOLD the sum into the contraction: the
+// mode is handed to the planner as a summed mode that the other operand carries with stride 0 (a broadcast), one direct
+// kernel launch, no temporary. Larger operands are pre-reduced by one HBM-bound unary_einsum pass (|X| read once) and the
+// contraction then runs on the smaller tensor - ext(x) times fewer tensor-core flops than folding.
+static int contract_entry(mb200_handle_t h, void *C, TensorDesc &dC, const int64_t *stridesC, const void *A, TensorDesc dA,
+                          const void *B, TensorDesc dB, const ScatterDesc *sc = nullptr) {
+    std::vector<int> da = dangling_modes(dA, dB, dC), db = dangling_modes(dB, dA, dC);
+    if (da.empty() && db.empty()) return contract_device(h, C, dC, stridesC, A, dA, B, dB, sc);
+    // extent-1 dangling modes never move an address
+    auto drop_unit = [](TensorDesc &T, std::vector<int> &d) {
+        std::vector<int> unit;
+        for (int i : d)
+            if (T.ext[i] == 1) unit.push_back(i);
+        if (unit.empty()) return;
+        T = without_modes(T, unit, false);
+    };
+    drop_unit(dA, da);
+    drop_unit(dB, db);
+    da = dangling_modes(dA, dB, dC);
+    db = dangling_modes(dB, dA, dC);
+    if (da.empty() && db.empty()) return contract_device(h, C, dC, stridesC, A, dA, B, dB, sc);
+
+    double macs = 1.0;
+    {
+        std::vector<int32_t> seen;
+        for (const TensorDesc *t : {&dA, &dB})
+            for (int i = 0; i < t->n; i++)
+                if (std::find(seen.begin(), seen.end(), t->modes[i]) == seen.end()) {
+                    seen.push_back(t->modes[i]);
+                    macs *= (double)t->ext[i];
+                }
+    }
+    const bool room = dA.n + (int)db.size() <= MB200_MAX_MODES && dB.n + (int)da.size() <= MB200_MAX_MODES;
+    if (macs <= (double)(1 << 20) && !sc && room) {
+        TensorDesc fa = dA, fb = dB;
+        for (int i : da) { fb.modes[fb.n] = dA.modes[i]; fb.ext[fb.n] = dA.ext[i]; fb.stride[fb.n] = 0; fb.n++; }
+        for (int i : db) { fa.modes[fa.n] = dB.modes[i]; fa.ext[fa.n] = dB.ext[i]; fa.stride[fa.n] = 0; fa.n++; }
+        const int saved = h->forced_path;
+        h->forced_path = MB200_PATH_DIRECT;
+        int st = contract_device(h, C, dC, stridesC, A, fa, B, fb, nullptr);
+        h->forced_path = saved;
+        return st;
+    }
+    cudaStream_t s = h->stream;
+    void *tmpA = nullptr, *tmpB = nullptr;
+    int st = MB200_OK;
+    auto prereduce = [&](const void *&X, TensorDesc &dX, const std::vector<int> &drop, void *&tmp) -> int {
+        if (drop.empty()) return MB200_OK;
+        TensorDesc dY = without_modes(dX, drop, true);
+        if (dY.numel() == 0) { dX = dY; return MB200_OK; }
+        cudaError_t e = cudaSetDevice(h->device);
+        if (e == cudaSuccess) e = cudaMallocAsync(&tmp, (size_t)dY.numel() * dtype_size(dY.dtype), s);
+        if (e != cudaSuccess) return cuda_fail(e, "pre-reduce workspace");
+        int r = unary_locked(h, tmp, dY.dtype, dY.n, dY.modes, nullptr, X, dX.dtype, dX.n, dX.modes, dX.ext, dX.stride);
+        if (r != MB200_OK) return r;
+        X = tmp;
+        dX = dY;
+        return MB200_OK;
+    };
+    st = prereduce(A, dA, da, tmpA);
+    if (st == MB200_OK) st = prereduce(B, dB, db, tmpB);
+    if (st == MB200_OK) st = contract_device(h, C, dC, stridesC, A, dA, B, dB, sc);
+    if (tmpA) cudaFreeAsync(tmpA, s);
+    if (tmpB) cudaFreeAsync(tmpB, s);
+    return st;
+}
+
+// descriptors as the planner sees them: dangling modes already summed away (introspection / host-side validation)
+static void strip_dangling_for_plan(TensorDesc &dA, TensorDesc &dB, const TensorDesc &dC) {
+    std::vector<int> da = dangling_modes(dA, dB, dC), db = dangling_modes(dB, dA, dC);
+    if (!da.empty()) dA = without_modes(dA, da, true);
+    if (!db.empty()) dB = without_modes(dB, db, true);
+}
+
+extern "C" {
+
+int mb200_version(void) { return 100; }
+
+const char *mb200_last_error_string(void) { return last_error().c_str(); }
+
+int mb200_device_count(int *count) {
+    if (!count) return fail(MB200_INVALID_ARGUMENT, "count is NULL");
+    *count = 0;
+    MB200_CUDA(cudaGetDeviceCount(count));
+    return MB200_OK;
+}
+
+int mb200_create(mb200_handle_t *handle, int device) {
+    if (!handle) return fail(MB200_INVALID_ARGUMENT, "handle is NULL");
+    *handle = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(MB200_CUDA_ERROR, "no usable CUDA device (%s); libmuscle_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(MB200_INVALID_ARGUMENT, "device %d outside [0, %d)", device, n);
+    MB200_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    MB200_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(MB200_NOT_SUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                    device, prop.major, prop.minor);
+    MB200_CUDA(gett_configure());
+    MB200_CUDA(permute_configure());
+    MB200_CUDA(tf32_configure());
+    // keep stream-ordered temporaries cached in the pool instead of returning them to the OS
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    auto *h = new mb200_handle_s();
+    h->device = device;
+    *handle = h;
+    return MB200_OK;
+}
+
+int mb200_destroy(mb200_handle_t h) {
+    MB200_CHECK_HANDLE(h);
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    if (h->side) { cudaStreamDestroy(h->side); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); }
+    delete h;   // cached plans free their tables unless a captured graph still holds them
+    return MB200_OK;
+}
+
+int mb200_set_stream(mb200_handle_t h, void *cuda_stream) {
+    MB200_CHECK_HANDLE(h);
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->stream = (cudaStream_t)cuda_stream;
+    return MB200_OK;
+}
+
+int mb200_stream_sync(mb200_handle_t h) {
+    MB200_CHECK_HANDLE(h);
+    MB200_CUDA(cudaSetDevice(h->device));
+    MB200_CUDA(cudaStreamSynchronize(h->stream));
+    return MB200_OK;
+}
+
+int mb200_set_path(mb200_handle_t h, int path) {
+    MB200_CHECK_HANDLE(h);
+    if (path < MB200_PATH_AUTO || path > MB200_PATH_TCGEN05_TF32)
+        return fail(MB200_INVALID_ARGUMENT, "unknown path %d", path);
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->forced_path = path;
+    return MB200_OK;
+}
+
+int mb200_set_compute_type(mb200_handle_t h, int compute_type) {
+    MB200_CHECK_HANDLE(h);
+    if (compute_type < MB200_COMPUTE_DEFAULT || compute_type > MB200_COMPUTE_3XTF32)
+        return fail(MB200_INVALID_ARGUMENT, "unknown compute type %d", compute_type);
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->compute_type = compute_type;
+    return MB200_OK;
+}
+
+int mb200_get_compute_type(mb200_handle_t h, int *compute_type) {
+    MB200_CHECK_HANDLE(h);
+    if (!compute_type) return fail(MB200_INVALID_ARGUMENT, "compute_type is NULL");
+    std::lock_guard<std::mutex> lk(h->mu);
+    *compute_type = h->compute_type;
+    return MB200_OK;
+}
+
+int mb200_malloc(mb200_handle_t h, void **dptr, size_t bytes) {
+    MB200_CHECK_HANDLE(h);
+    if (!dptr) return fail(MB200_INVALID_ARGUMENT, "dptr is NULL");
+    MB200_CUDA(cudaSetDevice(h->device));
+    MB200_CUDA(cudaMalloc(dptr, bytes ? bytes : 1));
+    return MB200_OK;
+}
+
+int mb200_free(mb200_handle_t h, void *dptr) {
+    MB200_CHECK_HANDLE(h);
+    MB200_CUDA(cudaSetDevice(h->device));
+    MB200_CUDA(cudaFree(dptr));
+    return MB200_OK;
+}
+
+int mb200_host_alloc(void **hptr, size_t bytes) {
+    if (!hptr) return fail(MB200_INVALID_ARGUMENT, "hptr is NULL");
+    MB200_CUDA(cudaMallocHost(hptr, bytes ? bytes : 1));
+    return MB200_OK;
+}
+
+int mb200_host_free(void *hptr) {
+    MB200_CUDA(cudaFreeHost(hptr));
+    return MB200_OK;
+}
+
+int mb200_memcpy_h2d(mb200_handle_t h, void *dst, const void *src, size_t bytes) {
+    MB200_CHECK_HANDLE(h);
+    MB200_CUDA(cudaSetDevice(h->device));
+    MB200_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    return MB200_OK;
+}
+
+int mb200_memcpy_d2h(mb200_handle_t h, void *dst, const void *src, size_t bytes) {
+    MB200_CHECK_HANDLE(h);
+    MB200_CUDA(cudaSetDevice(h->device));
+    MB200_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+    return MB200_OK;
+}
+
+int mb200_memset(mb200_handle_t h, void *dptr, int value, size_t bytes) {
+    MB200_CHECK_HANDLE(h);
+    MB200_CUDA(cudaSetDevice(h->device));
+    MB200_CUDA(cudaMemsetAsync(dptr, value, bytes, h->stream));
+    return MB200_OK;
+}
+
+int mb200_binary_einsum(mb200_handle_t h, void *C, int dtypeC, int nmodeC, const int32_t *modesC,
+                        const int64_t *stridesC, const void *A, int dtypeA, int nmodeA, const int32_t *modesA,
+                        const int64_t *extentsA, const int64_t *stridesA, const void *B, int dtypeB, int nmodeB,
+                        const int32_t *modesB, const int64_t *extentsB, const int64_t *stridesB) {
+    MB200_CHECK_HANDLE(h);
+    TensorDesc dA, dB, dC;
+    int st;
+    if ((st = make_desc(dA, dtypeA, nmodeA, modesA, extentsA, stridesA, "A")) != MB200_OK) return st;
+    if ((st = make_desc(dB, dtypeB, nmodeB, modesB, extentsB, stridesB, "B")) != MB200_OK) return st;
+    if ((st = make_c_desc(dC, dtypeC, nmodeC, modesC)) != MB200_OK) return st;
+    std::lock_guard<std::mutex> lk(h->mu);
+    return contract_entry(h, C, dC, stridesC, A, dA, B, dB);
+}
+
+int mb200_binary_einsum_host(mb200_handle_t h, void *C, int dtypeC, int nmodeC, const int32_t *modesC,
+                             const void *A, int dtypeA, int nmodeA, const int32_t *modesA,
+                             const int64_t *extentsA, const void *B, int dtypeB, int nmodeB,
+                             const int32_t *modesB, const int64_t *extentsB) {
+    MB200_CHECK_HANDLE(h);
+    TensorDesc dA, dB, dC;
+    int st;
+    if ((st = make_desc(dA, dtypeA, nmodeA, modesA, extentsA, nullptr, "A")) != MB200_OK) return st;
+    if ((st = make_desc(dB, dtypeB, nmodeB, modesB, extentsB, nullptr, "B")) != MB200_OK) return st;
+    if ((st = make_c_desc(dC, dtypeC, nmodeC, modesC)) != MB200_OK) return st;
+    std::lock_guard<std::mutex> lk(h->mu);
+    {   // validate before touching the device so argument errors do not depend on a GPU
+        Plan probe;
+        TensorDesc tmp = dC, pa = dA, pb = dB;
+        strip_dangling_for_plan(pa, pb, dC);
+        if ((st = make_plan(pa, pb, tmp, nullptr, h->forced_path, probe)) != MB200_OK) return st;
+        dC = tmp;
+    }
+    MB200_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const size_t bA = (size_t)dA.numel() * dtype_size(dA.dtype);
+    const size_t bB = (size_t)dB.numel() * dtype_size(dB.dtype);
+    const size_t bC = (size_t)dC.numel() * dtype_size(dC.dtype);
+    if (bC == 0) return MB200_OK;
+    if (!C || (!A && bA) || (!B && bB)) return fail(MB200_INVALID_ARGUMENT, "NULL data pointer");
+    void *dAp = nullptr, *dBp = nullptr, *dCp = nullptr;
+    MB200_CUDA(cudaMallocAsync(&dAp, bA ? bA : 1, s));
+    MB200_CUDA(cudaMallocAsync(&dBp, bB ? bB : 1, s));
+    MB200_CUDA(cudaMallocAsync(&dCp, bC, s));
+    if (bA) MB200_CUDA(cudaMemcpyAsync(dAp, A, bA, cudaMemcpyHostToDevice, s));
+    if (bB) MB200_CUDA(cudaMemcpyAsync(dBp, B, bB, cudaMemcpyHostToDevice, s));
+    st = contract_entry(h, dCp, dC, nullptr, dAp, dA, dBp, dB);
+    if (st == MB200_OK) {
+        cudaError_t e = cudaMemcpyAsync(C, dCp, bC, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) st = cuda_fail(e, "device-to-host copy of C");
+    }
+    cudaFreeAsync(dAp, s);
+    cudaFreeAsync(dBp, s);
+    cudaFreeAsync(dCp, s);
+    return st;
+}
+
+int mb200_plan_describe(int dtypeC, int nmodeC, const int32_t *modesC, const int64_t *stridesC, int dtypeA,
+                        int nmodeA, const int32_t *modesA, const int64_t *extentsA, const int64_t *stridesA,
+                        int dtypeB, int nmodeB, const int32_t *modesB, const int64_t *extentsB,
+                        const int64_t *stridesB, mb200_plan_info_t *info) {
+    if (!info) return fail(MB200_INVALID_ARGUMENT, "info is NULL");
+    TensorDesc dA, dB, dC;
+    int st;
+    if ((st = make_desc(dA, dtypeA, nmodeA, modesA, extentsA, stridesA, "A")) != MB200_OK) return st;
+    if ((st = make_desc(dB, dtypeB, nmodeB, modesB, extentsB, stridesB, "B")) != MB200_OK) return st;
+    if ((st = make_c_desc(dC, dtypeC, nmodeC, modesC)) != MB200_OK) return st;
+    Plan plan;
+    strip_dangling_for_plan(dA, dB, dC);   // the plan of the contraction that runs after the dangling modes are summed
+    if ((st = make_plan(dA, dB, dC, stridesC, MB200_PATH_AUTO, plan)) != MB200_OK) return st;
+    fill_info(plan, info);
+    return MB200_OK;
+}
+
+int mb200_permute(mb200_handle_t h, void *dst, const void *src, int dtype, int nmode, const int64_t *extents,
+                  const int32_t *perm, uint32_t flags) {
+    MB200_CHECK_HANDLE(h);
+    if (!dtype_valid(dtype)) return fail(MB200_INVALID_ARGUMENT, "unknown dtype %d", dtype);
+    if (nmode < 0 || nmode > MB200_MAX_MODES) return fail(MB200_INVALID_ARGUMENT, "nmode %d out of range", nmode);
+    if (nmode > 0 && (!extents || !perm)) return fail(MB200_INVALID_ARGUMENT, "extents/perm are NULL");
+    bool seen[MB200_MAX_MODES] = {false};
+    for (int d = 0; d < nmode; d++) {
+        if (perm[d] < 0 || perm[d] >= nmode || seen[perm[d]])
+            return fail(MB200_INVALID_ARGUMENT, "perm is not a permutation of 0..%d", nmode - 1);
+        seen[perm[d]] = true;
+        if (extents[d] < 0) return fail(MB200_INVALID_ARGUMENT, "negative extent");
+    }
+    if ((flags & MB200_PERMUTE_PLANAR) && !dtype_is_complex(dtype))
+        return fail(MB200_INVALID_ARGUMENT, "planar output needs a complex dtype");
+    // destination stride of every source mode
+    int64_t dstride_src[MB200_MAX_MODES];
+    int64_t st = 1, total = 1;
+    for (int d = 0; d < nmode; d++) {
+        dstride_src[perm[d]] = st;
+        st *= extents[perm[d]];
+    }
+    for (int i = 0; i < nmode; i++) total *= extents[i];
+    if (total == 0) return MB200_OK;
+    if (!dst || !src) return fail(MB200_INVALID_ARGUMENT, "NULL data pointer");
+    // canonical form: drop extent-1 modes, merge modes adjacent in both layouts
+    PermuteParams q{};
+    for (int i = 0; i < nmode; i++) {
+        if (extents[i] == 1) continue;
+        if (q.n > 0 && dstride_src[i] == q.dst_stride[q.n - 1] * q.ext[q.n - 1]) {
+            q.ext[q.n - 1] *= extents[i];
+        } else {
+            q.ext[q.n] = extents[i];
+            q.dst_stride[q.n] = dstride_src[i];
+            q.n++;
+        }
+    }
+    q.total = total;
+    q.plane_stride = (flags & MB200_PERMUTE_PLANAR) ? total : 0;
+    std::lock_guard<std::mutex> lk(h->mu);
+    MB200_CUDA(cudaSetDevice(h->device));
+    MB200_CUDA(launch_permute(dtype, q, src, dst, h->stream));
+    h->stats.launches_permute++;
+    h->stats.launches_total++;
+    return MB200_OK;
+}
+
+int mb200_unary_einsum(mb200_handle_t h, void *Y, int dtypeY, int nmodeY, const int32_t *modesY, const int64_t *stridesY,
+                       const void *X, int dtypeX, int nmodeX, const int32_t *modesX, const int64_t *extentsX,
+                       const int64_t *stridesX) {
+    MB200_CHECK_HANDLE(h);
+    std::lock_guard<std::mutex> lk(h->mu);
+    return unary_locked(h, Y, dtypeY, nmodeY, modesY, stridesY, X, dtypeX, nmodeX, modesX, extentsX, stridesX);
 }
 
 int mb200_hadamard(mb200_handle_t h, void *Cp, int dtypeC, const void *A, int dtypeA, int nmodeA, const int32_t *modesA,
@@ -997,7 +1176,66 @@ int mb200_binary_einsum_scatter(mb200_handle_t h, int dtypeC, int nmodeC, const 
     if ((st = make_desc(dB, dtypeB, nmodeB, modesB, extentsB, stridesB, "B")) != MB200_OK) return st;
     if ((st = make_c_desc(dC, dtypeC, nmodeC, modesC)) != MB200_OK) return st;
     std::lock_guard<std::mutex> lk(h->mu);
-    return contract_device(h, nullptr, dC, nullptr, A, dA, B, dB, &sc);
+    return contract_entry(h, nullptr, dC, nullptr, A, dA, B, dB, &sc);
+}
+
+static int make_dist(DistDesc &d, const mb200_comm_t *comm) {
+    if (!comm) return fail(MB200_INVALID_ARGUMENT, "comm is NULL");
+    if (comm->nranks < 1 || comm->nranks > MB200_MAX_PEERS || comm->rank < 0 || comm->rank >= comm->nranks)
+        return fail(MB200_INVALID_ARGUMENT, "bad comm: rank %d of %d", comm->rank, comm->nranks);
+    if (comm->epoch < 1) return fail(MB200_INVALID_ARGUMENT, "comm.epoch must be >= 1 and increase from call to call");
+    d = DistDesc{};
+    d.nranks = comm->nranks; d.rank = comm->rank; d.epoch = comm->epoch;
+    for (int r = 0; r < comm->nranks; r++) {
+        if (!comm->ws[r] || !comm->c[r] || !comm->flags[r]) return fail(MB200_INVALID_ARGUMENT, "comm: NULL buffer of rank %d", r);
+        d.ws[r] = comm->ws[r]; d.c[r] = comm->c[r]; d.flags[r] = (int *)comm->flags[r];
+    }
+    if ((comm->mc_ws == nullptr) != (comm->mc_c == nullptr))
+        return fail(MB200_INVALID_ARGUMENT, "comm: mc_ws and mc_c must both be set or both be NULL");
+    d.mc_ws = comm->mc_ws; d.mc_c = comm->mc_c;
+    return MB200_OK;
+}
+
+int mb200_allreduce_workspace(mb200_handle_t h, int dtypeC, int nmodeC, const int32_t *modesC,
+                              int dtypeA, int nmodeA, const int32_t *modesA, const int64_t *extentsA,
+                              int dtypeB, int nmodeB, const int32_t *modesB, const int64_t *extentsB,
+                              int nranks, size_t *ws_bytes, size_t *flag_bytes) {
+    MB200_CHECK_HANDLE(h);
+    if (!ws_bytes || !flag_bytes || nranks < 1 || nranks > MB200_MAX_PEERS) return fail(MB200_INVALID_ARGUMENT, "bad arguments");
+    TensorDesc dA, dB, dC;
+    int st;
+    if ((st = make_desc(dA, dtypeA, nmodeA, modesA, extentsA, nullptr, "A")) != MB200_OK) return st;
+    if ((st = make_desc(dB, dtypeB, nmodeB, modesB, extentsB, nullptr, "B")) != MB200_OK) return st;
+    if ((st = make_c_desc(dC, dtypeC, nmodeC, modesC)) != MB200_OK) return st;
+    std::lock_guard<std::mutex> lk(h->mu);
+    Plan plan;
+    if ((st = make_plan(dA, dB, dC, nullptr, h->forced_path, plan)) != MB200_OK) return st;
+    if (h->compute_type == MB200_COMPUTE_FP32 || plan.path != MB200_PATH_TCGEN05_TF32 || plan.empty_output)
+        return fail(MB200_NOT_SUPPORTED, "the fused all-reduce runs on the ComplexF32 / Float32 tcgen05 path (this contraction is "
+                                         "planned on path %d); use an NCCL all-reduce of the partial outputs", plan.path);
+    const DistGeometry geo = tf32_dist_geometry(plan.dtype, plan.M, plan.N, plan.L);
+    *ws_bytes = (size_t)geo.nunits * geo.unit_elems * dtype_size(plan.dtype);
+    *flag_bytes = ((size_t)geo.nunits * nranks + nranks + 1) * sizeof(int);
+    return MB200_OK;
+}
+
+int mb200_binary_einsum_allreduce(mb200_handle_t h, int dtypeC, int nmodeC, const int32_t *modesC,
+                                  const void *A, int dtypeA, int nmodeA, const int32_t *modesA, const int64_t *extentsA,
+                                  const int64_t *stridesA,
+                                  const void *B, int dtypeB, int nmodeB, const int32_t *modesB, const int64_t *extentsB,
+                                  const int64_t *stridesB, const mb200_comm_t *comm, int phases) {
+    MB200_CHECK_HANDLE(h);
+    if (phases < 1 || phases > 7) return fail(MB200_INVALID_ARGUMENT, "phases must be a non-empty subset of MB200_DIST_*");
+    DistDesc d;
+    int st;
+    if ((st = make_dist(d, comm)) != MB200_OK) return st;
+    TensorDesc dA, dB, dC;
+    if ((st = make_desc(dA, dtypeA, nmodeA, modesA, extentsA, stridesA, "A")) != MB200_OK) return st;
+    if ((st = make_desc(dB, dtypeB, nmodeB, modesB, extentsB, stridesB, "B")) != MB200_OK) return st;
+    if ((st = make_c_desc(dC, dtypeC, nmodeC, modesC)) != MB200_OK) return st;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->capturing) return fail(MB200_NOT_SUPPORTED, "the fused all-reduce cannot be captured into a graph");
+    return contract_device(h, nullptr, dC, nullptr, A, dA, B, dB, nullptr, &d, phases, comm->ws_bytes, comm->flag_bytes);
 }
 
 int mb200_reduce_slots(mb200_handle_t h, void *out, const void *staging_local, int dtype, int64_t slab_elems, int nslots) {
@@ -1021,6 +1259,7 @@ int mb200_graph_begin(mb200_handle_t h) {
     MB200_CUDA(cudaSetDevice(h->device));
     MB200_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
     h->capturing = true;
+    h->captured.clear();
     return MB200_OK;
 }
 
@@ -1034,6 +1273,7 @@ int mb200_graph_end(mb200_handle_t h, mb200_graph_t *graph) {
     MB200_CUDA(cudaSetDevice(h->device));
     auto g = std::make_unique<mb200_graph_s>();
     g->device = h->device;
+    g->plans.swap(h->captured);
     MB200_CUDA(cudaStreamEndCapture(h->stream, &g->graph));
     cudaError_t e = cudaGraphInstantiate(&g->exec, g->graph, 0);
     if (e != cudaSuccess) {
@@ -1059,7 +1299,7 @@ int mb200_graph_destroy(mb200_graph_t g) {
     cudaSetDevice(g->device);
     if (g->exec) cudaGraphExecDestroy(g->exec);
     if (g->graph) cudaGraphDestroy(g->graph);
-    delete g;
+    delete g;   // releases its plans; tables of plans already evicted from their handle's cache are freed here
     return MB200_OK;
 }
 

@@ -138,6 +138,29 @@ bool tf32_available();
 // mixed: operands are in the TF32 + BF16 format (split 2 / 3), else 3xTF32 (split 1); *pair (optional) reports whether the
 // CTA-pair kernel (cta_group::2, 256-row tiles) was launched
 cudaError_t launch_tf32_gemm(int dtype, const void *packA, const void *packB, const GettParams &g, bool mixed, cudaStream_t s,
-                             bool *pair = nullptr);
+                             bool *pair = nullptr, const struct DistDesc *dist = nullptr);
+
+// ---- cross-GPU split-K: summed-index slice with the all-reduce fused into the contraction (tf32.cu) -----------------------
+// Every rank contracts its K-slice into PARTIAL tiles, stored tile-linear (unit = one CTA's 128 x BN sub-tile, row fastest)
+// in its own workspace ws[rank]; the epilogue then raises flag[unit][rank] in the flag array of the unit's OWNER
+// (owner = unit % nranks) with a system-scope release store. The owner's reducer kernel - running concurrently with the
+// GEMM on a second stream - waits for the nranks flags of each unit it owns, adds the nranks partial sub-tiles in rank
+// order (peer loads over NVLink, or ONE multimem.ld_reduce through an NVLS multicast mapping: the switch adds), and stores
+// the finished sub-tile through the rowC / colC / batC tables into the C of EVERY rank (peer stores, or one multimem.st).
+// When its last unit is done it raises done[rank] on every rank; a rank's C is complete when all nranks done flags have
+// arrived (wait_done kernel). All ranks end with bit-identical C. Flag array layout (int32): [nunits * nranks] unit flags,
+// [nranks] done flags, [1] CTA counter; flags carry the call's epoch (strictly increasing), so nothing is ever reset.
+struct DistDesc {
+    int nranks, rank, epoch;
+    void *ws[MB200_MAX_PEERS];     // partial-tile workspace of every rank (peer mappings; [rank] = own)
+    void *c[MB200_MAX_PEERS];      // output C of every rank (peer mappings; [rank] = own)
+    int *flags[MB200_MAX_PEERS];   // flag array of every rank
+    void *mc_ws, *mc_c;            // NVLS multicast mappings of ws / c, or NULL
+};
+struct DistGeometry { int BN; int pair; int64_t nunits; int64_t unit_elems; };   // unit_elems = 128 * BN
+// geometry of the dist-mode GEMM for a (dtype, M, N, L) problem: which kernel variant runs, how many units it produces
+DistGeometry tf32_dist_geometry(int dtype, int64_t M, int64_t N, int64_t L);
+cudaError_t launch_tf32_allreduce(int dtype, const GettParams &g, const DistDesc &dist, cudaStream_t s);
+cudaError_t launch_dist_wait_done(const DistDesc &dist, int64_t nunits, cudaStream_t s);
 
 }  // namespace mb200

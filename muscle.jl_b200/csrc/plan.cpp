@@ -63,6 +63,29 @@ static int find_mode(const TensorDesc &t, int32_t m) {
     return -1;
 }
 
+std::vector<int> dangling_modes(const TensorDesc &T, const TensorDesc &other, const TensorDesc &C) {
+    std::vector<int> out;
+    for (int i = 0; i < T.n; i++)
+        if (find_mode(other, T.modes[i]) < 0 && find_mode(C, T.modes[i]) < 0) out.push_back(i);
+    return out;
+}
+
+TensorDesc without_modes(const TensorDesc &T, const std::vector<int> &drop, bool redense) {
+    TensorDesc r;
+    r.dtype = T.dtype;
+    r.n = 0;
+    int64_t s = 1;
+    for (int i = 0; i < T.n; i++) {
+        if (std::find(drop.begin(), drop.end(), i) != drop.end()) continue;
+        r.modes[r.n] = T.modes[i];
+        r.ext[r.n] = T.ext[i];
+        r.stride[r.n] = redense ? s : T.stride[i];
+        s *= T.ext[i];
+        r.n++;
+    }
+    return r;
+}
+
 int make_plan(const TensorDesc &A, const TensorDesc &B, TensorDesc &C, const int64_t *stridesC,
               int forced_path, Plan &plan) {
     // ---- validation -------------------------------------------------------------------------
@@ -80,14 +103,14 @@ int make_plan(const TensorDesc &A, const TensorDesc &B, TensorDesc &C, const int
                         (int)A.modes[i], (long long)A.ext[i], (long long)B.ext[j]);
         if (j < 0 && find_mode(C, A.modes[i]) < 0)
             return fail(MB200_INVALID_ARGUMENT,
-                        "mode %d appears only in A and not in the output (a free index missing from C is "
-                        "rejected, as by BackendBase)", (int)A.modes[i]);
+                        "internal: mode %d appears only in A and not in the output (dangling modes are summed by "
+                        "the entry points before planning)", (int)A.modes[i]);
     }
     for (int i = 0; i < B.n; i++)
         if (find_mode(A, B.modes[i]) < 0 && find_mode(C, B.modes[i]) < 0)
             return fail(MB200_INVALID_ARGUMENT,
-                        "mode %d appears only in B and not in the output (a free index missing from C is "
-                        "rejected, as by BackendBase)", (int)B.modes[i]);
+                        "internal: mode %d appears only in B and not in the output (dangling modes are summed by "
+                        "the entry points before planning)", (int)B.modes[i]);
     // C extents are implied by A / B
     {
         int64_t s = 1;

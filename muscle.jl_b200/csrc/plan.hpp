@@ -70,6 +70,13 @@ int make_plan(const TensorDesc &A, const TensorDesc &B, TensorDesc &C, const int
 
 void fill_info(const Plan &plan, mb200_plan_info_t *info);
 
+// "Dangling" modes: carried by ONE operand and absent from C. cuTENSOR.contract! (ext/MuscleCUDAExt.jl:30-38) and
+// OMEinsum (ext/MuscleOMEinsumExt.jl:40-59) sum them; BackendBase rejects them (binary_einsum.jl:83). The library sums
+// them before (or folded into) the contraction. Returns the positions inside T of its dangling modes.
+std::vector<int> dangling_modes(const TensorDesc &T, const TensorDesc &other, const TensorDesc &C);
+// T without the modes at `drop`; dense column-major strides in the remaining order when `redense`, else T's own strides
+TensorDesc without_modes(const TensorDesc &T, const std::vector<int> &drop, bool redense);
+
 // true when the leading summed modes tile a group of 8 k exactly (tcgen05 operand format, tf32.cu)
 bool k8_groupable(const std::vector<GroupMode> &sum);
 

@@ -206,7 +206,20 @@ struct Tf32Params {
     int nsplit;
     void *ws;
     int mixed;   // 1: TF32 + BF16 operand format (8 / 4 MMAs per line), 0: 3xTF32 (12 / 6)
+    // cross-GPU split-K (kernels.cuh DistDesc): partial sub-tiles go to ws (this rank's own workspace), then the unit's flag is
+    // raised in its owner's flag array
+    int dist_nranks, dist_rank, dist_epoch;
+    int *dist_flags[MB200_MAX_PEERS];
 };
+
+__device__ __forceinline__ void st_release_sys(int *p, int v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_sys(const int *p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 template <int BN, bool REAL, bool CTA2>
 struct Tf32Smem {
@@ -430,6 +443,21 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     else mbar_arrive(&tmem_empty[buf]);
                 }
             }
+            if (p.dist_nranks) {   // cross-GPU split-K: partial sub-tile -> own workspace (unit-linear, row fastest), then flag the owner
+                const int64_t u = tile * NCTA + rank;
+                const size_t base = (size_t)u * (TBM * BN) + row;
+#pragma unroll
+                for (int j = 0; j < HALF; j++) {
+                    const size_t o = base + (size_t)(half * HALF + j) * TBM;
+                    if constexpr (REAL) reinterpret_cast<float *>(p.ws)[o] = accr[j];
+                    else reinterpret_cast<float2 *>(p.ws)[o] = make_float2(accr[j], acci[j]);
+                }
+                __threadfence_system();                        // this thread's stores are visible system-wide ...
+                asm volatile("bar.sync 1, 256;" ::: "memory");   // ... and so are those of all 256 epilogue threads before the flag goes up
+                if (et == 0)
+                    st_release_sys(p.dist_flags[u % p.dist_nranks] + u * p.dist_nranks + p.dist_rank, p.dist_epoch);
+                continue;
+            }
             if (p.nsplit > 1) {   // partial tile -> workspace, row fastest (coalesced), every row / column of the tile (1-CTA only)
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 const size_t base = (size_t)unit * (TBM * BN) + row;
@@ -482,6 +510,138 @@ __global__ void __launch_bounds__(256) tf32_splitk_reduce_kernel(const __grid_co
     }
 }
 
+// ---- cross-GPU split-K: the owner's reducer (kernels.cuh DistDesc) -----------------------------------------------------------
+struct DistParams {
+    const void *ws[MB200_MAX_PEERS];
+    void *c[MB200_MAX_PEERS];
+    int *flags[MB200_MAX_PEERS];
+    const void *mc_ws;
+    void *mc_c;
+    int nranks, rank, epoch;
+    int64_t nunits;
+};
+
+__device__ __forceinline__ float4 ld_relaxed_sys_f4(const void *p) {
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 multimem_ld_reduce_f4(const void *p) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void multimem_st_f4(void *p, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void multimem_st_f2(void *p, float2 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void multimem_st_f1(void *p, float v) {
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+// bounded spin: a rank that never signals must surface as a trapped kernel, not as a hung GPU (~10 s at 2 GHz)
+__device__ __forceinline__ void spin_until(const int *flag, int epoch) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) < epoch) {
+        __nanosleep(64);
+        if (clock64() - t0 > 20000000000LL) __trap();
+    }
+}
+
+constexpr int RTHREADS = 256;   // 256 threads x <= 40 registers: co-resident with a 320-thread x 168-register GEMM CTA on one SM
+
+// One CTA per owned unit at a time (unit = rank, rank + nranks, ... strided over the CTAs). A 16-byte vector is 2 consecutive rows
+// (complex) or 4 (real) of one column of the sub-tile.
+template <int BN, bool REAL, bool CTA2>
+__global__ void __launch_bounds__(RTHREADS, 6) tf32_allreduce_kernel(const __grid_constant__ Tf32Params p, const __grid_constant__ DistParams d) {
+    constexpr int NCTA = CTA2 ? 2 : 1;
+    constexpr int PM = TBM * NCTA;
+    constexpr int VE = REAL ? 4 : 2;                 // elements per 16-byte vector
+    constexpr int ESZ = REAL ? 4 : 8;
+    constexpr int NVEC = TBM * BN / VE;
+    __shared__ int64_t sRow[TBM];
+    __shared__ int64_t sCol[BN];
+    const int tid = threadIdx.x;
+    const int64_t owned = (d.nunits - d.rank + d.nranks - 1) / d.nranks;   // units rank, rank + nranks, ...
+    for (int64_t j = blockIdx.x; j < owned; j += gridDim.x) {
+        const int64_t u = j * d.nranks + d.rank;
+        const int64_t tile = u / NCTA;
+        const int sub = (int)(u % NCTA);
+        const TileCoord tc = tile_coord<BN, PM>(p, tile);
+        const int64_t m0 = (int64_t)tc.m0 + sub * TBM;
+        __syncthreads();                               // previous unit's tables are no longer read
+        if (tid < TBM) sRow[tid] = (m0 + tid < p.M) ? p.rowC[m0 + tid] + p.batC[tc.l] : -1;
+        for (int i = tid; i < BN; i += RTHREADS) sCol[i] = (tc.n0 + i < p.N) ? p.colC[tc.n0 + i] : -1;
+        if (tid < d.nranks) spin_until(d.flags[d.rank] + u * d.nranks + tid, d.epoch);
+        __syncthreads();                               // all nranks partial sub-tiles of this unit are visible
+        const size_t ubase = (size_t)u * (TBM * BN) * ESZ;
+#pragma unroll 2
+        for (int v = tid; v < NVEC; v += RTHREADS) {
+            const int e = v * VE, r = e % TBM, c = e / TBM;
+            const size_t off = ubase + (size_t)v * 16;
+            float4 acc;
+            if (d.mc_ws) {
+                acc = multimem_ld_reduce_f4(reinterpret_cast<const char *>(d.mc_ws) + off);
+            } else {
+                acc = ld_relaxed_sys_f4(reinterpret_cast<const char *>(d.ws[0]) + off);
+                for (int s = 1; s < d.nranks; s++) {
+                    const float4 x = ld_relaxed_sys_f4(reinterpret_cast<const char *>(d.ws[s]) + off);
+                    acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+                }
+            }
+            const int64_t col = sCol[c];
+            if (col < 0) continue;
+            const int64_t r0 = sRow[r];
+            bool contig = r0 >= 0 && ((r0 + col) % VE) == 0;
+#pragma unroll
+            for (int i = 1; i < VE; i++) contig = contig && sRow[r + i] == r0 + i;
+            if (contig) {
+                const size_t co = (size_t)(r0 + col) * ESZ;
+                if (d.mc_c) multimem_st_f4(reinterpret_cast<char *>(d.mc_c) + co, acc);
+                else
+                    for (int s = 0; s < d.nranks; s++) *reinterpret_cast<float4 *>(reinterpret_cast<char *>(d.c[s]) + co) = acc;
+            } else {
+                const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+                for (int i = 0; i < VE; i++) {
+                    const int64_t ri = sRow[r + i];
+                    if (ri < 0) continue;
+                    const size_t co = (size_t)(ri + col) * ESZ;
+                    if constexpr (REAL) {
+                        if (d.mc_c) multimem_st_f1(reinterpret_cast<char *>(d.mc_c) + co, a4[i]);
+                        else
+                            for (int s = 0; s < d.nranks; s++) *reinterpret_cast<float *>(reinterpret_cast<char *>(d.c[s]) + co) = a4[i];
+                    } else {
+                        const float2 z = make_float2(a4[2 * i], a4[2 * i + 1]);
+                        if (d.mc_c) multimem_st_f2(reinterpret_cast<char *>(d.mc_c) + co, z);
+                        else
+                            for (int s = 0; s < d.nranks; s++) *reinterpret_cast<float2 *>(reinterpret_cast<char *>(d.c[s]) + co) = z;
+                    }
+                }
+            }
+        }
+    }
+    // every store of this CTA is visible system-wide, then the last CTA to finish raises done[rank] on every rank
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+        int *counter = d.flags[d.rank] + d.nunits * d.nranks + d.nranks;
+        const int prev = atomicAdd(counter, 1);
+        if (prev == (int)gridDim.x - 1) {
+            *counter = 0;                              // next call (stream-ordered after this kernel) starts from zero
+            __threadfence_system();
+            for (int s = 0; s < d.nranks; s++) st_release_sys(d.flags[s] + d.nunits * d.nranks + d.rank, d.epoch);
+        }
+    }
+}
+
+// a rank's C is complete when every owner has raised its done flag here
+__global__ void dist_wait_done_kernel(const int *done, int nranks, int epoch) {
+    if ((int)threadIdx.x < nranks) spin_until(done + threadIdx.x, epoch);
+}
+
 // ---- host side ----------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -519,12 +679,25 @@ int pair_mode() {
     static const int m = [] { const char *e = getenv("MB200_CTA_PAIR"); return e ? atoi(e) : 1; }();
     return m;
 }
+bool pair_mode_allows() { return pair_mode() != 0; }
+
+// dist mode decides the kernel variant from the shape alone (every rank, the GEMM and the reducer must agree)
+template <int BN, bool REAL>
+constexpr bool pair_ok() { return (REAL && BN == 256) || (!REAL && BN == 128); }
+template <int BN, bool REAL>
+bool dist_uses_pair(int64_t M) { return pair_ok<BN, REAL>() && pair_mode_allows() && M >= 2 * TBM; }
 
 template <int BN, bool REAL>
-cudaError_t launch_bn(const void *packA, const void *packB, const GettParams &g, bool mixed, cudaStream_t s, bool *pair) {
+cudaError_t launch_bn(const void *packA, const void *packB, const GettParams &g, bool mixed, cudaStream_t s, bool *pair,
+                      const DistDesc *dist) {
     CUtensorMap mapA, mapB;
     constexpr int W = REAL ? 2 : 4;
     Tf32Params p{};
+    if (dist) {
+        p.dist_nranks = dist->nranks; p.dist_rank = dist->rank; p.dist_epoch = dist->epoch;
+        for (int r = 0; r < dist->nranks; r++) p.dist_flags[r] = dist->flags[r];
+        p.ws = dist->ws[dist->rank];
+    }
     p.sc = g.sc;
     p.C = g.C;
     p.rowC = g.rowC; p.colC = g.colC; p.batC = g.batC;
@@ -538,7 +711,8 @@ cudaError_t launch_bn(const void *packA, const void *packB, const GettParams &g,
     constexpr bool PAIR_OK = (REAL && BN == 256) || (!REAL && BN == 128);
     if constexpr (PAIR_OK) {
         const int64_t ptiles = ((g.M + 2 * TBM - 1) / (2 * TBM)) * ((g.N + BN - 1) / BN) * g.L;
-        const bool want = pair_mode() == 2 ? g.M > TBM : (pair_mode() == 1 && g.M >= 2 * TBM && ptiles >= 148);
+        const bool want = dist ? dist_uses_pair<BN, REAL>(g.M)
+                               : (pair_mode() == 2 ? g.M > TBM : (pair_mode() == 1 && g.M >= 2 * TBM && ptiles >= 148));
         if (want) {
             if (!make_map(&mapA, packA, g.K, W, g.M, g.L, TBM) || !make_map(&mapB, packB, g.K, W, g.N, g.L, BN / 2))
                 return cudaErrorInvalidValue;
@@ -556,7 +730,7 @@ cudaError_t launch_bn(const void *packA, const void *packB, const GettParams &g,
             cfg.attrs = attr;
             cfg.numAttrs = 1;
             const cudaError_t le = cudaLaunchKernelEx(&cfg, tf32_gemm_kernel<BN, REAL, true>, mapA, mapB, p);
-            if (le == cudaSuccess) return le;
+            if (le == cudaSuccess || dist) return le;   // dist: the reducer decodes pair units, no silent change of variant
             // a device that cannot place the cluster (partitioned GPU, shared-memory carve-out): clear the launch-configuration
             // error and run the single-CTA kernel below
             if (le != cudaErrorInvalidConfiguration && le != cudaErrorLaunchOutOfResources && le != cudaErrorInvalidValue &&
@@ -572,10 +746,10 @@ cudaError_t launch_bn(const void *packA, const void *packB, const GettParams &g,
     // split-K when the tiles cannot fill the SMs: at most one slice per 128-k TMEM chunk
     const int64_t chunks = (g.K + CHUNK_K - 1) / CHUNK_K;
     static const int sk_mode = [] { const char *e = getenv("MB200_SPLITK"); return e ? atoi(e) : 1; }();
-    if (sk_mode && g.sc.nranks == 0 && ntiles * 4 <= 148 * 3 && chunks >= 2)
+    if (sk_mode && g.sc.nranks == 0 && !dist && ntiles * 4 <= 148 * 3 && chunks >= 2)
         p.nsplit = (int)std::min<int64_t>(chunks, std::max<int64_t>(1, 148 / ntiles));
     void *ws = nullptr;
-    if (p.nsplit > 1) {
+    if (p.nsplit > 1) {   // (never in dist mode: p.ws is the rank's cross-GPU workspace there)
         cudaError_t e = cudaMallocAsync(&ws, (size_t)p.nsplit * ntiles * TBM * BN * (REAL ? 4 : 8), s);
         if (e != cudaSuccess) return e;
         p.ws = ws;
@@ -610,15 +784,66 @@ cudaError_t tf32_configure() {
 
 // C (scattered through rowC/colC/batC) = packA [L][M][W*K] x packB [L][N][W*K]^T, K % 8 == 0;
 // dtype ComplexF32 (W = 4) or Float32 (W = 2)
-cudaError_t launch_tf32_gemm(int dtype, const void *packA, const void *packB, const GettParams &g, bool mixed, cudaStream_t s, bool *pair) {
+cudaError_t launch_tf32_gemm(int dtype, const void *packA, const void *packB, const GettParams &g, bool mixed, cudaStream_t s, bool *pair,
+                             const DistDesc *dist) {
     if (pair) *pair = false;
     if (g.K % 8 != 0 || g.K < 8) return cudaErrorInvalidValue;
     if (dtype == MB200_F32) {
-        if (g.N > 128) return launch_bn<256, true>(packA, packB, g, mixed, s, pair);
-        return launch_bn<128, true>(packA, packB, g, mixed, s, pair);
+        if (g.N > 128) return launch_bn<256, true>(packA, packB, g, mixed, s, pair, dist);
+        return launch_bn<128, true>(packA, packB, g, mixed, s, pair, dist);
     }
-    if (g.N > 64) return launch_bn<128, false>(packA, packB, g, mixed, s, pair);
-    return launch_bn<64, false>(packA, packB, g, mixed, s, pair);
+    if (g.N > 64) return launch_bn<128, false>(packA, packB, g, mixed, s, pair, dist);
+    return launch_bn<64, false>(packA, packB, g, mixed, s, pair, dist);
+}
+
+namespace {
+template <int BN, bool REAL>
+DistGeometry geometry_bn(int64_t M, int64_t N, int64_t L) {
+    const bool pair = dist_uses_pair<BN, REAL>(M);
+    const int64_t pm = pair ? 2 * TBM : TBM;
+    const int64_t tiles = ((M + pm - 1) / pm) * ((N + BN - 1) / BN) * L;
+    return DistGeometry{BN, pair ? 1 : 0, tiles * (pair ? 2 : 1), (int64_t)TBM * BN};
+}
+
+template <int BN, bool REAL>
+cudaError_t launch_allreduce_bn(const GettParams &g, const DistDesc &dist, cudaStream_t s) {
+    const DistGeometry geo = geometry_bn<BN, REAL>(g.M, g.N, g.L);
+    Tf32Params p{};
+    p.rowC = g.rowC; p.colC = g.colC; p.batC = g.batC;
+    p.M = g.M; p.N = g.N; p.L = g.L;
+    p.ntiles = geo.nunits / (geo.pair ? 2 : 1);
+    DistParams d{};
+    d.nranks = dist.nranks; d.rank = dist.rank; d.epoch = dist.epoch; d.nunits = geo.nunits;
+    for (int r = 0; r < dist.nranks; r++) { d.ws[r] = dist.ws[r]; d.c[r] = dist.c[r]; d.flags[r] = dist.flags[r]; }
+    d.mc_ws = dist.mc_ws; d.mc_c = dist.mc_c;
+    const int64_t owned = (geo.nunits - dist.rank + dist.nranks - 1) / dist.nranks;
+    // a rank that owns nothing still launches one CTA: its done flag must go up
+    static const int rctas = [] { const char *e = getenv("MB200_DIST_REDUCER_CTAS"); return e ? std::max(1, atoi(e)) : 16; }();
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(owned, rctas));
+    if constexpr (pair_ok<BN, REAL>()) {
+        if (geo.pair) {
+            tf32_allreduce_kernel<BN, REAL, true><<<grid, RTHREADS, 0, s>>>(p, d);
+            return cudaGetLastError();
+        }
+    }
+    tf32_allreduce_kernel<BN, REAL, false><<<grid, RTHREADS, 0, s>>>(p, d);
+    return cudaGetLastError();
+}
+}  // namespace
+
+DistGeometry tf32_dist_geometry(int dtype, int64_t M, int64_t N, int64_t L) {
+    if (dtype == MB200_F32) return N > 128 ? geometry_bn<256, true>(M, N, L) : geometry_bn<128, true>(M, N, L);
+    return N > 64 ? geometry_bn<128, false>(M, N, L) : geometry_bn<64, false>(M, N, L);
+}
+
+cudaError_t launch_tf32_allreduce(int dtype, const GettParams &g, const DistDesc &dist, cudaStream_t s) {
+    if (dtype == MB200_F32) return g.N > 128 ? launch_allreduce_bn<256, true>(g, dist, s) : launch_allreduce_bn<128, true>(g, dist, s);
+    return g.N > 64 ? launch_allreduce_bn<128, false>(g, dist, s) : launch_allreduce_bn<64, false>(g, dist, s);
+}
+
+cudaError_t launch_dist_wait_done(const DistDesc &dist, int64_t nunits, cudaStream_t s) {
+    dist_wait_done_kernel<<<1, 32, 0, s>>>(dist.flags[dist.rank] + nunits * dist.nranks, dist.nranks, dist.epoch);
+    return cudaGetLastError();
 }
 
 }  // namespace mb200

@@ -72,6 +72,15 @@ def _promote(a: Tensor, b: Tensor) -> np.dtype:
     return np.result_type(a.dtype, b.dtype)   # Base.promote_eltype (ext/MuscleCUDAExt.jl:16)
 
 
+def _common_device(*tensors) -> int:
+    """The one GPU all device-resident operands live on; operands on different devices are an ArgumentError
+    (a kernel launched on one device must never be handed another device's pointers)."""
+    devs = {t.data.device for t in tensors if t.on_device}
+    if len(devs) > 1:
+        raise ArgumentError(f"operands live on different devices {sorted(devs)}; move them to one GPU first")
+    return devs.pop()
+
+
 def _b200_out_of_place(inds_c, a: Tensor, b: Tensor) -> Tensor:
     """`binary_einsum(::BackendB200, inds_c, a, b)`: allocates C, returns Tensor(C, inds_c)."""
     inds_c = _as_index_list(inds_c)
@@ -97,7 +106,7 @@ def _b200_out_of_place(inds_c, a: Tensor, b: Tensor) -> Tensor:
         return Tensor(hc, inds_c)
     # device path (a host operand of a mixed pair is uploaded first — "hybrid" operands,
     # cf. binary_einsum.jl:23-24)
-    dev = a.data.device if a.on_device else b.data.device
+    dev = _common_device(a, b)
     da = a.data if a.on_device else B200Array.from_host(a.data, dev)
     db = b.data if b.on_device else B200Array.from_host(b.data, dev)
     shape_c = _result_shape(inds_c, a, b)
@@ -122,7 +131,7 @@ def _b200_in_place(c: Tensor, a: Tensor, b: Tensor) -> Tensor:
         raise _lib.DimensionMismatch(f"size(c) = {c.shape} does not match the contraction {_result_shape(c.inds, a, b)}")
     L = _lib.lib()
     if c.on_device:
-        dev = c.data.device
+        dev = _common_device(c, a, b)
         da = a.data if a.on_device else B200Array.from_host(a.data, dev)
         db = b.data if b.on_device else B200Array.from_host(b.data, dev)
         h = _lib.Handle.get(dev)

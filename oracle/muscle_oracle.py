@@ -2,7 +2,7 @@
 
 Julia is not installed in the build image, so the reference cannot be executed; this is a
 NumPy (OpenBLAS) restatement of the reference algorithm, column-major like Julia arrays.
-It is pinned by the reference's own known-answer tests (tests/test_oracle_reference_battery.py
+It is pinned by the reference's own known-answer tests (tests/test_oracle.py::test_reference_battery_on_oracle
 replays test/unit/operations/binary_einsum.jl and the OMEinsum/cuTENSOR integration batteries).
 Beyond that tiny known-answer set the reference holds no golden vectors for random data
 ("parity unpinned" by the reference itself for the large configs).

@@ -155,8 +155,10 @@ def test_planner_rejections():
         mb.plan_describe(d, [0], d, [0, 0], [2, 2], d, [1], [3])
     with pytest.raises(ArgumentError):      # label of C in neither operand (ext/MuscleStridedExt.jl:53)
         mb.plan_describe(d, [0, 5], d, [0, 1], [2, 3], d, [1], [3])
-    with pytest.raises(ArgumentError):      # free label missing from C (binary_einsum.jl:83)
-        mb.plan_describe(d, [0], d, [0, 1], [2, 3], d, [1, 2], [3, 4])
+    # a free label missing from C: BackendBase rejects it (binary_einsum.jl:83); BackendB200 sums it like cuTENSOR / OMEinsum
+    # (ext/MuscleCUDAExt.jl:30-38) - the plan is the contraction left after the pre-reduce
+    pre = mb.plan_describe(d, [0], d, [0, 1], [2, 3], d, [1, 2], [3, 4])
+    assert (pre.M, pre.N, pre.K) == (2, 1, 3)
     with pytest.raises(DimensionMismatch):  # shared label with different extents
         mb.plan_describe(d, [0], d, [0, 1], [2, 3], d, [1], [4])
     with pytest.raises(ArgumentError):      # eltype of C must be the promotion
@@ -173,8 +175,8 @@ def test_errors_surface_before_any_device_work():
     B = Tensor(np.ones((4, 5)), "jk")
     with pytest.raises(DimensionMismatch):
         binary_einsum(BackendB200(), [Index("i"), Index("k")], A, B)
-    with pytest.raises(ArgumentError):
-        binary_einsum(BackendB200(), [Index("i")], A, Tensor(np.ones((3, 5)), "jk"))
+    with pytest.raises(ArgumentError):      # a label of the output found in neither operand
+        binary_einsum(BackendB200(), [Index("i"), Index("q")], A, Tensor(np.ones((3, 5)), "jk"))
     with pytest.raises(ArgumentError):
         binary_einsum(BackendB200(), [Index("i"), Index("k")], Tensor(np.ones((2, 3), np.int64), "ij"),
                       Tensor(np.ones((3, 5)), "jk"))
