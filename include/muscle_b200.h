@@ -193,9 +193,15 @@ int mb200_hadamard(mb200_handle_t handle, void *C, int dtypeC,
  * Vt cols x k = conj(V) - exactly the three arrays `tensor_svd_thin(::BackendBase, A)` tensorifies
  * (src/Operations/tensor_svd.jl:100-124; `Vt = reshape(conj(V), ...)` :121), so A[u,v] = sum_s U[u,s] S[s] Vt[v,s].
  * Hand-written one-sided Jacobi (svd.cu). tol <= 0 selects sqrt(max(rows, cols)) * eps; max_sweeps <= 0 selects 30.
- * Stream-ordered, no host synchronisation. Limits: rows, cols < 2^31 and rows * cols elements of workspace. */
+ * Stream-ordered, no host synchronisation. Limits: rows, cols < 2^31 and rows * cols elements of workspace.
+ * The working copy is A scaled by an exact power of two so that max |a_ij| is in [1, 2): squared norms and inner products cannot
+ * under- / overflow whatever A's magnitude (S is scaled back). Rank-deficient input: columns whose norm vanishes are replaced
+ * by vectors orthonormal to all the others (Gram-Schmidt), so U and Vt are ALWAYS isometric, as LAPACK's are. */
 int mb200_svd_thin(mb200_handle_t handle, void *U, void *S, void *Vt, const void *A, int dtype,
                    int64_t rows, int64_t cols, double tol, int max_sweeps);
+/* Status of the last mb200_svd_thin on this handle (synchronises the stream): Jacobi sweeps used, whether the last sweep rotated
+ * nothing (converged = 0: max_sweeps exhausted, the factors are approximate), how many null columns were completed. */
+int mb200_svd_last_info(mb200_handle_t handle, int *sweeps, int *converged, int *completed_columns);
 
 /* Thin QR: A (rows x cols, dense column-major, device) = Q * R with k = min(rows, cols): Q rows x k (orthonormal
  * columns), R k x cols (upper triangular) - the two arrays `tensor_qr_thin(::BackendBase, A)` tensorifies

@@ -10,7 +10,7 @@ from ._lib import (ArgumentError, B200Error, DimensionMismatch, Handle, LIB_PATH
 from .backend import (Backend, BackendB200, BackendBase, BackendBlocks, BackendOMEinsum, Domain, DomainB200, DomainBlocks, DomainHost, choose_backend,
                       choose_backend_rule, domain, with_backend)
 from .einsum import binary_einsum, binary_einsum_, binary_einsum_inplace, flatten_labels, frontend_inds_c
-from .factorize import (AbsorbEqually, AbsorbU, AbsorbV, DontAbsorb, factorinds, simple_update,
+from .factorize import (AbsorbEqually, AbsorbU, AbsorbV, DontAbsorb, factorinds, simple_update, svd_last_info,
                         tensor_qr_thin, tensor_svd_thin, tensor_svd_trunc)
 from .family import hadamard, hadamard_, unary_einsum, unary_einsum_, unary_frontend_inds_y
 from .network import CapturedProgram, ContractionProgram, contract, find_path

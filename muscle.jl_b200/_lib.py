@@ -126,6 +126,7 @@ PROTOTYPES = {
                         _vp, _i, _i, _i32p, _i64p,
                         _vp, _i, _i, _i32p, _i64p], C.c_int),
     "mb200_svd_thin": ([_vp, _vp, _vp, _vp, _vp, _i, C.c_int64, C.c_int64, C.c_double, _i], C.c_int),
+    "mb200_svd_last_info": ([_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)], C.c_int),
     "mb200_qr_thin": ([_vp, _vp, _vp, _vp, _i, C.c_int64, C.c_int64], C.c_int),
     "mb200_shard_plan": ([_i, _i32p, _i, _i32p, _i64p, _i, _i32p, _i64p, _i, _i, _i,
                           C.POINTER(ShardInfo)], C.c_int),

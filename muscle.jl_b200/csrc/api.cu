@@ -66,6 +66,7 @@ struct mb200_handle_s {
     // cross-GPU split-K: the reducer runs on a high-priority side stream, concurrently with the GEMM on `stream`
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int *svd_info = nullptr;   // 8 ints written by the last mb200_svd_thin on this handle (sweeps, converged, ...)
 };
 
 struct mb200_graph_s {
@@ -719,6 +720,7 @@ int mb200_destroy(mb200_handle_t h) {
     MB200_CHECK_HANDLE(h);
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
+    if (h->svd_info) cudaFree(h->svd_info);
     if (h->side) { cudaStreamDestroy(h->side); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); }
     delete h;   // cached plans free their tables unless a captured graph still holds them
     return MB200_OK;
@@ -1031,18 +1033,31 @@ int mb200_svd_thin(mb200_handle_t h, void *U, void *S, void *Vt, const void *A, 
     MB200_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
     void *G = nullptr, *V = nullptr;
-    int *counters = nullptr;
     const size_t esz = dtype_size(dtype);
+    if (!h->svd_info) MB200_CUDA(cudaMalloc((void **)&h->svd_info, 8 * sizeof(int)));
     MB200_CUDA(cudaMallocAsync(&G, (size_t)m * k * esz, s));
     MB200_CUDA(cudaMallocAsync(&V, (size_t)k * k * esz, s));
-    MB200_CUDA(cudaMallocAsync((void **)&counters, 2 * sizeof(int), s));
-    cudaError_t e = launch_svd(dtype, A, (int)rows, (int)cols, U, S, Vt, G, V, counters, tol, max_sweeps, s);
+    cudaError_t e = launch_svd(dtype, A, (int)rows, (int)cols, U, S, Vt, G, V, h->svd_info, tol, max_sweeps, s);
     cudaFreeAsync(G, s);
     cudaFreeAsync(V, s);
-    cudaFreeAsync(counters, s);
     if (e != cudaSuccess) return cuda_fail(e, "svd launch");
     h->stats.launches_svd++;
     h->stats.launches_total++;
+    return MB200_OK;
+}
+
+int mb200_svd_last_info(mb200_handle_t h, int *sweeps, int *converged, int *completed_columns) {
+    MB200_CHECK_HANDLE(h);
+    std::lock_guard<std::mutex> lk(h->mu);
+    int info[8] = {0, 0, 0, 1, 0, 0, 0, 0};
+    if (h->svd_info) {
+        MB200_CUDA(cudaSetDevice(h->device));
+        MB200_CUDA(cudaMemcpyAsync(info, h->svd_info, sizeof info, cudaMemcpyDeviceToHost, h->stream));
+        MB200_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    if (sweeps) *sweeps = info[1];
+    if (converged) *converged = info[3];
+    if (completed_columns) *completed_columns = info[4];
     return MB200_OK;
 }
 

@@ -94,6 +94,25 @@ template <> __device__ __forceinline__ double2 zero_of_<double2>() { return make
 __device__ __forceinline__ double inv_sqrt(double x) { return rsqrt(x); }
 __device__ __forceinline__ float inv_sqrt(float x) { return 1.0f / sqrtf(x); }
 
+__device__ __forceinline__ float max_abs_part(float a) { return fabsf(a); }
+__device__ __forceinline__ double max_abs_part(double a) { return fabs(a); }
+__device__ __forceinline__ float max_abs_part(float2 a) { return fmaxf(fabsf(a.x), fabsf(a.y)); }
+__device__ __forceinline__ double max_abs_part(double2 a) { return fmax(fabs(a.x), fabs(a.y)); }
+template <typename T, typename R> __device__ __forceinline__ T make_cplx(R re, R im);
+template <> __device__ __forceinline__ float make_cplx<float, float>(float re, float) { return re; }
+template <> __device__ __forceinline__ double make_cplx<double, double>(double re, double) { return re; }
+template <> __device__ __forceinline__ float2 make_cplx<float2, float>(float re, float im) { return make_float2(re, im); }
+template <> __device__ __forceinline__ double2 make_cplx<double2, double>(double re, double im) { return make_double2(re, im); }
+// a - c * u
+__device__ __forceinline__ float sub_mul(float a, float c, float u) { return fmaf(-c, u, a); }
+__device__ __forceinline__ double sub_mul(double a, double c, double u) { return fma(-c, u, a); }
+__device__ __forceinline__ float2 sub_mul(float2 a, float2 c, float2 u) {
+    return make_float2(a.x - (c.x * u.x - c.y * u.y), a.y - (c.x * u.y + c.y * u.x));
+}
+__device__ __forceinline__ double2 sub_mul(double2 a, double2 c, double2 u) {
+    return make_double2(a.x - (c.x * u.x - c.y * u.y), a.y - (c.x * u.y + c.y * u.x));
+}
+
 template <typename R> __device__ __forceinline__ R warp_sum(R v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -105,7 +124,8 @@ struct SvdParams {
     void *G, *V;        // work: G (m x n), V (n x n)      [m >= n after the optional conjugate transpose]
     void *U, *Vt;       // outputs: U (rows x k), Vt (cols x k) = conj(right singular vectors), k = min(rows, cols)
     void *S;            // k singular values (real), descending
-    int *counters;      // [0] rotations of the current sweep, [1] sweeps done
+    int *counters;      // [0] rotations of the current sweep, [1] sweeps done, [2] scaling exponent + bias, [3] converged,
+                        // [4] completed (null) columns; [5..7] scratch (completion norm bits)
     int rows, cols, m, n, transposed;
     double tol;
     int max_sweeps;
@@ -122,17 +142,36 @@ __global__ void __launch_bounds__(256) jacobi_svd_kernel(const __grid_constant__
     const int lane = threadIdx.x & 31;
     const int64_t warp = tid >> 5, nwarps = nthreads >> 5;
 
-    // ---- init: G = A or A^H, V = I
+    // ---- pre-scale: alpha, beta and gamma^2 are 2nd and 4th powers of the data, so a matrix whose entries sit near 1e-11 or
+    // 1e+9 in Float32 (1e-77 / 1e+77 in Float64) would under- or overflow them and every rotation would be skipped. The working
+    // copy is A * 2^-e with e = exponent of max |a_ij| (an exact scaling); the singular values are scaled back at the end.
+    constexpr int EBIAS = 4096;
+    if (tid < 8) p.counters[tid] = 0;
+    grid.sync();
+    {
+        int emax = -EBIAS;
+        for (int64_t e = tid; e < (int64_t)m * n; e += nthreads) {
+            const R a = max_abs_part(A[e]);
+            if (a > (R)0 && a == a) emax = max(emax, (int)ilogb(a));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) emax = max(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+        if (lane == 0 && emax > -EBIAS) atomicMax(&p.counters[2], emax + EBIAS);
+    }
+    grid.sync();
+    const int escale = p.counters[2] > 0 ? p.counters[2] - EBIAS : 0;
+    const R down = (R)ldexp(1.0, -escale), up = (R)ldexp(1.0, escale);
+    // ---- init: G = A or A^H (scaled), V = I
     for (int64_t e = tid; e < (int64_t)m * n; e += nthreads) {
         const int i = (int)(e % m), j = (int)(e / m);
-        G[e] = p.transposed ? conj_(A[(int64_t)i * p.rows + j]) : A[e];
+        G[e] = scale<T, R>(p.transposed ? conj_(A[(int64_t)i * p.rows + j]) : A[e], down);
     }
     for (int64_t e = tid; e < (int64_t)n * n; e += nthreads) V[e] = (e % n == e / n) ? one_of<T>() : zero_of_<T>();
-    if (tid == 0) { p.counters[0] = 0; p.counters[1] = 0; }
     grid.sync();
 
     const int np = (n + 1) & ~1;          // players of the tournament (one dummy when n is odd)
     const R tol = (R)p.tol;
+    bool converged = n <= 1;
     for (int sweep = 0; sweep < p.max_sweeps && n > 1; sweep++) {
         for (int r = 0; r < np - 1; r++) {
             for (int64_t k = warp; k < np / 2; k += nwarps) {
@@ -177,8 +216,9 @@ __global__ void __launch_bounds__(256) jacobi_svd_kernel(const __grid_constant__
         grid.sync();
         if (tid == 0) { p.counters[0] = 0; p.counters[1] = sweep + 1; }
         grid.sync();
-        if (rotated == 0) break;
+        if (rotated == 0) { converged = true; break; }
     }
+    if (tid == 0) p.counters[3] = converged ? 1 : 0;   // read back by mb200_svd_last_info
 
     // ---- singular values: column norms, first in column order
     R *S = reinterpret_cast<R *>(p.S);
@@ -227,6 +267,56 @@ __global__ void __launch_bounds__(256) jacobi_svd_kernel(const __grid_constant__
     }
     grid.sync();
     if (myrank >= 0) S[myrank] = mine;
+    grid.sync();
+
+    // ---- null columns. A column whose norm is zero (or lost in the subnormal range) was written as a zero vector above, so U
+    // (or Vt) would not be isometric for rank-deficient input - product states, low-entanglement bonds - while LAPACK, which
+    // tensor_svd_thin / simple_update rely on (src/Operations/tensor_svd.jl:113), always returns orthonormal vectors. They are
+    // the LAST columns (S is sorted): each is replaced by a pseudo-random vector orthogonalised against all the columns before
+    // it (classical Gram-Schmidt, three passes: coefficients by one warp per column, update by one thread per row).
+    {
+        T *left = p.transposed ? reinterpret_cast<T *>(p.Vt) : reinterpret_cast<T *>(p.U);
+        const R tiny = sizeof(R) == 4 ? (R)2e-18 : (R)2.4e-153;   // ~16 sqrt(smallest normal): below it alpha, beta lose all bits
+        int first_null = n;
+        for (int j = n - 1; j >= 0 && S[j] < tiny; j--) first_null = j;
+        T *coef = V;                                   // V (n x n work) is free now: its first n entries hold the coefficients
+        for (int d = first_null; d < n; d++) {
+            T *v = left + (int64_t)d * m;
+            for (int64_t i = tid; i < m; i += nthreads) {
+                uint32_t hsh = (uint32_t)i * 2654435761u ^ ((uint32_t)d * 40503u + 0x9E3779B9u);
+                hsh ^= hsh >> 15; hsh *= 2246822519u; hsh ^= hsh >> 13;
+                v[i] = scale<T, R>(one_of<T>(), (R)((int)(hsh & 0xFFFF) - 32768) / (R)32768 + (R)(i == d % m ? 2 : 0));
+            }
+            grid.sync();
+            for (int pass = 0; pass < 3; pass++) {
+                for (int64_t c = warp; c < d; c += nwarps) {
+                    const T *u = left + c * m;
+                    R re = 0, im = 0;
+                    for (int i = lane; i < m; i += 32) cdot(u[i], v[i], re, im);
+                    re = warp_sum(re); im = warp_sum(im);
+                    if (lane == 0) coef[c] = make_cplx<T, R>(re, im);
+                }
+                grid.sync();
+                for (int64_t i = tid; i < m; i += nthreads) {
+                    T acc = v[i];
+                    for (int c = 0; c < d; c++) acc = sub_mul(acc, coef[c], left[(int64_t)c * m + i]);
+                    v[i] = acc;
+                }
+                grid.sync();
+            }
+            // normalise (every warp recomputes the norm: no extra barrier for a broadcast)
+            R a = 0;
+            for (int i = lane; i < m; i += 32) a += abs2(v[i]);
+            a = warp_sum(a);
+            const R inv = a > (R)0 ? inv_sqrt(a) : (R)0;
+            grid.sync();
+            for (int64_t i = tid; i < m; i += nthreads) v[i] = scale<T, R>(v[i], inv);
+            grid.sync();
+        }
+        if (tid == 0) p.counters[4] = n - first_null;
+    }
+    // singular values back to A's scale
+    for (int64_t j = tid; j < n; j += nthreads) S[j] *= up;
 }
 
 

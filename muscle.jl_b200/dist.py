@@ -230,3 +230,170 @@ def sum_slice_reduce_scatter(a_loc: Tensor, b_loc: Tensor, inds_c, group=None) -
 
 
 _MAX_PEERS = 8
+
+
+# ---- fused contraction + ALL-reduce: cross-GPU split-K (mb200_binary_einsum_allreduce) ------------------------------------
+class _SymmetricBuffers:
+    """One symmetric allocation per rank holding  ws | flags | C  and every rank's mapping of it.
+
+    Plumbing (torch is the allocator / rendezvous, the kernels only see raw pointers):
+      * "symm": torch.distributed._symmetric_memory (CUDA VMM handles exchanged over the process group); when the fabric
+        supports it the same allocation is also bound to an NVLS multicast object -> `multicast_ptr` (the reducer then uses
+        multimem.ld_reduce / multimem.st: the NVSwitch adds and replicates).
+      * "ipc": cudaMalloc + CUDA IPC handles (the plumbing of the fused reduce-scatter above); peer loads / stores only.
+    MB200_DIST_PLUMBING=symm|ipc forces one; MB200_DIST_MULTICAST=0 ignores an available multicast mapping."""
+
+    def __init__(self, device, ws_bytes, flag_bytes, c_bytes, group):
+        import ctypes as C
+        import os
+        import torch
+        import torch.distributed as dist
+        self.nranks = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        al = lambda n: (n + 4095) // 4096 * 4096
+        self.ws_off, self.flag_off, self.c_off = 0, al(ws_bytes), al(ws_bytes) + al(flag_bytes)
+        total = self.c_off + al(c_bytes)
+        self.ws_bytes, self.flag_bytes, self.c_bytes = ws_bytes, flag_bytes, c_bytes
+        self.epoch = 0
+        self.mc = 0
+        self.kind = None
+        want = os.environ.get("MB200_DIST_PLUMBING", "")
+        self.handle = _lib.Handle.get(device)
+        if want != "ipc" and self.nranks > 1:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                self._t = symm_mem.empty(total, dtype=torch.uint8, device=f"cuda:{device}")
+                self._t.zero_()
+                hdl = symm_mem.rendezvous(self._t, group if group is not None else dist.group.WORLD)
+                self.bases = [int(p) for p in hdl.buffer_ptrs]
+                if os.environ.get("MB200_DIST_MULTICAST", "1") != "0" and int(hdl.multicast_ptr or 0):
+                    self.mc = int(hdl.multicast_ptr)
+                self._hdl = hdl
+                self.kind = "symm"
+            except Exception as e:  # noqa: BLE001
+                if want == "symm":
+                    raise
+                self._symm_error = repr(e)[:300]
+        if self.kind is None:
+            L = _lib.lib()
+            p = C.c_void_p()
+            _lib.check(L.mb200_malloc(self.handle.ptr, C.byref(p), total))
+            _lib.check(L.mb200_memset(self.handle.ptr, p, 0, total))
+            own = int(p.value)
+            self.bases = [own]
+            if self.nranks > 1:
+                buf = C.create_string_buffer(64)
+                _lib.check(L.mb200_ipc_export(self.handle.ptr, p, buf))
+                gathered = [None] * self.nranks
+                dist.all_gather_object(gathered, buf.raw, group=group)
+                self.bases = []
+                for r in range(self.nranks):
+                    if r == self.rank:
+                        self.bases.append(own)
+                    else:
+                        q = C.c_void_p()
+                        _lib.check(L.mb200_ipc_import(self.handle.ptr, gathered[r], C.byref(q)))
+                        self.bases.append(int(q.value))
+            self.kind = "ipc"
+        self.handle.synchronize()                        # flags are zero before any peer can signal
+        try:
+            import torch
+            torch.cuda.synchronize(device)
+        except Exception:  # noqa: BLE001
+            pass
+        if self.nranks > 1:
+            dist.barrier(group=group)
+
+    def c_owner(self, device):
+        """uint8 torch tensor aliasing this rank's C region (the `_owner` a B200Array expects)."""
+        import torch
+        if self.kind == "symm":
+            return self._t[self.c_off: self.c_off + max(self.c_bytes, 1)]
+        if getattr(self, "_c_view", None) is None:
+            class _Raw:
+                pass
+            raw = _Raw()
+            raw.__cuda_array_interface__ = {"shape": (max(self.c_bytes, 1),), "typestr": "|u1", "version": 2,
+                                            "data": (self.bases[self.rank] + self.c_off, False)}
+            self._c_view = torch.as_tensor(raw, device=f"cuda:{device}")
+            self._c_view._mb200_keepalive = self
+        return self._c_view
+
+    def comm(self, epoch) -> "_lib.Comm":
+        cm = _lib.Comm()
+        cm.nranks, cm.rank, cm.epoch = self.nranks, self.rank, epoch
+        for r in range(self.nranks):
+            cm.ws[r] = self.bases[r] + self.ws_off
+            cm.flags[r] = self.bases[r] + self.flag_off
+            cm.c[r] = self.bases[r] + self.c_off
+        cm.mc_ws = (self.mc + self.ws_off) if self.mc else None
+        cm.mc_c = (self.mc + self.c_off) if self.mc else None
+        cm.ws_bytes, cm.flag_bytes = self.ws_bytes, self.flag_bytes
+        return cm
+
+
+_ALLREDUCE: dict = {}
+
+
+def allreduce_workspace(a_loc: Tensor, b_loc: Tensor, inds_c, nranks: int):
+    """(ws_bytes, flag_bytes) of the fused all-reduce for this contraction; ArgumentError when it is not on the tcgen05 path."""
+    import ctypes as C
+    inds_c = _as_index_list(inds_c)
+    ma, mb, mc = flatten_labels(a_loc.inds, b_loc.inds, inds_c)
+    T = np.result_type(a_loc.dtype, b_loc.dtype)
+    ws, fl = C.c_size_t(), C.c_size_t()
+    h = _lib.Handle.get(a_loc.data.device if a_loc.on_device else None)
+    _lib.check(_lib.lib().mb200_allreduce_workspace(
+        h.ptr, _lib.dtype_enum(T), len(mc), _lib.i32(mc),
+        _lib.dtype_enum(a_loc.dtype), len(ma), _lib.i32(ma), _lib.i64(a_loc.shape),
+        _lib.dtype_enum(b_loc.dtype), len(mb), _lib.i32(mb), _lib.i64(b_loc.shape),
+        nranks, C.byref(ws), C.byref(fl)))
+    return int(ws.value), int(fl.value)
+
+
+def sum_slice_all_reduce(a_loc: Tensor, b_loc: Tensor, inds_c, group=None, phases=7) -> Tensor:
+    """Summed-index slice with the all-reduce fused into the contraction (all-reduce semantics: every rank ends with the
+    full C, bit-identical on all ranks) - Dagger's `treereduce(AddComputeOp, ...)` over the summed blocks
+    (ext/MuscleDaggerExt/binary_einsum.jl:107-115) without a separate collective pass: see mb200_binary_einsum_allreduce.
+
+    The returned Tensor aliases a symmetric buffer that the NEXT call with the same signature overwrites; copy it
+    (`permutedims`, `to_host`) if it must outlive that call. Raises ArgumentError when the contraction is not on the
+    tcgen05 path; callers then use `all_reduce_sum` on the partial outputs."""
+    import ctypes as C
+    import torch.distributed as dist
+
+    inds_c = _as_index_list(inds_c)
+    if not (a_loc.on_device and b_loc.on_device):
+        raise _lib.ArgumentError("sum_slice_all_reduce needs device-resident slices")
+    nranks = dist.get_world_size(group) if dist.is_initialized() else 1
+    if nranks > _MAX_PEERS:
+        raise _lib.ArgumentError(f"at most {_MAX_PEERS} ranks")
+    ma, mb, mc = flatten_labels(a_loc.inds, b_loc.inds, inds_c)
+    T = np.result_type(a_loc.dtype, b_loc.dtype)
+    ext = {}
+    for t in (a_loc, b_loc):
+        for i, e in zip(t.inds, t.shape):
+            ext[i] = e
+    shape_c = tuple(ext[i] for i in inds_c)
+    numel = int(np.prod(shape_c, dtype=np.int64)) if shape_c else 1
+    dev = a_loc.data.device
+    key = (dev, nranks, id(group), T.str, tuple(ma), tuple(a_loc.shape), tuple(mb), tuple(b_loc.shape), tuple(mc))
+    st = _ALLREDUCE.get(key)
+    if st is None:
+        ws_bytes, flag_bytes = allreduce_workspace(a_loc, b_loc, inds_c, nranks)
+        st = _ALLREDUCE[key] = _SymmetricBuffers(dev, ws_bytes, flag_bytes, numel * T.itemsize, group)
+    st.epoch += 1
+    h = _lib.Handle.get(dev)
+    cm = st.comm(st.epoch)
+    _lib.check(_lib.lib().mb200_binary_einsum_allreduce(
+        h.ptr, _lib.dtype_enum(T), len(mc), _lib.i32(mc),
+        C.c_void_p(a_loc.data.ptr), _lib.dtype_enum(a_loc.dtype), len(ma), _lib.i32(ma), _lib.i64(a_loc.shape), None,
+        C.c_void_p(b_loc.data.ptr), _lib.dtype_enum(b_loc.dtype), len(mb), _lib.i32(mb), _lib.i64(b_loc.shape), None,
+        C.byref(cm), phases))
+    out = B200Array(shape_c, T, dev, _owner=st.c_owner(dev), _ptr=st.bases[st.rank] + st.c_off)
+    return Tensor(out, inds_c)
+
+
+def allreduce_plumbing_info() -> list:
+    """What the cached fused-all-reduce buffers run on: [(kind, multicast?)] - for bench / test reports."""
+    return [(s.kind, bool(s.mc)) for s in _ALLREDUCE.values()]

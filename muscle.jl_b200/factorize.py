@@ -14,7 +14,7 @@ import numpy as np
 from . import _lib
 from ._lib import ArgumentError
 from .backend import Backend, BackendB200, choose_backend
-from .einsum import binary_einsum
+from .einsum import binary_einsum, frontend_inds_c
 from .family import hadamard_
 from .tensor import B200Array, Index, Tensor, _as_index_list
 
@@ -71,6 +71,15 @@ def _b200_svd_thin(A: Tensor, inds_u=(), inds_v=(), ind_s=None, tol=0.0, max_swe
                                          float(tol), int(max_sweeps)))
     out = (Tensor(U, inds_u + [ind_s]), Tensor(S, [ind_s]), Tensor(Vt, inds_v + [ind_s]))
     return tuple(t.to_host() for t in out) if host else out
+
+
+def svd_last_info(device=None) -> dict:
+    """Status of the last `tensor_svd_thin` on this device / thread (synchronises): Jacobi sweeps, converged flag, number of
+    null columns completed to an orthonormal basis (rank deficiency)."""
+    h = _lib.Handle.get(device)
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    _lib.check(_lib.lib().mb200_svd_last_info(h.ptr, C.byref(a), C.byref(b), C.byref(c)))
+    return {"sweeps": int(a.value), "converged": bool(b.value), "completed_columns": int(c.value)}
 
 
 def tensor_svd_thin(*args, inds_u=(), inds_v=(), ind_s=None, **kwargs):
@@ -197,12 +206,20 @@ def _b200_simple_update(A, ind_physical_a, B, ind_physical_b, ind_bond_ab, G, in
     host = not (A.on_device or B.on_device or G.on_device)
     A, B, G = A.to_device(), B.to_device(), G.to_device()
     # Θ = binary_einsum(binary_einsum(A, B; dims=[bond]), G; dims=[phys_a, phys_b])          (simple_update.jl:51)
-    theta = binary_einsum(binary_einsum(A, B, dims=[ind_bond_ab]), G, dims=[ind_physical_a, ind_physical_b])
-    # replace(Θ, g_a => a, g_b => b)                                                          (:52)
-    ren = {ind_physical_g_a: ind_physical_a, ind_physical_g_b: ind_physical_b}
-    theta = Tensor(theta.data, [ren.get(i, i) for i in theta.inds])
+    # The second contraction is asked for Θ directly in the layout the factorisation wants, [inds_u; inds_v] (:54-57), so the
+    # permuting epilogue of the GEMM does the matricisation and tensor_svd_thin's permutedims (tensor_svd.jl:111) is a no-op:
+    # no K1 pass between the contraction and the SVD.
     inds_u = [i for i in A.inds if i != ind_bond_ab]                                          # :54-56
     inds_v = [i for i in B.inds if i != ind_bond_ab]
+    ren = {ind_physical_g_a: ind_physical_a, ind_physical_g_b: ind_physical_b}
+    back = {v: k for k, v in ren.items()}
+    ab = binary_einsum(A, B, dims=[ind_bond_ab])
+    default = frontend_inds_c(ab.inds, G.inds, dims=[ind_physical_a, ind_physical_b])
+    want = [back.get(i, i) for i in inds_u + inds_v]
+    out = want if sorted(map(repr, want)) == sorted(map(repr, default)) else None   # unusual gates keep the front-end order
+    theta = binary_einsum(ab, G, dims=[ind_physical_a, ind_physical_b], out=out)
+    # replace(Θ, g_a => a, g_b => b)                                                          (:52)
+    theta = Tensor(theta.data, [ren.get(i, i) for i in theta.inds])
     U, S, V = _b200_svd_thin(theta, inds_u=inds_u, inds_v=inds_v, ind_s=ind_bond_ab)          # :57
     if maxdim is not None:                                                                    # :61-65
         n = min(int(maxdim), S.shape[0])

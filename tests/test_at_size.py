@@ -217,3 +217,94 @@ def test_operands_on_one_device_only():
     b = Tensor(np.ones((4, 4)), I("jk")).to_device(1)
     with pytest.raises(mb.ArgumentError):
         binary_einsum(a, b)
+
+
+# ---- cross-GPU split-K (fused contraction + all-reduce) with the ranks EMULATED on one GPU ------------------------------------
+ALLREDUCE_EMU = [
+    # dt, (M, N, K), nranks, out permuted?            pair kernel: M >= 256
+    ("complex64", (512, 384, 1024), 4, False),
+    ("complex64", (1000, 520, 2048), 8, True),        # ragged tiles, transposed output (non-contiguous C rows)
+    ("complex64", (128, 256, 512), 2, False),         # single-CTA kernel (M < 256)
+    ("float32", (768, 640, 1024), 4, False),
+    ("float32", (520, 300, 2048), 3, True),
+]
+
+
+@pytest.mark.parametrize("dt,dims,nranks,permuted", ALLREDUCE_EMU)
+def test_fused_allreduce_emulated_ranks(dt, dims, nranks, permuted):
+    """mb200_binary_einsum_allreduce with the phases split so that one GPU can play every rank: all ranks contract their
+    K-slice (partial units -> own workspace, unit flags -> owners), then every owner's reducer adds the partials of its units
+    and stores them into the C of EVERY rank, then the done-flag waits. Every rank's C must equal the unsliced contraction
+    (what `treereduce(AddComputeOp)` / all_reduce(SUM) of the partials gives) and all ranks must hold identical bits."""
+    import ctypes as C
+    Mx, Nx, Kx = dims
+    rng = np.random.default_rng(23)
+    a = random_array(rng, (Kx, Mx), dt)          # [k, i]
+    b = random_array(rng, (Kx, Nx), dt)          # [k, j]
+    wide = np.complex128 if dt == "complex64" else np.float64
+    ref = a.astype(wide).T @ b.astype(wide)       # C[i, j]
+    modes_c = [2, 1] if permuted else [1, 2]
+    if permuted:
+        ref = ref.T
+    h = _lib.Handle.get()
+    h.set_path(mb.PATH_TCGEN05_TF32)
+    L = mb.lib()
+    en = _lib.dtype_enum(dt)
+    kc = Kx // nranks
+    assert kc * nranks == Kx and kc % 8 == 0
+    try:
+        ws_b, fl_b = C.c_size_t(), C.c_size_t()
+        _lib.check(L.mb200_allreduce_workspace(h.ptr, en, 2, _lib.i32(modes_c), en, 2, _lib.i32([0, 1]), _lib.i64((kc, Mx)),
+                                               en, 2, _lib.i32([0, 2]), _lib.i64((kc, Nx)), nranks, C.byref(ws_b), C.byref(fl_b)))
+        ws = [B200Array((ws_b.value,), np.float32) for _ in range(nranks)]          # oversized on purpose (bytes as floats)
+        fl = [B200Array((fl_b.value // 4 + 1,), np.float32) for _ in range(nranks)]
+        cs = [B200Array(ref.shape, dt) for _ in range(nranks)]
+        for r in range(nranks):
+            _lib.check(L.mb200_memset(h.ptr, C.c_void_p(fl[r].ptr), 0, fl[r].nbytes))
+            _lib.check(L.mb200_memset(h.ptr, C.c_void_p(cs[r].ptr), 0xFF, cs[r].nbytes))   # NaN-fill: every element must be written
+            _lib.check(L.mb200_memset(h.ptr, C.c_void_p(ws[r].ptr), 0xFF, ws[r].nbytes))
+        slices = [(B200Array.from_host(a[r * kc:(r + 1) * kc, :]), B200Array.from_host(b[r * kc:(r + 1) * kc, :])) for r in range(nranks)]
+        for epoch in (1, 2):                       # twice: flags carry epochs, nothing is reset between calls
+            for phase in (_lib.DIST_CONTRACT, _lib.DIST_REDUCE, _lib.DIST_WAIT):
+                for r in range(nranks):
+                    cm = _lib.Comm()
+                    cm.nranks, cm.rank, cm.epoch = nranks, r, epoch
+                    for q in range(nranks):
+                        cm.ws[q], cm.c[q], cm.flags[q] = ws[q].ptr, cs[q].ptr, fl[q].ptr
+                    cm.ws_bytes, cm.flag_bytes = ws_b.value, fl_b.value
+                    da, db = slices[r]
+                    _lib.check(L.mb200_binary_einsum_allreduce(
+                        h.ptr, en, 2, _lib.i32(modes_c),
+                        C.c_void_p(da.ptr), en, 2, _lib.i32([0, 1]), _lib.i64(da.shape), None,
+                        C.c_void_p(db.ptr), en, 2, _lib.i32([0, 2]), _lib.i64(db.shape), None, C.byref(cm), phase))
+            got = [c.to_host() for c in cs]
+            assert rel_frobenius(got[0].astype(wide), ref) <= 1e-5
+            for r in range(1, nranks):
+                assert np.array_equal(got[r], got[0])
+            if epoch == 1:
+                for r in range(nranks):
+                    _lib.check(L.mb200_memset(h.ptr, C.c_void_p(cs[r].ptr), 0xFF, cs[r].nbytes))
+        # the production call (all three phases at once, reducer on the side stream) with ONE rank: plain contraction semantics
+        cm = _lib.Comm()
+        cm.nranks, cm.rank, cm.epoch = 1, 0, 3
+        cm.ws[0], cm.c[0], cm.flags[0] = ws[0].ptr, cs[0].ptr, fl[0].ptr
+        cm.ws_bytes, cm.flag_bytes = ws_b.value, fl_b.value
+        _lib.check(L.mb200_memset(h.ptr, C.c_void_p(fl[0].ptr), 0, fl[0].nbytes))
+        _lib.check(L.mb200_memset(h.ptr, C.c_void_p(cs[0].ptr), 0xFF, cs[0].nbytes))
+        da, db = B200Array.from_host(a), B200Array.from_host(b)
+        _lib.check(L.mb200_binary_einsum_allreduce(
+            h.ptr, en, 2, _lib.i32(modes_c), C.c_void_p(da.ptr), en, 2, _lib.i32([0, 1]), _lib.i64(da.shape), None,
+            C.c_void_p(db.ptr), en, 2, _lib.i32([0, 2]), _lib.i64(db.shape), None, C.byref(cm), 7))
+        assert rel_frobenius(cs[0].to_host().astype(wide), ref) <= 1e-5
+    finally:
+        h.set_path(mb.PATH_AUTO)
+
+
+def test_fused_allreduce_rejects_other_paths():
+    import ctypes as C
+    h = _lib.Handle.get()
+    ws_b, fl_b = C.c_size_t(), C.c_size_t()
+    with pytest.raises(mb.ArgumentError):      # ComplexF64 runs on DMMA, not on the tcgen05 path
+        _lib.check(mb.lib().mb200_allreduce_workspace(h.ptr, _lib.C128, 2, _lib.i32([1, 2]), _lib.C128, 2, _lib.i32([0, 1]),
+                                                      _lib.i64((512, 512)), _lib.C128, 2, _lib.i32([0, 2]), _lib.i64((512, 512)),
+                                                      4, C.byref(ws_b), C.byref(fl_b)))

@@ -105,6 +105,86 @@ def test_tensor_svd_thin_rank_deficient_and_larger():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("dt", DTYPES)
+def test_tensor_svd_thin_is_isometric_on_rank_deficient_input(dt):
+    """LAPACK (the reference's `svd`, tensor_svd.jl:113) returns orthonormal U and Vt whatever the rank; so must the device
+    SVD: product states / low-entanglement bonds give exactly rank-deficient Theta, and canonical forms assume U'U = I."""
+    import muscle_b200 as mb
+    rng = np.random.default_rng(31)
+    I = lambda s: [mb.Index(c) for c in s]
+    wide = np.complex128 if np.dtype(dt).kind == "c" else np.float64
+    tol = 50 * TOL[dt]
+    cases = [np.asfortranarray(random_array(rng, (40, 1), dt) @ random_array(rng, (1, 24), dt)),          # product state: rank 1
+             np.asfortranarray(random_array(rng, (16, 3), dt) @ random_array(rng, (3, 48), dt)),          # wide, rank 3
+             np.zeros((12, 12), dt),                                                                       # all-zero
+             np.asfortranarray(np.diag(np.array([3, 0, 2, 0, 0, 1], dtype=dt)))]                           # exact zero columns
+    for a in cases:
+        U, S, Vt = mb.tensor_svd_thin(mb.Tensor(a, I("ab")).to_device(), inds_u=I("a"), ind_s=mb.Index("x"))
+        u, s, vt = U.to_host().data.astype(wide), S.to_host().data, Vt.to_host().data.astype(wide)
+        k = s.shape[0]
+        info = mb.svd_last_info()
+        assert info["converged"] and info["sweeps"] >= 0
+        assert np.linalg.norm(u.conj().T @ u - np.eye(k)) <= tol * k, (a.shape, info)
+        assert np.linalg.norm(vt.conj().T @ vt - np.eye(k)) <= tol * k, (a.shape, info)
+        assert rel_frobenius((u * s.astype(wide)) @ vt.T, a.astype(wide)) <= TOL[dt] or not a.any()
+        so = np.linalg.svd(a.astype(wide), compute_uv=False)
+        assert np.linalg.norm(s - so) <= TOL[dt] * max(np.linalg.norm(so), 1e-300)
+    assert mb.svd_last_info()["completed_columns"] >= 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dt,scale", [("float32", 1e-14), ("float32", 1e12), ("complex64", 3e-15), ("complex64", 2e11),
+                                      ("float64", 1e-120), ("complex128", 1e130)])
+def test_tensor_svd_thin_is_scale_invariant(dt, scale):
+    """Squared norms and gamma^2 are 2nd / 4th powers of the data: without the power-of-two pre-scaling every rotation was
+    skipped for Float32 data near 1e-11 (underflow) or 1e9 (overflow) and an un-diagonalised 'SVD' came back silently."""
+    import muscle_b200 as mb
+    rng = np.random.default_rng(32)
+    I = lambda s: [mb.Index(c) for c in s]
+    wide = np.complex128 if np.dtype(dt).kind == "c" else np.float64
+    a = np.asfortranarray((random_array(rng, (40, 28), dt).astype(wide) * scale).astype(dt))
+    U, S, Vt = mb.tensor_svd_thin(mb.Tensor(a, I("ab")).to_device(), inds_u=I("a"), ind_s=mb.Index("x"))
+    u, s, vt = U.to_host().data.astype(wide), S.to_host().data.astype(np.float64), Vt.to_host().data.astype(wide)
+    so = np.linalg.svd(a.astype(wide), compute_uv=False)
+    assert mb.svd_last_info()["converged"]
+    assert np.linalg.norm(s - so) <= TOL[dt] * np.linalg.norm(so)
+    assert rel_frobenius((u * s) @ vt.T, a.astype(wide)) <= TOL[dt]
+    assert np.linalg.norm(u.conj().T @ u - np.eye(28)) <= 50 * TOL[dt] * 28
+
+
+@pytest.mark.gpu
+def test_tensor_svd_thin_reports_non_convergence():
+    import muscle_b200 as mb
+    rng = np.random.default_rng(33)
+    I = lambda s: [mb.Index(c) for c in s]
+    A = mb.Tensor(random_array(rng, (64, 64), "complex128"), I("ab")).to_device()
+    mb.tensor_svd_thin(A, inds_u=I("a"), max_sweeps=1)
+    info = mb.svd_last_info()
+    assert info["sweeps"] == 1 and not info["converged"]
+    mb.tensor_svd_thin(A, inds_u=I("a"))
+    assert mb.svd_last_info()["converged"]
+
+
+@pytest.mark.gpu
+def test_simple_update_theta_needs_no_permute_pass():
+    """simple_update asks the second contraction for Theta in [inds_u; inds_v] order (simple_update.jl:54-57), so no K1
+    permutation runs between the contraction and the SVD."""
+    import muscle_b200 as mb
+    rng = np.random.default_rng(34)
+    chi, d = 32, 2
+    I = mb.Index
+    a, b = random_array(rng, (chi, d, chi), "complex128"), random_array(rng, (chi, d, chi), "complex128")
+    g = random_array(rng, (d, d, d, d), "complex128")
+    A, B, G = (mb.Tensor(x, ix).to_device() for x, ix in ((a, [I("l"), I("pa"), I("bond")]), (b, [I("bond"), I("pb"), I("r")]),
+                                                          (g, [I("pa"), I("pb"), I("ga"), I("gb")])))
+    h = mb.Handle.get(0)
+    h.reset_stats()
+    mb.simple_update(A, I("pa"), B, I("pb"), I("bond"), G, I("ga"), I("gb"))
+    st = h.stats()
+    assert st["launches_permute"] == 0 and st["launches_svd"] == 1, st
+
+
+@pytest.mark.gpu
 def test_tensor_svd_thin_rejects_like_the_reference():
     import muscle_b200 as mb
     I = lambda s: [mb.Index(c) for c in s]
