@@ -396,7 +396,11 @@ int contract_device(mb200_handle_t h, void *C, TensorDesc &dC, const int64_t *st
         // pack A, pack B (K1 with the split writer: a strided permutation when the layout allows it, else the table-driven
         // gather pack with K zero-padded to a multiple of 8), then the tcgen05 GEMM with the permuting epilogue
         const bool mixed = tf32_mixed(h);
-        const bool by_permute = p.tc_permute_pack && build_pack_params(p, 0, mixed, qa, rows_a) && build_pack_params(p, 1, mixed, qb, rows_b);
+        // MB200_PACK=permute: the K1 strided permutation with the 4-byte split writers (round 1); default: the table-driven
+        // line-writer pack for every layout
+        static const bool permute_pack = [] { const char *e = getenv("MB200_PACK"); return e && std::string(e) == "permute"; }();
+        const bool by_permute = permute_pack && p.tc_permute_pack && build_pack_params(p, 0, mixed, qa, rows_a) &&
+                                build_pack_params(p, 1, mixed, qb, rows_b);
         if (!by_permute) { rows_a = p.M; rows_b = p.N; }
         const int64_t Kp = by_permute ? p.K : (p.K + 7) / 8 * 8;
         void *pa = nullptr, *pb = nullptr;

@@ -459,6 +459,91 @@ __global__ void __launch_bounds__(256) pack_gather_kernel(const __grid_constant_
     }
 }
 
+// Line-writer pack into the tcgen05 operand format (tf32.cu): any layout (table-driven like pack_gather_kernel), but the destination
+// is written as whole 128-byte lines with 16-byte stores - a warp store instruction covers 512 contiguous bytes - instead of four
+// scattered 4-byte stores per element (ncu on the 4-byte writers: 35-56 % of HBM peak on 24 bytes moved per ComplexF32 element).
+//   tile = 64 rows x 32 k. Gather: lanes along k (K-major source) or along rows, 8 elements in flight per thread, into a
+//   shared-memory tile [row][k]. Write: 16-byte piece p of the line of (row, 8-k group): chunk type p >> 1 (re_hi, re_x, im_hi,
+//   im_x - or hi, x for Float32), 4 consecutive k each; the four lanes that need the same 4 elements read them as a broadcast.
+// Algorithmic bytes per element: sizeof(T) read + 2 sizeof(T) written (the hi and x planes) - declared in DESIGN 3.5.
+template <bool REAL>
+__global__ void __launch_bounds__(256) pack_lines_kernel(const __grid_constant__ PackGather q, const void *__restrict__ srcv,
+                                                         float *__restrict__ dst) {
+    using E = typename std::conditional<REAL, float, float2>::type;
+    constexpr int W = REAL ? 2 : 4;
+    constexpr int TR = 64, TK = 32;
+    constexpr int PITCH = TK + (REAL ? 4 : 2);            // keeps every row 16-byte aligned
+    __shared__ __align__(16) E tile[TR][PITCH];
+    __shared__ int64_t sRow[TR], sK[TK];
+    const E *src = reinterpret_cast<const E *>(srcv);
+    const int tid = threadIdx.x;
+    const int64_t tiles_k = (q.Kp + TK - 1) / TK, tiles_r = (q.rows + TR - 1) / TR;
+    int64_t b = blockIdx.x;
+    const int64_t k0 = (b % tiles_k) * TK; b /= tiles_k;
+    const int64_t r0 = (b % tiles_r) * TR;
+    const int64_t l = b / tiles_r;
+    if (tid < TR) sRow[tid] = (r0 + tid < q.rows) ? q.row_tab[r0 + tid] : -1;
+    else if (tid < TR + TK) sK[tid - TR] = (k0 + tid - TR < q.K) ? q.k_tab[k0 + tid - TR] : -1;
+    const int64_t bat = q.bat_tab[l];
+    __syncthreads();
+    E v[8];
+    if (q.kmajor) {
+        const int kk = tid & 31, rb = tid >> 5;
+        const int64_t ko = sK[kk];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int64_t ro = sRow[rb + 8 * i];
+            v[i] = E{};
+            if (ko >= 0 && ro >= 0) v[i] = src[ro + ko + bat];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) tile[rb + 8 * i][kk] = v[i];
+    } else {
+        const int rr = tid & 63, kb = tid >> 6;
+        const int64_t ro = sRow[rr];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int64_t ko = sK[kb + 4 * i];
+            v[i] = E{};
+            if (ko >= 0 && ro >= 0) v[i] = src[ro + ko + bat];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) tile[rr][kb + 4 * i] = v[i];
+    }
+    __syncthreads();
+    const int aux = q.aux;
+    auto hi_of = [aux](float x) { return aux == 0 ? tf32_hi(x) : tf32_rn(x); };
+    auto x_of = [aux](float x, float h) { return aux == 0 ? x - h : cross_word(x, x - h, aux); };
+    constexpr int PIECES = REAL ? 4 : 8;                  // 16-byte pieces per 8-k group
+    constexpr int STORES = TR * (TK / 8) * PIECES / 256;  // per thread: 4 (real) / 8 (complex)
+#pragma unroll
+    for (int i = 0; i < STORES; i++) {
+        const int sidx = tid + 256 * i;
+        const int pc = sidx % PIECES, g = (sidx / PIECES) & 3, r = sidx / (PIECES * 4);
+        const int64_t row = r0 + r, kg = k0 + g * 8;
+        if (row >= q.rows || kg >= q.Kp) continue;
+        const int c = pc >> 1, half = pc & 1;
+        const E *e = &tile[r][g * 8 + half * 4];
+        float in[4];
+        if constexpr (REAL) {
+            const float4 t = *reinterpret_cast<const float4 *>(e);
+            in[0] = t.x; in[1] = t.y; in[2] = t.z; in[3] = t.w;
+        } else {
+            const float4 t0 = *reinterpret_cast<const float4 *>(e), t1 = *reinterpret_cast<const float4 *>(e + 2);
+            if (c < 2) { in[0] = t0.x; in[1] = t0.z; in[2] = t1.x; in[3] = t1.z; }
+            else { in[0] = t0.y; in[1] = t0.w; in[2] = t1.y; in[3] = t1.w; }
+        }
+        float4 w;
+        if ((c & 1) == 0) {
+            w = make_float4(hi_of(in[0]), hi_of(in[1]), hi_of(in[2]), hi_of(in[3]));
+        } else {
+            w = make_float4(x_of(in[0], hi_of(in[0])), x_of(in[1], hi_of(in[1])), x_of(in[2], hi_of(in[2])), x_of(in[3], hi_of(in[3])));
+        }
+        float *d = dst + (l * q.rows + row) * (W * q.Kp) + (kg >> 3) * (8 * W) + c * 8 + half * 4;
+        *reinterpret_cast<float4 *>(d) = w;
+    }
+}
+
 inline int floor_log2(int64_t v) { int l = 0; while ((int64_t)2 << l <= v) l++; return l; }
 inline int ceil_log2(int64_t v) { int l = 0; while (((int64_t)1 << l) < v) l++; return l; }
 
@@ -666,6 +751,13 @@ cudaError_t launch_pack_gather(int dtype, const void *src, const int64_t *row_ta
     PackGather q{row_tab, k_tab, bat_tab, rows, K, Kp, L, kmajor, split - 1};
     const int64_t grid = ((Kp + 31) / 32) * ((rows + 31) / 32) * L;
     if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    static const int lines = [] { const char *e = getenv("MB200_PACK_LINES"); return e ? atoi(e) : 1; }();
+    if (lines && (((uintptr_t)dst) & 15) == 0) {   // whole 128-byte lines, 16-byte stores (MB200_PACK_LINES=0: the 4-byte writer, A/B)
+        const int64_t g2 = ((Kp + 31) / 32) * ((rows + 63) / 64) * L;
+        if (dtype == MB200_F32) pack_lines_kernel<true><<<(unsigned)g2, 256, 0, s>>>(q, src, dst);
+        else pack_lines_kernel<false><<<(unsigned)g2, 256, 0, s>>>(q, src, dst);
+        return cudaGetLastError();
+    }
     if (dtype == MB200_F32) pack_gather_kernel<true><<<(unsigned)grid, 256, 0, s>>>(q, src, dst);
     else pack_gather_kernel<false><<<(unsigned)grid, 256, 0, s>>>(q, src, dst);
     return cudaGetLastError();
