@@ -163,6 +163,12 @@ int mb200_plan_describe(int dtypeC, int nmodeC, const int32_t *modesC, const int
  * dst mode d = src mode perm[d]; both dense column-major. `extents` are the SOURCE extents.
  * flags: MB200_PERMUTE_PLANAR writes a complex dst as two planes (all re, then all im). */
 #define MB200_PERMUTE_PLANAR 1u
+/* kernel choice for pure transpositions (A/B measurements, tests): TMA = the TMA-staged kernel (cp.async.bulk.tensor load -> shared-
+ * memory transposition -> cp.async.bulk.tensor store) whenever the layout is eligible (<= 5 canonical modes, runs of >= 32 elements
+ * on both sides, 16-byte aligned strides), NO_TMA = never; neither flag: the library's policy (MB200_PERMUTE_TMA env, default from
+ * the measurements in DESIGN 3.5). Ineligible layouts silently take the register-tile / shared-memory-tile kernels. */
+#define MB200_PERMUTE_TMA 2u
+#define MB200_PERMUTE_NO_TMA 4u
 int mb200_permute(mb200_handle_t handle, void *dst, const void *src, int dtype, int nmode,
                   const int64_t *extents, const int32_t *perm, uint32_t flags);
 

@@ -118,7 +118,20 @@ function Muscle.binary_einsum!(::BackendB200, c::Tensor, a::Tensor, b::Tensor)
     mc, ma, mb = modes(inds(c), inds(a), inds(b))
     ea, eb = Int64[size(a)...], Int64[size(b)...]
     pa, pb, pc = parent(a), parent(b), parent(c)
-    entry = pc isa B200Array ? :device : :host
+    # dispatch on ALL THREE parents: the device entry takes device pointers only, the host entry host pointers only
+    # (this shim drives one device per process - handle() - so device arrays always share a GPU)
+    ondev = (pa isa B200Array, pb isa B200Array, pc isa B200Array)
+    if all(ondev)
+        entry = :device
+    elseif !any(ondev)
+        entry = :host
+    else
+        # hybrid operands (cf. binary_einsum.jl:23-24): upload the host ones next to the device ones, then recurse
+        pc isa B200Array || throw(ArgumentError("binary_einsum!: c on the host needs host operands"))
+        a2 = pa isa B200Array ? a : Tensor(B200Array(pa), inds(a))
+        b2 = pb isa B200Array ? b : Tensor(B200Array(pb), inds(b))
+        return Muscle.binary_einsum!(BackendB200(), c, a2, b2)
+    end
     GC.@preserve pa pb pc mc ma mb ea eb begin
         if entry === :device
             check(ccall((:mb200_binary_einsum, libmuscle_b200[]), Cint,
@@ -146,6 +159,14 @@ function Muscle.binary_einsum!(::BackendB200, c::Tensor, a::Tensor, b::Tensor)
         end
     end
     return c
+end
+
+# Arithmetic of Float32 / ComplexF32 contractions on this thread's handle (mb200_compute_type_t): :default = tensor-core split
+# scheme (TF32 + BF16 cross terms, rel. Frobenius error <= 1e-5), :fp32 = strict FP32 FMAs (what cuTENSOR's COMPUTE_32F and
+# BackendBase give), :tf32x3 = the classic three-pass split.
+function set_compute_type!(kind::Symbol)
+    v = kind === :default ? 0 : kind === :fp32 ? 1 : kind === :tf32x3 ? 2 : throw(ArgumentError("unknown compute type $kind"))
+    check(ccall((:mb200_set_compute_type, libmuscle_b200[]), Cint, (Ptr{Cvoid}, Cint), handle().ptr, v))
 end
 
 pointer_of(x::B200Array) = x.ptr

@@ -930,6 +930,7 @@ int mb200_permute(mb200_handle_t h, void *dst, const void *src, int dtype, int n
     }
     q.total = total;
     q.plane_stride = (flags & MB200_PERMUTE_PLANAR) ? total : 0;
+    q.tma = (flags & MB200_PERMUTE_TMA) ? 1 : ((flags & MB200_PERMUTE_NO_TMA) ? -1 : 0);
     std::lock_guard<std::mutex> lk(h->mu);
     MB200_CUDA(cudaSetDevice(h->device));
     MB200_CUDA(launch_permute(dtype, q, src, dst, h->stream));

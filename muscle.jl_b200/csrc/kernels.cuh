@@ -122,6 +122,7 @@ struct PermuteParams {
     int64_t dst_stride[MB200_MAX_MODES]; // stride of each source mode in the destination (elements)
     int64_t total;
     int64_t plane_stride;                // != 0: complex dst written planar, im plane at +plane_stride
+    int tma;                             // 1: prefer the TMA-staged transposition kernel when eligible, -1: never, 0: library policy
     int split;                           // != 0: write an operand of the tcgen05 kernel (tf32.cu) — per 8 k, ComplexF32 -> four chunks of 8
                                          //    words (re_hi, re_x, im_hi, im_x at +0,+8,+16,+24), Float32 -> two (hi, x at +0,+8).
                                          //    1: 3xTF32 format (x = fp32 remainder); 2 / 3: mixed TF32 + BF16 format of the row / column

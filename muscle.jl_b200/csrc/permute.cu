@@ -17,8 +17,11 @@
 //   * smem pitch per y is padded so the transposed read is bank-conflict free for 4/8/16 B elements.
 //   * When the tile needs no transposition (no x or no y range) elements go straight from global to
 //     global in one loop, no shared memory.
+#include <cuda.h>
+
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
 #include <type_traits>
 #include <vector>
 
@@ -544,6 +547,124 @@ __global__ void __launch_bounds__(256) pack_lines_kernel(const __grid_constant__
     }
 }
 
+// ---- TMA-staged transposition (north star: "tiled through shared memory or staged via TMA") ---------------------------------
+// Pure transpositions (source unit-stride mode x != destination unit-stride mode y) of 4 / 8 / 16-byte elements with at most
+// 5 canonical modes: both tensors are described by 5-D tiled tensor maps over 32-bit words (an element = ESZ / 4 words folded into
+// the unit-stride dimension of EACH map, so 16-byte elements need no extra dimension). A persistent CTA walks 16 KB tiles through
+// a 3-stage ring: one thread issues cp.async.bulk.tensor loads (box [TX][TY], source order: x fastest) that complete on per-stage
+// mbarriers, all 8 warps transpose the tile in shared memory (diagonal lane mapping: element (x = lane, y = (lane + i) % 32) of a
+// 32 x 32 sub-tile per step - conflict-free on both sides without padding, which a dense TMA box would not allow), and one thread
+// issues the cp.async.bulk.tensor store (box [TY][TX], destination order: y fastest) as a bulk group. Ragged edges cost nothing:
+// the load zero-fills out-of-bounds elements, the store clips them. No global load / store instruction, no offset tables.
+__device__ __forceinline__ uint32_t pt_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pt_mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pt_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void pt_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pt_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pt_mbar_wait(uint64_t *bar, uint32_t parity) {
+    const long long t0 = clock64();
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(pt_smem_u32(bar)), "r"(parity) : "memory");
+        if (!ok && clock64() - t0 > 4000000000LL) __trap();   // a descriptor bug must not hang the GPU
+    }
+}
+__device__ __forceinline__ void pt_tma_load_5d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(pt_smem_u32(dst)), "l"(map), "r"(pt_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void pt_tma_store_5d(const CUtensorMap *map, const void *src, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                 ::"l"(map), "r"(pt_smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+
+struct TmaPermK {
+    unsigned x_chunks, y_chunks;
+    unsigned o_ext[3];     // outer modes (map dimensions 2..4), extent 1 when absent
+    unsigned ntiles;
+};
+
+template <int ESZ, int TX, int TY>
+struct TmaPermCfg {
+    static constexpr int STAGES = 3;
+    static constexpr int TILE_BYTES = TX * TY * ESZ;
+    static constexpr int SMEM = 2 * STAGES * TILE_BYTES + 128 /*align*/ + 64 /*barriers*/;
+};
+
+template <int ESZ, int TX, int TY>
+__global__ void __launch_bounds__(PT_THREADS) permute_tma_kernel(const __grid_constant__ CUtensorMap mapS,
+                                                                 const __grid_constant__ CUtensorMap mapD,
+                                                                 const __grid_constant__ TmaPermK k) {
+    using Cfg = TmaPermCfg<ESZ, TX, TY>;
+    using E = typename std::conditional<ESZ == 16, uint4, typename std::conditional<ESZ == 8, uint2, uint32_t>::type>::type;
+    constexpr int STAGES = Cfg::STAGES, W = ESZ / 4;
+    extern __shared__ unsigned char tma_raw[];
+    unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(tma_raw) + 127) & ~(uintptr_t)127);
+    E *tin = reinterpret_cast<E *>(base);                                     // [STAGES][TY][TX]
+    E *tout = reinterpret_cast<E *>(base + STAGES * Cfg::TILE_BYTES);         // [STAGES][TX][TY]
+    uint64_t *full = reinterpret_cast<uint64_t *>(base + 2 * STAGES * Cfg::TILE_BYTES);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapS) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapD) : "memory");
+        for (int s = 0; s < STAGES; s++) pt_mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (blockIdx.x >= k.ntiles) return;
+    const unsigned n_my = (k.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    auto coords = [&](unsigned it, int (&c)[5]) {   // tile -> (x chunk, y chunk, outer digits)
+        unsigned t = blockIdx.x + it * gridDim.x;
+        c[0] = (int)(t % k.x_chunks) * TX; t /= k.x_chunks;
+        c[1] = (int)(t % k.y_chunks) * TY; t /= k.y_chunks;
+        c[2] = (int)(t % k.o_ext[0]); t /= k.o_ext[0];
+        c[3] = (int)(t % k.o_ext[1]); t /= k.o_ext[1];
+        c[4] = (int)t;
+    };
+    auto issue_load = [&](unsigned it) {
+        int c[5];
+        coords(it, c);
+        const int s = it % STAGES;
+        pt_mbar_expect_tx(&full[s], Cfg::TILE_BYTES);
+        pt_tma_load_5d(tin + (size_t)s * TX * TY, &mapS, &full[s], c[0] * W, c[1], c[2], c[3], c[4]);
+    };
+    if (tid == 0)
+        for (unsigned it = 0; it < n_my && it < (unsigned)STAGES; it++) issue_load(it);
+    for (unsigned it = 0; it < n_my; it++) {
+        const int s = it % STAGES;
+        pt_mbar_wait(&full[s], (it / STAGES) & 1);
+        // the bulk store that read out[s] three tiles ago has finished reading shared memory
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(STAGES - 1) : "memory");
+        __syncthreads();
+        const E *in = tin + (size_t)s * TX * TY;
+        E *out = tout + (size_t)s * TX * TY;
+        constexpr int NSUB = (TX / 32) * (TY / 32);
+#pragma unroll 4
+        for (int item = warp; item < NSUB * 32; item += PT_THREADS / 32) {
+            const int sub = item >> 5, i = item & 31;
+            const int x = (sub % (TX / 32)) * 32 + lane, y = (sub / (TX / 32)) * 32 + ((lane + i) & 31);
+            out[x * TY + y] = in[y * TX + x];
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA store
+        __syncthreads();
+        if (tid == 0) {
+            int c[5];
+            coords(it, c);
+            pt_tma_store_5d(&mapD, out, c[1] * W, c[0], c[2], c[3], c[4]);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (it + STAGES < n_my) issue_load(it + STAGES);            // in[s] has been read by every thread (barrier above)
+        }
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory stays valid until the stores have read it
+}
+
 inline int floor_log2(int64_t v) { int l = 0; while ((int64_t)2 << l <= v) l++; return l; }
 inline int ceil_log2(int64_t v) { int l = 0; while (((int64_t)1 << l) < v) l++; return l; }
 
@@ -653,6 +774,90 @@ bool regT_ok(const PermK &k, size_t esz, const void *src, const void *dst) {
 
 }  // namespace
 
+namespace {
+
+typedef CUresult (*PtEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PtEncodeTiledFn pt_encode_fn() {
+    static PtEncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PtEncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// 0: not eligible (caller falls back to the register-tile / smem-tile kernels), 1: launched, -1: launch error in *err
+template <int ESZ, int TX, int TY>
+int launch_tma_cfg(const PermuteParams &q, int j, const void *src, void *dst, cudaStream_t s, cudaError_t *err) {
+    PtEncodeTiledFn fn = pt_encode_fn();
+    if (!fn) return 0;
+    constexpr int W = ESZ / 4;
+    int64_t sstride[MB200_MAX_MODES];
+    {
+        int64_t st = 1;
+        for (int i = 0; i < q.n; i++) { sstride[i] = st; st *= q.ext[i]; }
+    }
+    // map dimension order: (x = mode 0, y = mode j, others) for the source, (y, x, others) for the destination
+    int others[3], no = 0;
+    for (int i = 1; i < q.n; i++)
+        if (i != j) others[no++] = i;
+    cuuint64_t dimS[5], dimD[5], strS[4], strD[4];
+    cuuint32_t boxS[5] = {TX * W, TY, 1, 1, 1}, boxD[5] = {TY * W, TX, 1, 1, 1}, estr[5] = {1, 1, 1, 1, 1};
+    dimS[0] = (cuuint64_t)q.ext[0] * W; dimS[1] = (cuuint64_t)q.ext[j];
+    dimD[0] = (cuuint64_t)q.ext[j] * W; dimD[1] = (cuuint64_t)q.ext[0];
+    strS[0] = (cuuint64_t)sstride[j] * ESZ;          // byte stride of map dimension 1
+    strD[0] = (cuuint64_t)q.dst_stride[0] * ESZ;
+    TmaPermK k{};
+    for (int d = 0; d < 3; d++) {
+        const bool have = d < no;
+        const int m = have ? others[d] : 0;
+        dimS[2 + d] = dimD[2 + d] = have ? (cuuint64_t)q.ext[m] : 1;
+        strS[1 + d] = have ? (cuuint64_t)sstride[m] * ESZ : (cuuint64_t)q.total * ESZ;
+        strD[1 + d] = have ? (cuuint64_t)q.dst_stride[m] * ESZ : (cuuint64_t)q.total * ESZ;
+        k.o_ext[d] = have ? (unsigned)q.ext[m] : 1u;
+    }
+    for (int d = 0; d < 4; d++)
+        if (strS[d] % 16 || strD[d] % 16 || strS[d] >= ((cuuint64_t)1 << 40) || strD[d] >= ((cuuint64_t)1 << 40)) return 0;
+    for (int d = 0; d < 5; d++)
+        if (dimS[d] >= ((cuuint64_t)1 << 32) || dimD[d] >= ((cuuint64_t)1 << 32)) return 0;
+    CUtensorMap mapS, mapD;
+    if (fn(&mapS, CU_TENSOR_MAP_DATA_TYPE_UINT32, 5, const_cast<void *>(src), dimS, strS, boxS, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return 0;
+    if (fn(&mapD, CU_TENSOR_MAP_DATA_TYPE_UINT32, 5, dst, dimD, strD, boxD, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return 0;
+    k.x_chunks = (unsigned)((q.ext[0] + TX - 1) / TX);
+    k.y_chunks = (unsigned)((q.ext[j] + TY - 1) / TY);
+    const int64_t ntiles = (int64_t)k.x_chunks * k.y_chunks * k.o_ext[0] * k.o_ext[1] * k.o_ext[2];
+    if (ntiles <= 0 || ntiles > 0x7fffffffLL) return 0;
+    k.ntiles = (unsigned)ntiles;
+    const unsigned grid = (unsigned)std::min<int64_t>(ntiles, 148 * 2);
+    permute_tma_kernel<ESZ, TX, TY><<<grid, PT_THREADS, TmaPermCfg<ESZ, TX, TY>::SMEM, s>>>(mapS, mapD, k);
+    *err = cudaGetLastError();
+    return *err == cudaSuccess ? 1 : -1;
+}
+
+int try_permute_tma(const PermuteParams &q, size_t esz, const void *src, void *dst, cudaStream_t s, cudaError_t *err) {
+    if (q.n < 2 || q.n > 5 || q.dst_stride[0] == 1) return 0;
+    if ((((uintptr_t)src) | ((uintptr_t)dst)) & 15) return 0;
+    int j = -1;
+    for (int i = 1; i < q.n; i++)
+        if (q.dst_stride[i] == 1) j = i;
+    if (j < 0 || q.ext[0] < 32 || q.ext[j] < 32) return 0;      // short runs: the register-tile kernel wastes less
+    if (esz == 16) return launch_tma_cfg<16, 32, 32>(q, j, src, dst, s, err);
+    if (esz == 8) return launch_tma_cfg<8, 64, 32>(q, j, src, dst, s, err);
+    if (esz == 4) return launch_tma_cfg<4, 64, 64>(q, j, src, dst, s, err);
+    return 0;
+}
+
+}  // namespace
+
 cudaError_t launch_permute(int dtype, const PermuteParams &q_in, const void *src, void *dst, cudaStream_t s) {
     if (q_in.total <= 0) return cudaSuccess;
     PermuteParams q = q_in;
@@ -681,6 +886,15 @@ cudaError_t launch_permute(int dtype, const PermuteParams &q_in, const void *src
         }
     }
     const int ltile = esz == 16 ? 11 : (esz == 8 ? 12 : 13);
+
+    // MB200_PERMUTE_TMA: 0 = never, 1 = whenever eligible (pure transposition, <= 5 modes, runs >= 32 elements on both sides)
+    static const int tma_mode = [] { const char *e = getenv("MB200_PERMUTE_TMA"); return e ? atoi(e) : 0; }();
+    if (plain && q.tma >= 0 && (tma_mode || q.tma > 0)) {
+        cudaError_t terr = cudaSuccess;
+        const int r = try_permute_tma(q, esz, src, dst, s, &terr);
+        if (r == 1) return cudaSuccess;
+        if (r < 0) return terr;
+    }
 
     PermK k;
     std::vector<int> dord;
@@ -776,6 +990,11 @@ cudaError_t permute_configure() {
     MB200_PCFG(float2, float, 0); MB200_PCFG(float2, float, 1); MB200_PCFG(float2, float, 2);
     MB200_PCFG(double2, double, 0); MB200_PCFG(double2, double, 1);
 #undef MB200_PCFG
+#define MB200_TCFG(ESZ, TX, TY)                                                                                                  \
+    if (e == cudaSuccess)                                                                                                        \
+        e = cudaFuncSetAttribute(permute_tma_kernel<ESZ, TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, TmaPermCfg<ESZ, TX, TY>::SMEM)
+    MB200_TCFG(16, 32, 32); MB200_TCFG(8, 64, 32); MB200_TCFG(4, 64, 64);
+#undef MB200_TCFG
     return e;
 }
 

@@ -204,9 +204,10 @@ class Tensor:
             return self
         return Tensor(self.data.to_host(), self._inds)
 
-    def permutedims(self, perm) -> "Tensor":
+    def permutedims(self, perm, flags: int = 0) -> "Tensor":
         """`permutedims(t, perm)` by positions or by `Index` (src/Tensor.jl:302-319). Device tensors go
-        through the K1 permute kernel; host tensors are plain container sugar (not on the hot path)."""
+        through the K1 permute kernel; host tensors are plain container sugar (not on the hot path).
+        `flags`: MB200_PERMUTE_TMA (2) / MB200_PERMUTE_NO_TMA (4) pick the transposition kernel (A/B measurements)."""
         if self.ndim == 0:
             return self
         perm = list(perm)
@@ -219,7 +220,7 @@ class Tensor:
             h = _lib.Handle.get(src.device)
             _lib.check(_lib.lib().mb200_permute(h.ptr, C.c_void_p(dst.ptr), C.c_void_p(src.ptr),
                                                 _lib.dtype_enum(src.dtype), src.ndim, _lib.i64(src.shape),
-                                                _lib.i32(perm), 0))
+                                                _lib.i32(perm), flags))
             return Tensor(dst, new_inds)
         return Tensor(_lib.fortran(np.transpose(self.data, perm)), new_inds)
 

@@ -226,7 +226,7 @@ ALLREDUCE_EMU = [
     ("complex64", (1000, 520, 2048), 8, True),        # ragged tiles, transposed output (non-contiguous C rows)
     ("complex64", (128, 256, 512), 2, False),         # single-CTA kernel (M < 256)
     ("float32", (768, 640, 1024), 4, False),
-    ("float32", (520, 300, 2048), 3, True),
+    ("float32", (520, 300, 2064), 3, True),
 ]
 
 

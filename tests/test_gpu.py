@@ -251,6 +251,29 @@ def test_permute_bit_exact(shape, perm, dt):
     assert np.array_equal(got.to_host().data, np.transpose(x, perm))
 
 
+TMA_PERMUTE_CASES = [
+    ((64, 64, 64, 64), (1, 3, 0, 2)),        # config-1 A pack: k,i,l,j -> i,j,k,l
+    ((4096, 512), (1, 0)), ((100, 96), (1, 0)), ((33, 70, 40), (2, 1, 0)), ((48, 3, 80, 2), (2, 1, 0, 3)),
+    ((256, 8, 8, 256, 2), (3, 1, 0, 2, 4)),  # config-3 A matricise (5 modes)
+    ((40, 36, 5, 3, 2), (1, 0, 4, 3, 2)), ((130, 34), (1, 0)), ((32, 32), (1, 0)), ((64, 2, 64), (2, 1, 0)),
+]
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("shape,perm", TMA_PERMUTE_CASES)
+def test_permute_tma_variant_bit_exact(shape, perm, dt):
+    """The TMA-staged transposition kernel (cp.async.bulk.tensor load -> shared-memory transposition -> bulk tensor store),
+    forced through MB200_PERMUTE_TMA: bit-exact against numpy, ragged edges (zero-filled loads, clipped stores), 4 / 8 / 16-byte
+    elements, up to 5 modes; ineligible layouts fall back silently and must still be exact."""
+    rng = np.random.default_rng(3)
+    a = random_array(rng, shape, dt)
+    t = Tensor(a, [Index(i) for i in range(len(shape))]).to_device()
+    got = t.permutedims(list(perm), flags=2).to_host().data
+    assert np.array_equal(got, np.transpose(a, perm))
+    ref = t.permutedims(list(perm), flags=4).to_host().data
+    assert np.array_equal(ref, got)
+
+
 def test_permute_unaligned_pointers_skip_the_wide_paths():
     """16-byte vector paths (element widening, register-tile transposition) need 16-byte aligned buffers: a Float32
     view that starts 4 bytes into an allocation must fall back to the element-wise kernels and still be exact."""
