@@ -349,12 +349,23 @@ def max_over_ranks(c, x):
     return float(x)
 
 
-def timed(c, fn, iters, warmup=3):
-    """CUDA events on the launching (current torch) stream, warm-up first, barrier + synchronize on both sides, max over ranks."""
+def timed(c, fn, iters, warmup=3, min_ms=0.0):
+    """CUDA events on the launching (current torch) stream, warm-up first, barrier + synchronize on both sides, max over ranks.
+    min_ms > 0: at least that much device time (sustained figure, long enough for the 50 ms clock / power samples)."""
     torch = c.torch
     for _ in range(warmup):
         fn()
     barrier(c)
+    if min_ms > 0:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        est = max_over_ranks(c, e0.elapsed_time(e1) / 3)
+        iters = int(min(max(iters, min_ms / max(est, 1e-4)), 20000))
+        barrier(c)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
@@ -363,6 +374,7 @@ def timed(c, fn, iters, warmup=3):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     barrier(c)
+    c.last_iters = iters
     return max_over_ranks(c, ms)
 
 
@@ -556,14 +568,14 @@ def per_config_n1(c, args, sampler):
         Cc = fn()
         s1 = h.stats()
         m0 = sampler.mark()
-        ms = timed(c, fn, iters)
+        ms = timed(c, fn, iters, min_ms=400.0)
         m1 = sampler.mark()
         labels = set(ia) | set(ib)
         cplx = dtype.startswith("complex")
         flops = (8.0 if cplx else 2.0) * float(np.prod([ext[x] for x in labels], dtype=np.float64))
         par = parity_slab(c, ia, ib, ic, A, B, Cc, restrict)
         out[name] = {"workload": note, "dtype": dtype, "value": flops / (ms * 1e-3) / 1e12, "unit": "TFLOP/s", "ms": ms,
-                     "iters": iters, "flops": flops, "roofline": roof_fn(flops, ms), "clocks": sampler.window(m0, m1),
+                     "iters": c.last_iters, "flops": flops, "roofline": roof_fn(flops, ms), "clocks": sampler.window(m0, m1),
                      "launches_per_call": {k: v for k, v in s1.items() if v and k.startswith("launches")},
                      "parity": {"rel_frobenius": par, "tolerance": tol, "slab": {k: list(v) for k, v in restrict.items()}}}
         del A, B, Cc
@@ -575,7 +587,7 @@ def per_config_n1(c, args, sampler):
             lambda f, ms: fp64_roofline("gett_kernel<CoreZ<128,64,...>>", f, ms, "gett_z_cfg1_dram_bytes_per_launch"), 1e-12,
             "BASELINE configs[0]: two random ComplexF64 rank-4 tensors, dim 64, two summed labels (4096^3), scrambled layout "
             "A[k,i,l,j] B[n,l,m,k] -> C[m,j,n,i]")
-    out["config2_mps_mpo_chain"] = config2_chain(c, args, sampler, iters)
+    out["config2_mps_mpo_chain"] = config2_chain(c, args, sampler, max(iters, 50))
     chi, Dd, beta = 256, 8, 8
     run_one("config3_peps_batched_c64", "complex64", dict(l=chi, k=Dd, b=Dd, m=chi, q=Dd, r=chi, z=beta), "lkbmz", "mkqrz", "lbqrz",
             (3000, 3100), {"l": list(range(0, 256, 8)), "z": [5]},
@@ -655,10 +667,11 @@ def k1_rooflines(c, args, sampler):
         t = Tensor(dev_rand(c, shape, dt, 77), I(src))
         fn = lambda: t.permutedims(I(dst))
         m0 = sampler.mark()
-        ms = timed(c, fn, 20)
+        ms = timed(c, fn, 20, min_ms=200.0)
         nbytes = 2.0 * t.data.nbytes
         out[name] = hbm_roofline("permute kernels (csrc/permute.cu)", nbytes, ms)
         out[name]["clocks"] = sampler.window(m0, sampler.mark())
+        out[name]["iters"] = c.last_iters
         del t
         c.torch.cuda.empty_cache()
     return out
@@ -721,7 +734,7 @@ def sharded_configs(c, args, sampler):
     fn3 = lambda: binary_einsum(A3, B3, out=I("lbqrz"))
     C3 = fn3()
     m0 = sampler.mark()
-    ms = timed(c, fn3, iters)
+    ms = timed(c, fn3, iters, min_ms=300.0)
     flops3 = 8.0 * float(chi * Dd) ** 3 * (bl * min(world, beta))
     par = parity_slab(c, "lkbmz", "mkqrz", "lbqrz", A3, B3, C3, {"l": list(range(0, 256, 8)), "z": [0]})
     pars = [None] * world
@@ -764,8 +777,8 @@ def sharded_configs(c, args, sampler):
         mdist.all_reduce_sum(cc)
         return cc
     m0 = sampler.mark()
-    ms = timed(c, nccl_step, iters)
-    ms_gemm = timed(c, lambda: binary_einsum(A5, B5, out=I(ic)), iters)
+    ms = timed(c, nccl_step, iters, min_ms=300.0)
+    ms_gemm = timed(c, lambda: binary_einsum(A5, B5, out=I(ic)), iters, min_ms=100.0)
     res5["variants"]["nccl_all_reduce"] = {"value": flops5 / (ms * 1e-3) / 1e12, "unit": "TFLOP/s", "ms": ms, "ms_contraction_only": ms_gemm,
                                            "semantics": "all-reduce (every rank ends with the full C)",
                                            "parity_rel_frobenius": err_full(nccl_step()), "clocks": sampler.window(m0, sampler.mark())}
@@ -786,7 +799,7 @@ def sharded_configs(c, args, sampler):
                 sl = full[rank * mine.size:(rank + 1) * mine.size]
                 err = float(np.linalg.norm(mine - sl) / max(np.linalg.norm(sl), 1e-30))
             m0 = sampler.mark()
-            ms_f = timed(c, lambda: f(A5, B5, I(ic)), iters)
+            ms_f = timed(c, lambda: f(A5, B5, I(ic)), iters, min_ms=300.0)
             res5["variants"][key] = {"value": flops5 / (ms_f * 1e-3) / 1e12, "unit": "TFLOP/s", "ms": ms_f, "semantics": sem,
                                      ("parity_rel_frobenius" if key == "fused_all_reduce" else "rel_err_vs_nccl_all_reduce"): err,
                                      "clocks": sampler.window(m0, sampler.mark())}

@@ -264,12 +264,11 @@ class Handle:
             self._stream = stream_ptr
 
     def sync_stream_with_torch(self):
-        try:
-            import torch
-            if torch.cuda.is_available():
-                self.set_stream(int(torch.cuda.current_stream(self.device).cuda_stream))
-        except ImportError:
-            pass
+        raw = _raw_stream_fn()
+        if raw is not None:
+            sp = raw(self.device)              # torch._C._cuda_getCurrentRawStream: one C call, no Stream object
+            if sp != self._stream:
+                self.set_stream(sp)
 
     def synchronize(self):
         check(lib().mb200_stream_sync(self._h))
@@ -293,6 +292,25 @@ class Handle:
 
     def reset_stats(self):
         check(lib().mb200_reset_stats(self._h))
+
+
+_RAW_STREAM = [False, None]   # [resolved?, torch._C._cuda_getCurrentRawStream or None]
+
+
+def _raw_stream_fn():
+    """torch's current-stream getter when torch sees a GPU (resolved once), else None."""
+    if not _RAW_STREAM[0]:
+        fn = None
+        try:
+            import torch
+            if torch.cuda.is_available():
+                fn = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+                if fn is None:
+                    fn = lambda d: int(torch.cuda.current_stream(d).cuda_stream)  # noqa: E731
+        except ImportError:
+            pass
+        _RAW_STREAM[0], _RAW_STREAM[1] = True, fn
+    return _RAW_STREAM[1]
 
 
 def current_device() -> int:

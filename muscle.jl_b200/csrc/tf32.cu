@@ -550,74 +550,99 @@ __device__ __forceinline__ void spin_until(const int *flag, int epoch) {
     }
 }
 
-constexpr int RTHREADS = 256;   // 256 threads x <= 40 registers: co-resident with a 320-thread x 168-register GEMM CTA on one SM
+constexpr int RTHREADS = 128;   // 128 threads x <= 80 registers: co-resident with a 320-thread x 168-register GEMM CTA on one SM
+constexpr int RPARTS = 4;       // a unit is reduced by 4 work items (quarters of its vectors): short tail after the last GEMM tile
 
-// One CTA per owned unit at a time (unit = rank, rank + nranks, ... strided over the CTAs). A 16-byte vector is 2 consecutive rows
-// (complex) or 4 (real) of one column of the sub-tile.
-template <int BN, bool REAL, bool CTA2>
+// Work item = (owned unit, quarter); items are strided over the CTAs (one CTA per SM, next to the GEMM's CTA). A 16-byte vector is
+// 2 consecutive rows (complex) or 4 (real) of one column of the sub-tile. Memory-level parallelism is what makes this kernel: a
+// thread keeps 8 multimem.ld_reduce (MC) or 4 peer loads per step of the rank loop in flight - what the register budget of a
+// co-resident CTA allows - and the grid supplies the rest (148 x 128 x 8 x 16 B = 2.4 MB in flight per GPU).
+template <int BN, bool REAL, bool CTA2, bool MC>
 __global__ void __launch_bounds__(RTHREADS, 6) tf32_allreduce_kernel(const __grid_constant__ Tf32Params p, const __grid_constant__ DistParams d) {
     constexpr int NCTA = CTA2 ? 2 : 1;
     constexpr int PM = TBM * NCTA;
     constexpr int VE = REAL ? 4 : 2;                 // elements per 16-byte vector
     constexpr int ESZ = REAL ? 4 : 8;
-    constexpr int NVEC = TBM * BN / VE;
+    constexpr int NVEC = TBM * BN / VE, PVEC = NVEC / RPARTS;
+    constexpr int U = MC ? 8 : 4;
+    static_assert(PVEC % RTHREADS == 0, "part size");
     __shared__ int64_t sRow[TBM];
     __shared__ int64_t sCol[BN];
     const int tid = threadIdx.x;
     const int64_t owned = (d.nunits - d.rank + d.nranks - 1) / d.nranks;   // units rank, rank + nranks, ...
-    for (int64_t j = blockIdx.x; j < owned; j += gridDim.x) {
-        const int64_t u = j * d.nranks + d.rank;
+    const int64_t items = owned > 0 ? owned * RPARTS : 0;
+    for (int64_t j = blockIdx.x; j < items; j += gridDim.x) {
+        const int64_t u = (j / RPARTS) * d.nranks + d.rank;
+        const int part = (int)(j % RPARTS);
         const int64_t tile = u / NCTA;
         const int sub = (int)(u % NCTA);
         const TileCoord tc = tile_coord<BN, PM>(p, tile);
         const int64_t m0 = (int64_t)tc.m0 + sub * TBM;
-        __syncthreads();                               // previous unit's tables are no longer read
+        __syncthreads();                               // previous item's tables are no longer read
         if (tid < TBM) sRow[tid] = (m0 + tid < p.M) ? p.rowC[m0 + tid] + p.batC[tc.l] : -1;
         for (int i = tid; i < BN; i += RTHREADS) sCol[i] = (tc.n0 + i < p.N) ? p.colC[tc.n0 + i] : -1;
         if (tid < d.nranks) spin_until(d.flags[d.rank] + u * d.nranks + tid, d.epoch);
         __syncthreads();                               // all nranks partial sub-tiles of this unit are visible
         const size_t ubase = (size_t)u * (TBM * BN) * ESZ;
-#pragma unroll 2
-        for (int v = tid; v < NVEC; v += RTHREADS) {
-            const int e = v * VE, r = e % TBM, c = e / TBM;
-            const size_t off = ubase + (size_t)v * 16;
-            float4 acc;
-            if (d.mc_ws) {
-                acc = multimem_ld_reduce_f4(reinterpret_cast<const char *>(d.mc_ws) + off);
+        for (int v0 = part * PVEC + tid; v0 < (part + 1) * PVEC; v0 += RTHREADS * U) {
+            float4 acc[U];
+            if constexpr (MC) {
+#pragma unroll
+                for (int k = 0; k < U; k++) {
+                    const int v = v0 + k * RTHREADS;
+                    if (v < (part + 1) * PVEC) acc[k] = multimem_ld_reduce_f4(reinterpret_cast<const char *>(d.mc_ws) + ubase + (size_t)v * 16);
+                }
             } else {
-                acc = ld_relaxed_sys_f4(reinterpret_cast<const char *>(d.ws[0]) + off);
-                for (int s = 1; s < d.nranks; s++) {
-                    const float4 x = ld_relaxed_sys_f4(reinterpret_cast<const char *>(d.ws[s]) + off);
-                    acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+#pragma unroll
+                for (int k = 0; k < U; k++) {
+                    const int v = v0 + k * RTHREADS;
+                    if (v < (part + 1) * PVEC) acc[k] = ld_relaxed_sys_f4(reinterpret_cast<const char *>(d.ws[0]) + ubase + (size_t)v * 16);
+                }
+                for (int s = 1; s < d.nranks; s++) {   // rank order: deterministic, identical on every rank
+                    float4 x[U];
+                    const char *w = reinterpret_cast<const char *>(d.ws[s]) + ubase;
+#pragma unroll
+                    for (int k = 0; k < U; k++) {
+                        const int v = v0 + k * RTHREADS;
+                        if (v < (part + 1) * PVEC) x[k] = ld_relaxed_sys_f4(w + (size_t)v * 16);
+                    }
+#pragma unroll
+                    for (int k = 0; k < U; k++) { acc[k].x += x[k].x; acc[k].y += x[k].y; acc[k].z += x[k].z; acc[k].w += x[k].w; }
                 }
             }
-            const int64_t col = sCol[c];
-            if (col < 0) continue;
-            const int64_t r0 = sRow[r];
-            bool contig = r0 >= 0 && ((r0 + col) % VE) == 0;
 #pragma unroll
-            for (int i = 1; i < VE; i++) contig = contig && sRow[r + i] == r0 + i;
-            if (contig) {
-                const size_t co = (size_t)(r0 + col) * ESZ;
-                if (d.mc_c) multimem_st_f4(reinterpret_cast<char *>(d.mc_c) + co, acc);
-                else
-                    for (int s = 0; s < d.nranks; s++) *reinterpret_cast<float4 *>(reinterpret_cast<char *>(d.c[s]) + co) = acc;
-            } else {
-                const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
+            for (int k = 0; k < U; k++) {
+                const int v = v0 + k * RTHREADS;
+                if (v >= (part + 1) * PVEC) continue;
+                const int e = v * VE, r = e % TBM, c = e / TBM;
+                const int64_t col = sCol[c];
+                if (col < 0) continue;
+                const int64_t r0 = sRow[r];
+                bool contig = r0 >= 0 && ((r0 + col) % VE) == 0;
 #pragma unroll
-                for (int i = 0; i < VE; i++) {
-                    const int64_t ri = sRow[r + i];
-                    if (ri < 0) continue;
-                    const size_t co = (size_t)(ri + col) * ESZ;
-                    if constexpr (REAL) {
-                        if (d.mc_c) multimem_st_f1(reinterpret_cast<char *>(d.mc_c) + co, a4[i]);
-                        else
-                            for (int s = 0; s < d.nranks; s++) *reinterpret_cast<float *>(reinterpret_cast<char *>(d.c[s]) + co) = a4[i];
-                    } else {
-                        const float2 z = make_float2(a4[2 * i], a4[2 * i + 1]);
-                        if (d.mc_c) multimem_st_f2(reinterpret_cast<char *>(d.mc_c) + co, z);
-                        else
-                            for (int s = 0; s < d.nranks; s++) *reinterpret_cast<float2 *>(reinterpret_cast<char *>(d.c[s]) + co) = z;
+                for (int i = 1; i < VE; i++) contig = contig && sRow[r + i] == r0 + i;
+                if (contig) {
+                    const size_t co = (size_t)(r0 + col) * ESZ;
+                    if constexpr (MC) multimem_st_f4(reinterpret_cast<char *>(d.mc_c) + co, acc[k]);
+                    else
+                        for (int s = 0; s < d.nranks; s++) *reinterpret_cast<float4 *>(reinterpret_cast<char *>(d.c[s]) + co) = acc[k];
+                } else {
+                    const float a4[4] = {acc[k].x, acc[k].y, acc[k].z, acc[k].w};
+#pragma unroll
+                    for (int i = 0; i < VE; i++) {
+                        const int64_t ri = sRow[r + i];
+                        if (ri < 0) continue;
+                        const size_t co = (size_t)(ri + col) * ESZ;
+                        if constexpr (REAL) {
+                            if constexpr (MC) multimem_st_f1(reinterpret_cast<char *>(d.mc_c) + co, a4[i]);
+                            else
+                                for (int s = 0; s < d.nranks; s++) *reinterpret_cast<float *>(reinterpret_cast<char *>(d.c[s]) + co) = a4[i];
+                        } else {
+                            const float2 z = make_float2(a4[2 * i], a4[2 * i + 1]);
+                            if constexpr (MC) multimem_st_f2(reinterpret_cast<char *>(d.mc_c) + co, z);
+                            else
+                                for (int s = 0; s < d.nranks; s++) *reinterpret_cast<float2 *>(reinterpret_cast<char *>(d.c[s]) + co) = z;
+                        }
                     }
                 }
             }
@@ -818,15 +843,18 @@ cudaError_t launch_allreduce_bn(const GettParams &g, const DistDesc &dist, cudaS
     d.mc_ws = dist.mc_ws; d.mc_c = dist.mc_c;
     const int64_t owned = (geo.nunits - dist.rank + dist.nranks - 1) / dist.nranks;
     // a rank that owns nothing still launches one CTA: its done flag must go up
-    static const int rctas = [] { const char *e = getenv("MB200_DIST_REDUCER_CTAS"); return e ? std::max(1, atoi(e)) : 16; }();
-    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(owned, rctas));
+    static const int rctas = [] { const char *e = getenv("MB200_DIST_REDUCER_CTAS"); return e ? std::max(1, atoi(e)) : 148; }();
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(owned * RPARTS, rctas));   // one reducer CTA per SM
+    const bool mc = d.mc_ws != nullptr;
     if constexpr (pair_ok<BN, REAL>()) {
         if (geo.pair) {
-            tf32_allreduce_kernel<BN, REAL, true><<<grid, RTHREADS, 0, s>>>(p, d);
+            if (mc) tf32_allreduce_kernel<BN, REAL, true, true><<<grid, RTHREADS, 0, s>>>(p, d);
+            else tf32_allreduce_kernel<BN, REAL, true, false><<<grid, RTHREADS, 0, s>>>(p, d);
             return cudaGetLastError();
         }
     }
-    tf32_allreduce_kernel<BN, REAL, false><<<grid, RTHREADS, 0, s>>>(p, d);
+    if (mc) tf32_allreduce_kernel<BN, REAL, false, true><<<grid, RTHREADS, 0, s>>>(p, d);
+    else tf32_allreduce_kernel<BN, REAL, false, false><<<grid, RTHREADS, 0, s>>>(p, d);
     return cudaGetLastError();
 }
 }  // namespace

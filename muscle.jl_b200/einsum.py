@@ -85,11 +85,12 @@ def _common_device(*tensors) -> int:
 # function of (labels, shapes, eltypes), so it is computed once per signature and the ctypes argument arrays are reused.
 # Entry: (T, dtype enum of T, shape_c, mc, ma, mb, ea, eb, len(mc), len(ma), len(mb)) with the ctypes arrays ready to pass.
 _SIG_CACHE: dict = {}
+_FRONT_CACHE: dict = {}
 _SIG_CACHE_CAP = 4096
 
 
 def _signature(inds_c, a: Tensor, b: Tensor):
-    key = (tuple(inds_c), a._inds, b._inds, a.data.shape, b.data.shape, a.data.dtype, b.data.dtype)
+    key = (inds_c, a._inds, b._inds, a.data.shape, b.data.shape, a.data.dtype, b.data.dtype)
     sig = _SIG_CACHE.get(key)
     if sig is None:
         ma, mb, mc = flatten_labels(a.inds, b.inds, inds_c)
@@ -97,25 +98,36 @@ def _signature(inds_c, a: Tensor, b: Tensor):
         shape_c = _result_shape(inds_c, a, b)
         if len(_SIG_CACHE) >= _SIG_CACHE_CAP:
             _SIG_CACHE.clear()
+        nbytes = (int(np.prod(shape_c, dtype=np.int64)) if shape_c else 1) * T.itemsize
         sig = _SIG_CACHE[key] = (T, _lib.dtype_enum(T), shape_c, _lib.i32(mc), _lib.i32(ma), _lib.i32(mb),
                                  _lib.i64(a.shape), _lib.i64(b.shape), len(mc), len(ma), len(mb),
-                                 _lib.dtype_enum(a.dtype), _lib.dtype_enum(b.dtype))
+                                 _lib.dtype_enum(a.dtype), _lib.dtype_enum(b.dtype), nbytes)
     return sig
+
+
+def _b200_device_fast(inds_c: tuple, a: Tensor, b: Tensor) -> Tensor:
+    """Both operands device-resident: cached bookkeeping, one allocation, one C-ABI call."""
+    da, db = a.data, b.data
+    if da.device != db.device:
+        raise ArgumentError(f"operands live on different devices {sorted({da.device, db.device})}; move them to one GPU first")
+    T, eT, shape_c, mc, ma, mb, ea, eb, nc, na, nb, eA, eB, nbytes = _signature(inds_c, a, b)
+    dc = B200Array._fast(shape_c, T, da.device, nbytes)
+    st = _LIB_CALL[0](dc.handle._h, dc.ptr, eT, nc, mc, None, da.ptr, eA, na, ma, ea, None, db.ptr, eB, nb, mb, eb, None)
+    if st:
+        _lib.check(st)
+    return Tensor._trusted(dc, inds_c)
+
+
+_LIB_CALL = [None]
 
 
 def _b200_out_of_place(inds_c, a: Tensor, b: Tensor) -> Tensor:
     """`binary_einsum(::BackendB200, inds_c, a, b)`: allocates C, returns Tensor(C, inds_c)."""
-    inds_c = _as_index_list(inds_c)
     if a.on_device and b.on_device:
-        # device fast path: cached bookkeeping, one allocation, one C-ABI call
-        da, db = a.data, b.data
-        if da.device != db.device:
-            raise ArgumentError(f"operands live on different devices {sorted({da.device, db.device})}; move them to one GPU first")
-        T, eT, shape_c, mc, ma, mb, ea, eb, nc, na, nb, eA, eB = _signature(inds_c, a, b)
-        dc = B200Array(shape_c, T, da.device)
-        _lib.check(_lib.lib().mb200_binary_einsum(
-            dc.handle.ptr, dc.ptr, eT, nc, mc, None, da.ptr, eA, na, ma, ea, None, db.ptr, eB, nb, mb, eb, None))
-        return Tensor(dc, inds_c)
+        if _LIB_CALL[0] is None:
+            _LIB_CALL[0] = _lib.lib().mb200_binary_einsum
+        return _b200_device_fast(tuple(_as_index_list(inds_c)), a, b)
+    inds_c = _as_index_list(inds_c)
     ma, mb, mc = flatten_labels(a.inds, b.inds, inds_c)
     T = _promote(a, b)
     L = _lib.lib()
@@ -191,8 +203,25 @@ def binary_einsum(*args, dims=None, out=None) -> Tensor:
         a, b = args
         if not isinstance(a, Tensor) or not isinstance(b, Tensor):
             raise ArgumentError("binary_einsum(a::Tensor, b::Tensor; dims, out)")
-        inds_c = frontend_inds_c(a.inds, b.inds, dims=dims, out=out)
-        backend = choose_backend("binary_einsum", a.parent, b.parent)
+        # kwargs -> inds_c is a pure function of the labels: cached per (labels, dims, out)
+        try:
+            fkey = (a._inds, b._inds, None if dims is None else (dims if isinstance(dims, Index) else tuple(dims)),
+                    None if out is None else tuple(out))
+            inds_c = _FRONT_CACHE.get(fkey)
+        except TypeError:
+            fkey, inds_c = None, None
+        if inds_c is None:
+            inds_c = tuple(frontend_inds_c(a.inds, b.inds, dims=dims, out=out))
+            if fkey is not None:
+                if len(_FRONT_CACHE) >= _SIG_CACHE_CAP:
+                    _FRONT_CACHE.clear()
+                _FRONT_CACHE[fkey] = inds_c
+        backend = choose_backend("binary_einsum", a.data, b.data)
+        if type(backend) is BackendB200 and a.on_device and b.on_device:
+            if _LIB_CALL[0] is None:
+                _LIB_CALL[0] = _lib.lib().mb200_binary_einsum
+            return _b200_device_fast(inds_c, a, b)
+        inds_c = list(inds_c)
     else:
         raise ArgumentError("binary_einsum(a, b; dims, out) or binary_einsum(backend, inds_c, a, b)")
     if isinstance(backend, BackendB200):

@@ -50,6 +50,19 @@ def findperm(frm, to):
     return perm
 
 
+_TORCH_DEV: dict = {}   # device index -> (torch module, torch.device, torch.uint8) or False
+
+
+def _torch_device(index):
+    try:
+        import torch
+        ok = torch.cuda.is_available()
+    except ImportError:
+        ok = False
+    _TORCH_DEV[index] = (torch, torch.device("cuda", index), torch.uint8) if ok else False
+    return _TORCH_DEV[index]
+
+
 class B200Array:
     """Dense column-major array in B200 HBM. Memory comes from torch's caching allocator when torch
     sees a GPU (so it is ordered with torch streams), else from mb200_malloc."""
@@ -67,6 +80,27 @@ class B200Array:
             self.ptr = int(_ptr)
         else:
             self.ptr = self._alloc(max(self.nbytes, 1))
+
+    @classmethod
+    def _fast(cls, shape, dtype, device, nbytes):
+        """Trusted constructor of the launch-bound fast path: `shape` a tuple of ints, `dtype` a supported np.dtype, `nbytes`
+        precomputed; memory from torch's caching allocator (no dtype / shape re-validation)."""
+        self = object.__new__(cls)
+        self.shape, self.dtype, self.nbytes = shape, dtype, nbytes
+        h = self.handle = _lib.Handle.get(device)
+        self.device = h.device
+        self._own_malloc = False
+        tv = _TORCH_DEV.get(h.device)
+        if tv is None:
+            tv = _torch_device(h.device)
+        if tv is False:
+            self._owner = None
+            self.ptr = self._alloc(max(nbytes, 1))
+        else:
+            torch, dev, u8 = tv
+            self._owner = torch.empty(max(nbytes, 1), dtype=u8, device=dev)
+            self.ptr = self._owner.data_ptr()
+        return self
 
     def _alloc(self, nbytes):
         try:
@@ -159,6 +193,13 @@ class Tensor:
                 raise DimensionMismatch("nonuniform size of repeated indices")
         self.data = data
         self._inds = tuple(inds)
+
+    @classmethod
+    def _trusted(cls, data, inds_tuple):
+        """Result of a backend call: labels and shape are consistent by construction (no constructor checks)."""
+        self = object.__new__(cls)
+        self.data, self._inds = data, inds_tuple
+        return self
 
     # accessors the backend shim needs (src/Tensor.jl:69,144,156-158,241-242)
     @property

@@ -92,7 +92,8 @@ def main():
             check(tag, rel_frobenius(got.astype(np.complex128), ref), 1e-5)
             # all ranks hold the same bits
             digest = [None] * world
-            dist.all_gather_object(digest, hash(got.tobytes()))
+            import hashlib
+            dist.all_gather_object(digest, hashlib.sha1(got.tobytes()).hexdigest())
             same = len(set(digest)) == 1
             ok = ok and same
             report[tag]["bit_identical_across_ranks"] = same
