@@ -291,7 +291,8 @@ int ensure_side_stream(mb200_handle_t h) {
     if (h->side) return MB200_OK;
     int lo = 0, hi = 0;
     MB200_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    MB200_CUDA(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, hi));
+    (void)hi;
+    MB200_CUDA(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, lo));   // never ahead of the GEMM in the CTA scheduler
     MB200_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     MB200_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     return MB200_OK;
@@ -406,17 +407,6 @@ int contract_device(mb200_handle_t h, void *C, TensorDesc &dC, const int64_t *st
         void *pa = nullptr, *pb = nullptr;
         const size_t W = p.dtype == MB200_F32 ? 2 : 4;
         const size_t ba = (size_t)p.L * rows_a * W * Kp * sizeof(float), bb = (size_t)p.L * rows_b * W * Kp * sizeof(float);
-        if (dist && (phases & DIST_REDUCE) && (phases & DIST_CONTRACT)) {
-            // the owner-side reducer first, on the side stream: it is resident (spinning on unit flags) before the GEMM's
-            // CTAs arrive and drains finished units while the GEMM is still producing the later ones
-            if ((st = ensure_side_stream(h)) != MB200_OK) return st;
-            MB200_CUDA(cudaEventRecord(h->ev_fork, s));
-            MB200_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-            GettParams gr = cp->gp;
-            MB200_CUDA(launch_tf32_allreduce(p.dtype, gr, *dist, h->side));
-            MB200_CUDA(cudaEventRecord(h->ev_join, h->side));
-            h->stats.launches_reduce++; h->stats.launches_total++;
-        }
         if (dist && !(phases & DIST_CONTRACT)) {
             e = cudaSuccess;
             if (phases & DIST_REDUCE) {
@@ -451,9 +441,26 @@ int contract_device(mb200_handle_t h, void *C, TensorDesc &dC, const int64_t *st
             g.K = Kp;
             if (sc) g.sc = *sc;
             bool pair = false;
+            if (dist && (phases & DIST_REDUCE)) {
+                // fork point of the owner-side reducer: after the packs (and everything the caller enqueued before), so that it
+                // becomes runnable together with the GEMM and not earlier
+                if ((st = ensure_side_stream(h)) != MB200_OK) return st;
+                MB200_CUDA(cudaEventRecord(h->ev_fork, s));
+            }
             e = launch_tf32_gemm(p.dtype, pa, pb, g, mixed, s, &pair, dist);
             h->stats.launches_tcgen05++;
             if (pair) h->stats.launches_tcgen05_pair++;
+            if (dist && (phases & DIST_REDUCE) && e == cudaSuccess) {
+                // The reducer is launched AFTER the GEMM, on the side stream: the persistent GEMM CTAs (one per SM, maximum shared-
+                // memory carve-out) are resident first and every SM still has room for exactly one reducer CTA (128 threads x 80
+                // registers, 3 KB of shared memory) next to them, so the two kernels run CONCURRENTLY: the reducer drains finished
+                // units while the GEMM produces the later ones. Should the reducer win the race for some SMs, its CTAs ask for the
+                // same carve-out (tf32_configure), and its grid leaves most SMs free, so the GEMM can never be starved.
+                MB200_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+                MB200_CUDA(launch_tf32_allreduce(p.dtype, cp->gp, *dist, h->side));
+                MB200_CUDA(cudaEventRecord(h->ev_join, h->side));
+                h->stats.launches_reduce++; h->stats.launches_total++;
+            }
         }
         cudaFreeAsync(pa, s);
         cudaFreeAsync(pb, s);

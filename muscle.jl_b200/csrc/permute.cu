@@ -469,7 +469,40 @@ __global__ void __launch_bounds__(256) pack_gather_kernel(const __grid_constant_
 //   shared-memory tile [row][k]. Write: 16-byte piece p of the line of (row, 8-k group): chunk type p >> 1 (re_hi, re_x, im_hi,
 //   im_x - or hi, x for Float32), 4 consecutive k each; the four lanes that need the same 4 elements read them as a broadcast.
 // Algorithmic bytes per element: sizeof(T) read + 2 sizeof(T) written (the hi and x planes) - declared in DESIGN 3.5.
-template <bool REAL>
+// split of 4 values into their hi words (tf32) and x words (fp32 remainder, or the bf16 cross-term pair of the mixed scheme).
+// AUX 0: 3xTF32 (hi = truncated tf32, x = remainder), 1 / 2: TF32 + BF16, row / column operand. The fast path is 3 instructions per
+// value (cvt.rna.tf32, FADD, cvt.rn.bf16x2): rounding can reach infinity only from an exponent of 254 or 255, so ONE test of the
+// four input magnitudes replaces the per-conversion overflow guards; the rare slow path is the guarded scalar code of put().
+template <int AUX>
+__device__ __forceinline__ void split4(const float (&in)[4], float4 &hi, float4 &xw) {
+    float h[4], x[4];
+    if constexpr (AUX == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) { h[i] = tf32_hi(in[i]); x[i] = in[i] - h[i]; }
+    } else {
+        const uint32_t m01 = max(__float_as_uint(in[0]) & 0x7FFFFFFFu, __float_as_uint(in[1]) & 0x7FFFFFFFu);
+        const uint32_t m23 = max(__float_as_uint(in[2]) & 0x7FFFFFFFu, __float_as_uint(in[3]) & 0x7FFFFFFFu);
+        if (max(m01, m23) < 0x7F000000u) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                uint32_t r, w;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(in[i]));
+                h[i] = __uint_as_float(r);
+                const float lo = in[i] - h[i];
+                if constexpr (AUX == 1) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(lo), "f"(in[i]));      // (x, x_lo): x in the low half
+                else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(in[i]), "f"(lo));                          // (x_lo, x)
+                x[i] = __uint_as_float(w);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) { h[i] = tf32_rn(in[i]); x[i] = cross_word(in[i], in[i] - h[i], AUX); }
+        }
+    }
+    hi = make_float4(h[0], h[1], h[2], h[3]);
+    xw = make_float4(x[0], x[1], x[2], x[3]);
+}
+
+template <bool REAL, int AUX>
 __global__ void __launch_bounds__(256) pack_lines_kernel(const __grid_constant__ PackGather q, const void *__restrict__ srcv,
                                                          float *__restrict__ dst) {
     using E = typename std::conditional<REAL, float, float2>::type;
@@ -487,7 +520,7 @@ __global__ void __launch_bounds__(256) pack_lines_kernel(const __grid_constant__
     const int64_t l = b / tiles_r;
     if (tid < TR) sRow[tid] = (r0 + tid < q.rows) ? q.row_tab[r0 + tid] : -1;
     else if (tid < TR + TK) sK[tid - TR] = (k0 + tid - TR < q.K) ? q.k_tab[k0 + tid - TR] : -1;
-    const int64_t bat = q.bat_tab[l];
+    const E *srcb = src + q.bat_tab[l];
     __syncthreads();
     E v[8];
     if (q.kmajor) {
@@ -497,7 +530,7 @@ __global__ void __launch_bounds__(256) pack_lines_kernel(const __grid_constant__
         for (int i = 0; i < 8; i++) {
             const int64_t ro = sRow[rb + 8 * i];
             v[i] = E{};
-            if (ko >= 0 && ro >= 0) v[i] = src[ro + ko + bat];
+            if (ko >= 0 && ro >= 0) v[i] = srcb[ro + ko];
         }
 #pragma unroll
         for (int i = 0; i < 8; i++) tile[rb + 8 * i][kk] = v[i];
@@ -508,24 +541,25 @@ __global__ void __launch_bounds__(256) pack_lines_kernel(const __grid_constant__
         for (int i = 0; i < 8; i++) {
             const int64_t ko = sK[kb + 4 * i];
             v[i] = E{};
-            if (ko >= 0 && ro >= 0) v[i] = src[ro + ko + bat];
+            if (ko >= 0 && ro >= 0) v[i] = srcb[ro + ko];
         }
 #pragma unroll
         for (int i = 0; i < 8; i++) tile[rr][kb + 4 * i] = v[i];
     }
     __syncthreads();
-    const int aux = q.aux;
-    auto hi_of = [aux](float x) { return aux == 0 ? tf32_hi(x) : tf32_rn(x); };
-    auto x_of = [aux](float x, float h) { return aux == 0 ? x - h : cross_word(x, x - h, aux); };
-    constexpr int PIECES = REAL ? 4 : 8;                  // 16-byte pieces per 8-k group
-    constexpr int STORES = TR * (TK / 8) * PIECES / 256;  // per thread: 4 (real) / 8 (complex)
+    // Write phase. A work item = 4 consecutive k of one component (re / im; Float32: the value) of one row: it produces the matching
+    // 16-byte pieces of the hi chunk and of the x chunk. Complex: 4 items per (row, 8-k group) -> lanes 4j..4j+3 cover one 128-byte
+    // line; the 32 lanes of a warp cover two rows' worth of 4 groups... item index = tid + 256 * i.
+    constexpr int ITEMS_PER_GROUP = REAL ? 2 : 4;                       // (half) x (re, im)
+    constexpr int NITEMS = TR * (TK / 8) * ITEMS_PER_GROUP;             // 512 (real) / 1024 (complex)
+    float *dl = dst + l * q.rows * (W * q.Kp);
 #pragma unroll
-    for (int i = 0; i < STORES; i++) {
-        const int sidx = tid + 256 * i;
-        const int pc = sidx % PIECES, g = (sidx / PIECES) & 3, r = sidx / (PIECES * 4);
+    for (int i = 0; i < NITEMS / 256; i++) {
+        const int it = tid + 256 * i;
+        const int sub = it % ITEMS_PER_GROUP, g = (it / ITEMS_PER_GROUP) & 3, r = it / (ITEMS_PER_GROUP * 4);
         const int64_t row = r0 + r, kg = k0 + g * 8;
         if (row >= q.rows || kg >= q.Kp) continue;
-        const int c = pc >> 1, half = pc & 1;
+        const int half = sub & 1, comp = sub >> 1;                      // comp: 0 = re (or the real value), 1 = im
         const E *e = &tile[r][g * 8 + half * 4];
         float in[4];
         if constexpr (REAL) {
@@ -533,17 +567,14 @@ __global__ void __launch_bounds__(256) pack_lines_kernel(const __grid_constant__
             in[0] = t.x; in[1] = t.y; in[2] = t.z; in[3] = t.w;
         } else {
             const float4 t0 = *reinterpret_cast<const float4 *>(e), t1 = *reinterpret_cast<const float4 *>(e + 2);
-            if (c < 2) { in[0] = t0.x; in[1] = t0.z; in[2] = t1.x; in[3] = t1.z; }
+            if (comp == 0) { in[0] = t0.x; in[1] = t0.z; in[2] = t1.x; in[3] = t1.z; }
             else { in[0] = t0.y; in[1] = t0.w; in[2] = t1.y; in[3] = t1.w; }
         }
-        float4 w;
-        if ((c & 1) == 0) {
-            w = make_float4(hi_of(in[0]), hi_of(in[1]), hi_of(in[2]), hi_of(in[3]));
-        } else {
-            w = make_float4(x_of(in[0], hi_of(in[0])), x_of(in[1], hi_of(in[1])), x_of(in[2], hi_of(in[2])), x_of(in[3], hi_of(in[3])));
-        }
-        float *d = dst + (l * q.rows + row) * (W * q.Kp) + (kg >> 3) * (8 * W) + c * 8 + half * 4;
-        *reinterpret_cast<float4 *>(d) = w;
+        float4 hi, xw;
+        split4<AUX>(in, hi, xw);
+        float *d = dl + row * (W * q.Kp) + (kg >> 3) * (8 * W) + comp * 16 + half * 4;   // chunk order: hi | x | (im) hi | x
+        *reinterpret_cast<float4 *>(d) = hi;
+        *reinterpret_cast<float4 *>(d + 8) = xw;
     }
 }
 
@@ -968,8 +999,15 @@ cudaError_t launch_pack_gather(int dtype, const void *src, const int64_t *row_ta
     static const int lines = [] { const char *e = getenv("MB200_PACK_LINES"); return e ? atoi(e) : 1; }();
     if (lines && (((uintptr_t)dst) & 15) == 0) {   // whole 128-byte lines, 16-byte stores (MB200_PACK_LINES=0: the 4-byte writer, A/B)
         const int64_t g2 = ((Kp + 31) / 32) * ((rows + 63) / 64) * L;
-        if (dtype == MB200_F32) pack_lines_kernel<true><<<(unsigned)g2, 256, 0, s>>>(q, src, dst);
-        else pack_lines_kernel<false><<<(unsigned)g2, 256, 0, s>>>(q, src, dst);
+        const bool real = dtype == MB200_F32;
+        switch (q.aux) {
+            case 0: if (real) pack_lines_kernel<true, 0><<<(unsigned)g2, 256, 0, s>>>(q, src, dst);
+                    else pack_lines_kernel<false, 0><<<(unsigned)g2, 256, 0, s>>>(q, src, dst); break;
+            case 1: if (real) pack_lines_kernel<true, 1><<<(unsigned)g2, 256, 0, s>>>(q, src, dst);
+                    else pack_lines_kernel<false, 1><<<(unsigned)g2, 256, 0, s>>>(q, src, dst); break;
+            default: if (real) pack_lines_kernel<true, 2><<<(unsigned)g2, 256, 0, s>>>(q, src, dst);
+                     else pack_lines_kernel<false, 2><<<(unsigned)g2, 256, 0, s>>>(q, src, dst); break;
+        }
         return cudaGetLastError();
     }
     if (dtype == MB200_F32) pack_gather_kernel<true><<<(unsigned)grid, 256, 0, s>>>(q, src, dst);

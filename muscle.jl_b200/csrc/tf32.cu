@@ -804,6 +804,16 @@ cudaError_t tf32_configure() {
     MB200_TCFG(128, false, false); MB200_TCFG(64, false, false); MB200_TCFG(256, true, false); MB200_TCFG(128, true, false);
     MB200_TCFG(128, false, true); MB200_TCFG(256, true, true);
 #undef MB200_TCFG
+    // reducer of the fused all-reduce: same (maximum) shared-memory carve-out as the GEMM it shares SMs with
+#define MB200_RCFG(BN, REAL, CTA2, MC)                                                                                      \
+    if (e == cudaSuccess)                                                                                                   \
+        e = cudaFuncSetAttribute(tf32_allreduce_kernel<BN, REAL, CTA2, MC>, cudaFuncAttributePreferredSharedMemoryCarveout, \
+                                 (int)cudaSharedmemCarveoutMaxShared)
+    MB200_RCFG(128, false, false, false); MB200_RCFG(128, false, false, true); MB200_RCFG(64, false, false, false);
+    MB200_RCFG(64, false, false, true); MB200_RCFG(256, true, false, false); MB200_RCFG(256, true, false, true);
+    MB200_RCFG(128, true, false, false); MB200_RCFG(128, true, false, true); MB200_RCFG(128, false, true, false);
+    MB200_RCFG(128, false, true, true); MB200_RCFG(256, true, true, false); MB200_RCFG(256, true, true, true);
+#undef MB200_RCFG
     return e;
 }
 
@@ -843,8 +853,11 @@ cudaError_t launch_allreduce_bn(const GettParams &g, const DistDesc &dist, cudaS
     d.mc_ws = dist.mc_ws; d.mc_c = dist.mc_c;
     const int64_t owned = (geo.nunits - dist.rank + dist.nranks - 1) / dist.nranks;
     // a rank that owns nothing still launches one CTA: its done flag must go up
-    static const int rctas = [] { const char *e = getenv("MB200_DIST_REDUCER_CTAS"); return e ? std::max(1, atoi(e)) : 148; }();
-    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(owned * RPARTS, rctas));   // one reducer CTA per SM
+    // At most one reducer CTA per SM can sit next to a GEMM CTA. The default grid leaves 84 SMs untouched: even if no SM could be
+    // shared (the reducer CTAs resident first, with a different shared-memory carve-out), the persistent GEMM still makes progress
+    // and its remaining CTAs run as soon as the first ones retire - a slower run, never a deadlock. 148 deadlocks in that case.
+    static const int rctas = [] { const char *e = getenv("MB200_DIST_REDUCER_CTAS"); return e ? std::min(120, std::max(1, atoi(e))) : 64; }();
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(owned * RPARTS, rctas));
     const bool mc = d.mc_ws != nullptr;
     if constexpr (pair_ok<BN, REAL>()) {
         if (geo.pair) {
