@@ -296,6 +296,11 @@ int mb200_binary_einsum_allreduce(mb200_handle_t handle, int dtypeC, int nmodeC,
                                   const int64_t *extentsB, const int64_t *stridesB,
                                   const mb200_comm_t *comm, int phases);
 
+/* Diagnostics: with MB200_DIST_TIMELINE=1 every fused all-reduce stamps %globaltimer (ns) into 8 slots - [0] first GEMM CTA starts,
+ * [1] last GEMM epilogue ends, [2] first reducer CTA starts, [3] first reducer unit ready, [4] last reducer CTA done, [5] all done
+ * flags seen - readable after the call with this entry (synchronises the device). */
+int mb200_dist_timeline(mb200_handle_t handle, unsigned long long *out8);
+
 /* ---- CUDA-graph replay of a fixed sequence of calls (n-ary contraction chains) ------------
  * Everything enqueued on the handle's stream between graph_begin and graph_end (binary_einsum, unary_einsum,
  * hadamard, permute ... on fixed device pointers) is captured instead of executed and can then be replayed with one

@@ -147,6 +147,7 @@ PROTOTYPES = {
                                        _vp, _i, _i, _i32p, _i64p, _i64p,
                                        _vp, _i, _i, _i32p, _i64p, _i64p,
                                        C.POINTER(Comm), _i], C.c_int),
+    "mb200_dist_timeline": ([_vp, C.POINTER(C.c_ulonglong)], C.c_int),
     "mb200_graph_begin": ([_vp], C.c_int),
     "mb200_graph_end": ([_vp, C.POINTER(_vp)], C.c_int),
     "mb200_graph_launch": ([_vp, _vp], C.c_int),

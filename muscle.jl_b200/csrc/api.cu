@@ -66,6 +66,7 @@ struct mb200_handle_s {
     // cross-GPU split-K: the reducer runs on a high-priority side stream, concurrently with the GEMM on `stream`
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    unsigned long long *timeline = nullptr;   // MB200_DIST_TIMELINE=1: globaltimer stamps of the last fused all-reduce (diagnostics)
     int *svd_info = nullptr;   // 8 ints written by the last mb200_svd_thin on this handle (sweeps, converged, ...)
 };
 
@@ -277,6 +278,25 @@ bool build_pack_params(const Plan &p, int which, bool mixed, PermuteParams &q, i
     return true;
 }
 
+// Row visiting order of the line-writer pack for one operand (which = 0: row operand / mleft, 1: column operand / mright): the
+// merged row modes sorted by the operand's own stride. nd = 0 when that is already the C-order walk or there are too many modes.
+PackRowOrder pack_row_order(const Plan &p, int which) {
+    PackRowOrder o{};
+    const std::vector<GroupMode> &g = which ? p.mright : p.mleft;
+    if (g.size() < 2 || g.size() > (size_t)MB200_PACK_DIGITS) return o;
+    std::vector<int> idx(g.size());
+    std::vector<int64_t> w(g.size());
+    int64_t acc = 1;
+    for (size_t i = 0; i < g.size(); i++) { idx[i] = (int)i; w[i] = acc; acc *= g[i].extent; }
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return (which ? g[a].sb : g[a].sa) < (which ? g[b].sb : g[b].sa); });
+    bool identity = true;
+    for (size_t i = 0; i < idx.size(); i++) identity = identity && idx[i] == (int)i;
+    if (identity) return o;
+    o.nd = (int)g.size();
+    for (size_t i = 0; i < idx.size(); i++) { o.ext[i] = g[idx[i]].extent; o.weight[i] = w[idx[i]]; }
+    return o;
+}
+
 // span (in elements) touched by a possibly strided tensor
 int64_t span_of(const TensorDesc &t) {
     int64_t s = 1;
@@ -291,8 +311,8 @@ int ensure_side_stream(mb200_handle_t h) {
     if (h->side) return MB200_OK;
     int lo = 0, hi = 0;
     MB200_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    (void)hi;
-    MB200_CUDA(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, lo));   // never ahead of the GEMM in the CTA scheduler
+    (void)lo;
+    MB200_CUDA(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, hi));   // the reducer's few CTAs are placed first
     MB200_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     MB200_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     return MB200_OK;
@@ -429,9 +449,10 @@ int contract_device(mb200_handle_t h, void *C, TensorDesc &dC, const int64_t *st
             e = launch_permute(p.dtype, qa, R, pa, s);
             if (e == cudaSuccess) e = launch_permute(p.dtype, qb, Q, pb, s);
         } else {
-            e = launch_pack_gather(p.dtype, R, t.rowA, t.kA, t.batA, p.M, p.K, Kp, p.L, p.a_kmajor, mixed ? 2 : 1, (float *)pa, s);
+            const PackRowOrder oa = pack_row_order(p, 0), ob = pack_row_order(p, 1);
+            e = launch_pack_gather(p.dtype, R, t.rowA, t.kA, t.batA, p.M, p.K, Kp, p.L, p.a_kmajor, mixed ? 2 : 1, (float *)pa, s, &oa);
             if (e == cudaSuccess)
-                e = launch_pack_gather(p.dtype, Q, t.colB, t.kB, t.batB, p.N, p.K, Kp, p.L, p.b_kmajor, mixed ? 3 : 1, (float *)pb, s);
+                e = launch_pack_gather(p.dtype, Q, t.colB, t.kB, t.batB, p.N, p.K, Kp, p.L, p.b_kmajor, mixed ? 3 : 1, (float *)pb, s, &ob);
         }
         h->stats.launches_permute += 2;
         h->stats.launches_total += 2;
@@ -441,31 +462,48 @@ int contract_device(mb200_handle_t h, void *C, TensorDesc &dC, const int64_t *st
             g.K = Kp;
             if (sc) g.sc = *sc;
             bool pair = false;
-            if (dist && (phases & DIST_REDUCE)) {
-                // fork point of the owner-side reducer: after the packs (and everything the caller enqueued before), so that it
-                // becomes runnable together with the GEMM and not earlier
-                if ((st = ensure_side_stream(h)) != MB200_OK) return st;
-                MB200_CUDA(cudaEventRecord(h->ev_fork, s));
+            DistDesc dd{};
+            if (dist) {
+                dd = *dist;
+                // Overlap policy. Reserving SMs costs the persistent GEMM whole rounds (512 pair tiles on 74 TPCs are 6.92 rounds: ANY
+                // reservation makes them 8, +14 %), so it only pays when the reduction is long: each rank pulls and pushes
+                // 2 |C| / nranks bytes. Measured (tools/diag_allreduce.py): N = 2 (134 MB per rank) 1.14 ms overlapped vs 1.35 ms
+                // one after the other; at N = 8 (34 MB) the reducer on all 148 SMs takes ~30 us and running it after the GEMM wins.
+                // MB200_DIST_OVERLAP = 0 / 1 forces one-after-the-other / overlapped; MB200_DIST_REDUCER_SMS sets the reservation
+                // (default 12 SMs with an NVLS multicast mapping, 24 with peer loads / stores).
+                static const int overlap = [] { const char *e = getenv("MB200_DIST_OVERLAP"); return e ? atoi(e) : -1; }();
+                static const int rsms = [] { const char *e = getenv("MB200_DIST_REDUCER_SMS"); return e ? atoi(e) : 0; }();
+                const double reduce_bytes = 2.0 * (double)p.M * (double)p.N * (double)p.L * (double)dtype_size(p.dtype) / dd.nranks;
+                const bool want_overlap = overlap >= 0 ? overlap != 0 : reduce_bytes >= 64.0e6;
+                const bool fused_now = (phases & DIST_REDUCE) && (phases & DIST_CONTRACT) && want_overlap;
+                dd.reserve_sms = fused_now ? std::min(96, std::max(2, rsms > 0 ? rsms : (dd.mc_ws ? 12 : 24))) & ~1 : 0;
+                if (fused_now) {
+                    // the reducer first, on the side stream (it must not start before everything the caller enqueued so far: the
+                    // previous consumer of C and of the workspace); it occupies its reserved SMs and polls unit flags while the
+                    // packs and the GEMM run on the others
+                    if ((st = ensure_side_stream(h)) != MB200_OK) return st;
+                    MB200_CUDA(cudaEventRecord(h->ev_fork, s));
+                    MB200_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+                    MB200_CUDA(launch_tf32_allreduce(p.dtype, cp->gp, dd, h->side));
+                    MB200_CUDA(cudaEventRecord(h->ev_join, h->side));
+                    h->stats.launches_reduce++; h->stats.launches_total++;
+                }
             }
-            e = launch_tf32_gemm(p.dtype, pa, pb, g, mixed, s, &pair, dist);
+            e = launch_tf32_gemm(p.dtype, pa, pb, g, mixed, s, &pair, dist ? &dd : nullptr);
             h->stats.launches_tcgen05++;
             if (pair) h->stats.launches_tcgen05_pair++;
-            if (dist && (phases & DIST_REDUCE) && e == cudaSuccess) {
-                // The reducer is launched AFTER the GEMM, on the side stream: the persistent GEMM CTAs (one per SM, maximum shared-
-                // memory carve-out) are resident first and every SM still has room for exactly one reducer CTA (128 threads x 80
-                // registers, 3 KB of shared memory) next to them, so the two kernels run CONCURRENTLY: the reducer drains finished
-                // units while the GEMM produces the later ones. Should the reducer win the race for some SMs, its CTAs ask for the
-                // same carve-out (tf32_configure), and its grid leaves most SMs free, so the GEMM can never be starved.
-                MB200_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-                MB200_CUDA(launch_tf32_allreduce(p.dtype, cp->gp, *dist, h->side));
-                MB200_CUDA(cudaEventRecord(h->ev_join, h->side));
-                h->stats.launches_reduce++; h->stats.launches_total++;
+            if (dist && e == cudaSuccess && (phases & DIST_REDUCE)) {
+                if (dd.reserve_sms > 0) {
+                    e = cudaStreamWaitEvent(s, h->ev_join, 0);   // join: the reducer has drained every owned unit
+                } else {
+                    e = launch_tf32_allreduce(p.dtype, cp->gp, dd, s);   // no overlap: after the GEMM, on every SM
+                    h->stats.launches_reduce++; h->stats.launches_total++;
+                }
             }
         }
         cudaFreeAsync(pa, s);
         cudaFreeAsync(pb, s);
         if (dist && e == cudaSuccess) {
-            if (phases & DIST_REDUCE) e = cudaStreamWaitEvent(s, h->ev_join, 0);   // join: the reducer has drained every owned unit
             if (e == cudaSuccess && (phases & DIST_WAIT)) {
                 e = launch_dist_wait_done(*dist, tf32_dist_geometry(p.dtype, p.M, p.N, p.L).nunits, s);
                 h->stats.launches_reduce++; h->stats.launches_total++;
@@ -1262,7 +1300,28 @@ int mb200_binary_einsum_allreduce(mb200_handle_t h, int dtypeC, int nmodeC, cons
     if ((st = make_c_desc(dC, dtypeC, nmodeC, modesC)) != MB200_OK) return st;
     std::lock_guard<std::mutex> lk(h->mu);
     if (h->capturing) return fail(MB200_NOT_SUPPORTED, "the fused all-reduce cannot be captured into a graph");
+    static const bool want_tl = [] { const char *e = getenv("MB200_DIST_TIMELINE"); return e && atoi(e) != 0; }();
+    if (want_tl) {
+        MB200_CUDA(cudaSetDevice(h->device));
+        if (!h->timeline) MB200_CUDA(cudaMalloc((void **)&h->timeline, 8 * sizeof(unsigned long long)));
+        if (phases & DIST_CONTRACT) {   // a new call: min-stamps start at +inf, max-stamps at 0
+            const unsigned long long init[8] = {~0ull, 0, ~0ull, ~0ull, 0, 0, 0, 0};
+            MB200_CUDA(cudaMemcpyAsync(h->timeline, init, sizeof init, cudaMemcpyHostToDevice, h->stream));
+        }
+        d.timeline = h->timeline;
+    }
     return contract_device(h, nullptr, dC, nullptr, A, dA, B, dB, nullptr, &d, phases, comm->ws_bytes, comm->flag_bytes);
+}
+
+int mb200_dist_timeline(mb200_handle_t h, unsigned long long *out8) {
+    MB200_CHECK_HANDLE(h);
+    if (!out8) return fail(MB200_INVALID_ARGUMENT, "out8 is NULL");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!h->timeline) return fail(MB200_NOT_SUPPORTED, "no timeline recorded (MB200_DIST_TIMELINE=1 and one fused all-reduce first)");
+    MB200_CUDA(cudaSetDevice(h->device));
+    MB200_CUDA(cudaDeviceSynchronize());
+    MB200_CUDA(cudaMemcpy(out8, h->timeline, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return MB200_OK;
 }
 
 int mb200_reduce_slots(mb200_handle_t h, void *out, const void *staging_local, int dtype, int64_t slab_elems, int nslots) {

@@ -131,8 +131,14 @@ struct PermuteParams {
 cudaError_t launch_permute(int dtype, const PermuteParams &p, const void *src, void *dst, cudaStream_t s);
 // Table-driven pack of one operand into the tcgen05 operand format, any strides and any K (zero-padded to Kp, a multiple of 8):
 // dst[l][row][W * Kp] <- src[row_tab[row] + k_tab[k] + bat_tab[l]]; split = PermuteParams::split (1, 2 or 3)
+// Optional row visiting order: the row modes listed by ascending SOURCE stride with their extents and their weights in the GEMM's row
+// index (product of the extents of the modes before them in the C-order walk). A tile of 64 consecutive n' then covers runs that are
+// contiguous in the source even when C's order scatters them (rank-8 dim-8 operands: 8-byte gathers become 64-byte runs).
+#define MB200_PACK_DIGITS 6
+struct PackRowOrder { int nd; int64_t ext[MB200_PACK_DIGITS], weight[MB200_PACK_DIGITS]; };
 cudaError_t launch_pack_gather(int dtype, const void *src, const int64_t *row_tab, const int64_t *k_tab, const int64_t *bat_tab,
-                               int64_t rows, int64_t K, int64_t Kp, int64_t L, int kmajor, int split, float *dst, cudaStream_t s);
+                               int64_t rows, int64_t K, int64_t Kp, int64_t L, int kmajor, int split, float *dst, cudaStream_t s,
+                               const PackRowOrder *order = nullptr);
 
 // ---- K3: tcgen05 / TMEM 3xTF32 ComplexF32 GEMM on packed operands (tf32.cu) ---------------------------------
 bool tf32_available();
@@ -145,7 +151,7 @@ cudaError_t launch_tf32_gemm(int dtype, const void *packA, const void *packB, co
 // Every rank contracts its K-slice into PARTIAL tiles, stored tile-linear (unit = one CTA's 128 x BN sub-tile, row fastest)
 // in its own workspace ws[rank]; the epilogue then raises flag[unit][rank] in the flag array of the unit's OWNER
 // (owner = unit % nranks) with a system-scope release store. The owner's reducer kernel - running concurrently with the
-// GEMM on a second stream - waits for the nranks flags of each unit it owns, adds the nranks partial sub-tiles in rank
+// GEMM on a second stream, on SMs the GEMM's persistent grid leaves free - waits for the nranks flags of each unit it owns, adds the nranks partial sub-tiles in rank
 // order (peer loads over NVLink, or ONE multimem.ld_reduce through an NVLS multicast mapping: the switch adds), and stores
 // the finished sub-tile through the rowC / colC / batC tables into the C of EVERY rank (peer stores, or one multimem.st).
 // When its last unit is done it raises done[rank] on every rank; a rank's C is complete when all nranks done flags have
@@ -157,6 +163,10 @@ struct DistDesc {
     void *c[MB200_MAX_PEERS];      // output C of every rank (peer mappings; [rank] = own)
     int *flags[MB200_MAX_PEERS];   // flag array of every rank
     void *mc_ws, *mc_c;            // NVLS multicast mappings of ws / c, or NULL
+    int reserve_sms;               // > 0: the reducer runs NEXT TO the GEMM on this many SMs, which the GEMM's persistent grid leaves free;
+                                   // 0: the reducer runs after the GEMM on every SM (no overlap)
+    unsigned long long *timeline;  // optional 8 x u64 (device): globaltimer stamps [0] GEMM first CTA start, [1] GEMM last epilogue end,
+                                   // [2] reducer first CTA start, [3] reducer first unit ready, [4] reducer end, [5] wait_done end
 };
 struct DistGeometry { int BN; int pair; int64_t nunits; int64_t unit_elems; };   // unit_elems = 128 * BN
 // geometry of the dist-mode GEMM for a (dtype, M, N, L) problem: which kernel variant runs, how many units it produces

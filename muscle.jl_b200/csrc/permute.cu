@@ -413,6 +413,10 @@ struct PackGather {
     const int64_t *row_tab, *k_tab, *bat_tab;
     int64_t rows, K, Kp, L;
     int kmajor, aux;   // aux: split writer format / side (see put)
+    // Row visiting order of the line-writer pack (kernels.cuh PackRowOrder): the rows of a tile are 64 consecutive values of n', whose
+    // digits run over the row modes in SOURCE-stride order; n = sum digit_i * weight_i is the GEMM's row index. nd == 0: n' = n.
+    int nd;
+    int64_t d_ext[MB200_PACK_DIGITS], d_w[MB200_PACK_DIGITS];
 };
 template <bool REAL>
 __global__ void __launch_bounds__(256) pack_gather_kernel(const __grid_constant__ PackGather q, const void *__restrict__ srcv,
@@ -510,7 +514,7 @@ __global__ void __launch_bounds__(256) pack_lines_kernel(const __grid_constant__
     constexpr int TR = 64, TK = 32;
     constexpr int PITCH = TK + (REAL ? 4 : 2);            // keeps every row 16-byte aligned
     __shared__ __align__(16) E tile[TR][PITCH];
-    __shared__ int64_t sRow[TR], sK[TK];
+    __shared__ int64_t sRow[TR], sK[TK], sDst[TR];
     const E *src = reinterpret_cast<const E *>(srcv);
     const int tid = threadIdx.x;
     const int64_t tiles_k = (q.Kp + TK - 1) / TK, tiles_r = (q.rows + TR - 1) / TR;
@@ -518,8 +522,21 @@ __global__ void __launch_bounds__(256) pack_lines_kernel(const __grid_constant__
     const int64_t k0 = (b % tiles_k) * TK; b /= tiles_k;
     const int64_t r0 = (b % tiles_r) * TR;
     const int64_t l = b / tiles_r;
-    if (tid < TR) sRow[tid] = (r0 + tid < q.rows) ? q.row_tab[r0 + tid] : -1;
-    else if (tid < TR + TK) sK[tid - TR] = (k0 + tid - TR < q.K) ? q.k_tab[k0 + tid - TR] : -1;
+    if (tid < TR) {
+        int64_t n = r0 + tid;
+        const bool ok = n < q.rows;
+        if (ok && q.nd) {   // n' -> n: digits of n' in source-stride order, recombined with their weights in the GEMM's row order
+            int64_t rem = n;
+            n = 0;
+            for (int i = 0; i < q.nd; i++) {
+                const int64_t e = q.d_ext[i], dgt = rem % e;
+                rem /= e;
+                n += dgt * q.d_w[i];
+            }
+        }
+        sRow[tid] = ok ? q.row_tab[n] : -1;
+        sDst[tid] = ok ? n : -1;
+    } else if (tid < TR + TK) sK[tid - TR] = (k0 + tid - TR < q.K) ? q.k_tab[k0 + tid - TR] : -1;
     const E *srcb = src + q.bat_tab[l];
     __syncthreads();
     E v[8];
@@ -557,8 +574,8 @@ __global__ void __launch_bounds__(256) pack_lines_kernel(const __grid_constant__
     for (int i = 0; i < NITEMS / 256; i++) {
         const int it = tid + 256 * i;
         const int sub = it % ITEMS_PER_GROUP, g = (it / ITEMS_PER_GROUP) & 3, r = it / (ITEMS_PER_GROUP * 4);
-        const int64_t row = r0 + r, kg = k0 + g * 8;
-        if (row >= q.rows || kg >= q.Kp) continue;
+        const int64_t row = sDst[r], kg = k0 + g * 8;
+        if (row < 0 || kg >= q.Kp) continue;
         const int half = sub & 1, comp = sub >> 1;                      // comp: 0 = re (or the real value), 1 = im
         const E *e = &tile[r][g * 8 + half * 4];
         float in[4];
@@ -990,10 +1007,17 @@ cudaError_t launch_permute(int dtype, const PermuteParams &q_in, const void *src
 }
 
 cudaError_t launch_pack_gather(int dtype, const void *src, const int64_t *row_tab, const int64_t *k_tab, const int64_t *bat_tab,
-                               int64_t rows, int64_t K, int64_t Kp, int64_t L, int kmajor, int split, float *dst, cudaStream_t s) {
+                               int64_t rows, int64_t K, int64_t Kp, int64_t L, int kmajor, int split, float *dst, cudaStream_t s,
+                               const PackRowOrder *order) {
     if (rows <= 0 || L <= 0 || Kp <= 0) return cudaSuccess;
     if (split < 1 || (dtype != MB200_C64 && dtype != MB200_F32)) return cudaErrorInvalidValue;
-    PackGather q{row_tab, k_tab, bat_tab, rows, K, Kp, L, kmajor, split - 1};
+    PackGather q{};
+    q.row_tab = row_tab; q.k_tab = k_tab; q.bat_tab = bat_tab;
+    q.rows = rows; q.K = K; q.Kp = Kp; q.L = L; q.kmajor = kmajor; q.aux = split - 1;
+    if (order && order->nd > 0 && !kmajor) {
+        q.nd = order->nd;
+        for (int i = 0; i < order->nd; i++) { q.d_ext[i] = order->ext[i]; q.d_w[i] = order->weight[i]; }
+    }
     const int64_t grid = ((Kp + 31) / 32) * ((rows + 31) / 32) * L;
     if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     static const int lines = [] { const char *e = getenv("MB200_PACK_LINES"); return e ? atoi(e) : 1; }();

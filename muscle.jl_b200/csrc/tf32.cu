@@ -210,7 +210,14 @@ struct Tf32Params {
     // raised in its owner's flag array
     int dist_nranks, dist_rank, dist_epoch;
     int *dist_flags[MB200_MAX_PEERS];
+    unsigned long long *timeline;
 };
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ void st_release_sys(int *p, int v) {
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -285,6 +292,7 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     int64_t *sColC = reinterpret_cast<int64_t *>(tiles + TSTAGES * SM::STAGE + 256);   // [2][BN], per tile parity
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (p.timeline && threadIdx.x == 0) atomicMin(&p.timeline[0], global_ns());
     const int64_t ntiles = p.ntiles, nunits = p.ntiles * p.nsplit;
     const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;          // 0 = leader
     const int64_t walker = CTA2 ? blockIdx.x / 2 : blockIdx.x;    // persistent walker id (CTA or CTA pair)
@@ -483,6 +491,7 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             }
         }
         if (p.sc.nranks) __threadfence_system();   // peer stores must be visible before the cross-rank barrier
+        if (p.timeline && et == 0) atomicMax(&p.timeline[1], global_ns());
     }
     tc_fence_before();
     if constexpr (CTA2) cluster_sync_all(); else __syncthreads();   // pair: no CTA frees TMEM / exits while the other still uses it
@@ -512,6 +521,7 @@ __global__ void __launch_bounds__(256) tf32_splitk_reduce_kernel(const __grid_co
 
 // ---- cross-GPU split-K: the owner's reducer (kernels.cuh DistDesc) -----------------------------------------------------------
 struct DistParams {
+    unsigned long long *timeline;
     const void *ws[MB200_MAX_PEERS];
     void *c[MB200_MAX_PEERS];
     int *flags[MB200_MAX_PEERS];
@@ -550,27 +560,33 @@ __device__ __forceinline__ void spin_until(const int *flag, int epoch) {
     }
 }
 
-constexpr int RTHREADS = 128;   // 128 threads x <= 80 registers: co-resident with a 320-thread x 168-register GEMM CTA on one SM
-constexpr int RPARTS = 4;       // a unit is reduced by 4 work items (quarters of its vectors): short tail after the last GEMM tile
+// Measured on the box (tools/diag_allreduce.py, globaltimer stamps): a reducer CTA and a GEMM CTA never share an SM, whatever the
+// register / shared-memory arithmetic says - a small reducer CTA resident on an SM keeps the GEMM's CTA (pair) off it, and with the
+// GEMM resident first the reducer only starts when GEMM CTAs retire. So the SMs are PARTITIONED: the GEMM's persistent grid leaves
+// `reserve` SMs free (whole TPCs for the CTA-pair kernel: the reducer is then launched as 2-CTA clusters too) and the reducer runs
+// fat CTAs (512 threads, 8 x 16 bytes in flight per thread) on exactly those SMs.
+constexpr int RTHREADS = 512;
+constexpr int RPARTS = 2;       // a unit is reduced by 2 work items (halves of its vectors): one round of 8 vectors per thread
 
 // Work item = (owned unit, quarter); items are strided over the CTAs (one CTA per SM, next to the GEMM's CTA). A 16-byte vector is
 // 2 consecutive rows (complex) or 4 (real) of one column of the sub-tile. Memory-level parallelism is what makes this kernel: a
 // thread keeps 8 multimem.ld_reduce (MC) or 4 peer loads per step of the rank loop in flight - what the register budget of a
 // co-resident CTA allows - and the grid supplies the rest (148 x 128 x 8 x 16 B = 2.4 MB in flight per GPU).
 template <int BN, bool REAL, bool CTA2, bool MC>
-__global__ void __launch_bounds__(RTHREADS, 6) tf32_allreduce_kernel(const __grid_constant__ Tf32Params p, const __grid_constant__ DistParams d) {
+__global__ void __launch_bounds__(RTHREADS, 1) tf32_allreduce_kernel(const __grid_constant__ Tf32Params p, const __grid_constant__ DistParams d) {
     constexpr int NCTA = CTA2 ? 2 : 1;
     constexpr int PM = TBM * NCTA;
     constexpr int VE = REAL ? 4 : 2;                 // elements per 16-byte vector
     constexpr int ESZ = REAL ? 4 : 8;
     constexpr int NVEC = TBM * BN / VE, PVEC = NVEC / RPARTS;
-    constexpr int U = MC ? 8 : 4;
+    constexpr int U = 8;
     static_assert(PVEC % RTHREADS == 0, "part size");
     __shared__ int64_t sRow[TBM];
     __shared__ int64_t sCol[BN];
     const int tid = threadIdx.x;
     const int64_t owned = (d.nunits - d.rank + d.nranks - 1) / d.nranks;   // units rank, rank + nranks, ...
     const int64_t items = owned > 0 ? owned * RPARTS : 0;
+    if (d.timeline && tid == 0) atomicMin(&d.timeline[2], global_ns());
     for (int64_t j = blockIdx.x; j < items; j += gridDim.x) {
         const int64_t u = (j / RPARTS) * d.nranks + d.rank;
         const int part = (int)(j % RPARTS);
@@ -583,6 +599,7 @@ __global__ void __launch_bounds__(RTHREADS, 6) tf32_allreduce_kernel(const __gri
         for (int i = tid; i < BN; i += RTHREADS) sCol[i] = (tc.n0 + i < p.N) ? p.colC[tc.n0 + i] : -1;
         if (tid < d.nranks) spin_until(d.flags[d.rank] + u * d.nranks + tid, d.epoch);
         __syncthreads();                               // all nranks partial sub-tiles of this unit are visible
+        if (d.timeline && tid == 0 && j == blockIdx.x) atomicMin(&d.timeline[3], global_ns());
         const size_t ubase = (size_t)u * (TBM * BN) * ESZ;
         for (int v0 = part * PVEC + tid; v0 < (part + 1) * PVEC; v0 += RTHREADS * U) {
             float4 acc[U];
@@ -651,6 +668,7 @@ __global__ void __launch_bounds__(RTHREADS, 6) tf32_allreduce_kernel(const __gri
     // every store of this CTA is visible system-wide, then the last CTA to finish raises done[rank] on every rank
     __threadfence_system();
     __syncthreads();
+    if (d.timeline && tid == 0) atomicMax(&d.timeline[4], global_ns());
     if (tid == 0) {
         int *counter = d.flags[d.rank] + d.nunits * d.nranks + d.nranks;
         const int prev = atomicAdd(counter, 1);
@@ -663,8 +681,10 @@ __global__ void __launch_bounds__(RTHREADS, 6) tf32_allreduce_kernel(const __gri
 }
 
 // a rank's C is complete when every owner has raised its done flag here
-__global__ void dist_wait_done_kernel(const int *done, int nranks, int epoch) {
+__global__ void dist_wait_done_kernel(const int *done, int nranks, int epoch, unsigned long long *timeline) {
     if ((int)threadIdx.x < nranks) spin_until(done + threadIdx.x, epoch);
+    __syncthreads();
+    if (timeline && threadIdx.x == 0) timeline[5] = global_ns();
 }
 
 // ---- host side ----------------------------------------------------------------------------------------
@@ -722,6 +742,7 @@ cudaError_t launch_bn(const void *packA, const void *packB, const GettParams &g,
         p.dist_nranks = dist->nranks; p.dist_rank = dist->rank; p.dist_epoch = dist->epoch;
         for (int r = 0; r < dist->nranks; r++) p.dist_flags[r] = dist->flags[r];
         p.ws = dist->ws[dist->rank];
+        p.timeline = dist->timeline;
     }
     p.sc = g.sc;
     p.C = g.C;
@@ -744,7 +765,8 @@ cudaError_t launch_bn(const void *packA, const void *packB, const GettParams &g,
             p.ntiles = ptiles;
             if (pair) *pair = true;
             cudaLaunchConfig_t cfg{};
-            const int64_t pairs = ptiles < 74 ? ptiles : 74;   // persistent: one CTA pair per TPC
+            const int64_t tpcs = 74 - (dist ? (dist->reserve_sms + 1) / 2 : 0);   // dist mode: whole TPCs left to the reducer
+            const int64_t pairs = ptiles < tpcs ? ptiles : tpcs;   // persistent: one CTA pair per TPC
             cfg.gridDim = dim3((unsigned)(2 * pairs));
             cfg.blockDim = dim3(TTHREADS);
             cfg.dynamicSmemBytes = Tf32Smem<BN, REAL, true>::TOTAL;
@@ -780,7 +802,8 @@ cudaError_t launch_bn(const void *packA, const void *packB, const GettParams &g,
         p.ws = ws;
     }
     const int64_t nunits = ntiles * p.nsplit;
-    const int64_t grid = nunits < 148 ? nunits : 148;   // persistent: one CTA per SM
+    const int64_t sms = 148 - (dist ? dist->reserve_sms : 0);
+    const int64_t grid = nunits < sms ? nunits : sms;   // persistent: one CTA per SM (dist mode: minus the reducer's SMs)
     tf32_gemm_kernel<BN, REAL, false><<<(unsigned)grid, TTHREADS, Tf32Smem<BN, REAL, false>::TOTAL, s>>>(mapA, mapB, p);
     if (p.nsplit > 1) {
         const int64_t threads = ntiles * TBM * BN;
@@ -804,16 +827,6 @@ cudaError_t tf32_configure() {
     MB200_TCFG(128, false, false); MB200_TCFG(64, false, false); MB200_TCFG(256, true, false); MB200_TCFG(128, true, false);
     MB200_TCFG(128, false, true); MB200_TCFG(256, true, true);
 #undef MB200_TCFG
-    // reducer of the fused all-reduce: same (maximum) shared-memory carve-out as the GEMM it shares SMs with
-#define MB200_RCFG(BN, REAL, CTA2, MC)                                                                                      \
-    if (e == cudaSuccess)                                                                                                   \
-        e = cudaFuncSetAttribute(tf32_allreduce_kernel<BN, REAL, CTA2, MC>, cudaFuncAttributePreferredSharedMemoryCarveout, \
-                                 (int)cudaSharedmemCarveoutMaxShared)
-    MB200_RCFG(128, false, false, false); MB200_RCFG(128, false, false, true); MB200_RCFG(64, false, false, false);
-    MB200_RCFG(64, false, false, true); MB200_RCFG(256, true, false, false); MB200_RCFG(256, true, false, true);
-    MB200_RCFG(128, true, false, false); MB200_RCFG(128, true, false, true); MB200_RCFG(128, false, true, false);
-    MB200_RCFG(128, false, true, true); MB200_RCFG(256, true, true, false); MB200_RCFG(256, true, true, true);
-#undef MB200_RCFG
     return e;
 }
 
@@ -851,24 +864,34 @@ cudaError_t launch_allreduce_bn(const GettParams &g, const DistDesc &dist, cudaS
     d.nranks = dist.nranks; d.rank = dist.rank; d.epoch = dist.epoch; d.nunits = geo.nunits;
     for (int r = 0; r < dist.nranks; r++) { d.ws[r] = dist.ws[r]; d.c[r] = dist.c[r]; d.flags[r] = dist.flags[r]; }
     d.mc_ws = dist.mc_ws; d.mc_c = dist.mc_c;
+    d.timeline = dist.timeline;
     const int64_t owned = (geo.nunits - dist.rank + dist.nranks - 1) / dist.nranks;
     // a rank that owns nothing still launches one CTA: its done flag must go up
-    // At most one reducer CTA per SM can sit next to a GEMM CTA. The default grid leaves 84 SMs untouched: even if no SM could be
-    // shared (the reducer CTAs resident first, with a different shared-memory carve-out), the persistent GEMM still makes progress
-    // and its remaining CTAs run as soon as the first ones retire - a slower run, never a deadlock. 148 deadlocks in that case.
-    static const int rctas = [] { const char *e = getenv("MB200_DIST_REDUCER_CTAS"); return e ? std::min(120, std::max(1, atoi(e))) : 64; }();
-    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(owned * RPARTS, rctas));
+    // grid: the reserved SMs when the reducer runs next to the GEMM (overlap), every SM when it runs after it
+    const int64_t want = dist.reserve_sms > 0 ? dist.reserve_sms : 148;
+    unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(owned * RPARTS, want));
     const bool mc = d.mc_ws != nullptr;
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(RTHREADS);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
     if constexpr (pair_ok<BN, REAL>()) {
         if (geo.pair) {
-            if (mc) tf32_allreduce_kernel<BN, REAL, true, true><<<grid, RTHREADS, 0, s>>>(p, d);
-            else tf32_allreduce_kernel<BN, REAL, true, false><<<grid, RTHREADS, 0, s>>>(p, d);
-            return cudaGetLastError();
+            if (dist.reserve_sms > 0 && grid >= 2) {   // whole TPCs, like the GEMM's CTA pairs
+                grid &= ~1u;
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr;
+                cfg.numAttrs = 1;
+            }
+            cfg.gridDim = dim3(grid);
+            return mc ? cudaLaunchKernelEx(&cfg, tf32_allreduce_kernel<BN, REAL, true, true>, p, d)
+                      : cudaLaunchKernelEx(&cfg, tf32_allreduce_kernel<BN, REAL, true, false>, p, d);
         }
     }
-    if (mc) tf32_allreduce_kernel<BN, REAL, false, true><<<grid, RTHREADS, 0, s>>>(p, d);
-    else tf32_allreduce_kernel<BN, REAL, false, false><<<grid, RTHREADS, 0, s>>>(p, d);
-    return cudaGetLastError();
+    cfg.gridDim = dim3(grid);
+    return mc ? cudaLaunchKernelEx(&cfg, tf32_allreduce_kernel<BN, REAL, false, true>, p, d)
+              : cudaLaunchKernelEx(&cfg, tf32_allreduce_kernel<BN, REAL, false, false>, p, d);
 }
 }  // namespace
 
@@ -883,7 +906,7 @@ cudaError_t launch_tf32_allreduce(int dtype, const GettParams &g, const DistDesc
 }
 
 cudaError_t launch_dist_wait_done(const DistDesc &dist, int64_t nunits, cudaStream_t s) {
-    dist_wait_done_kernel<<<1, 32, 0, s>>>(dist.flags[dist.rank] + nunits * dist.nranks, dist.nranks, dist.epoch);
+    dist_wait_done_kernel<<<1, 32, 0, s>>>(dist.flags[dist.rank] + nunits * dist.nranks, dist.nranks, dist.epoch, dist.timeline);
     return cudaGetLastError();
 }
 

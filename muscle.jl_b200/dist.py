@@ -351,7 +351,7 @@ def allreduce_workspace(a_loc: Tensor, b_loc: Tensor, inds_c, nranks: int):
     return int(ws.value), int(fl.value)
 
 
-def sum_slice_all_reduce(a_loc: Tensor, b_loc: Tensor, inds_c, group=None, phases=7) -> Tensor:
+def sum_slice_all_reduce(a_loc: Tensor, b_loc: Tensor, inds_c, group=None, phases=7, bump_epoch=True) -> Tensor:
     """Summed-index slice with the all-reduce fused into the contraction (all-reduce semantics: every rank ends with the
     full C, bit-identical on all ranks) - Dagger's `treereduce(AddComputeOp, ...)` over the summed blocks
     (ext/MuscleDaggerExt/binary_einsum.jl:107-115) without a separate collective pass: see mb200_binary_einsum_allreduce.
@@ -382,7 +382,8 @@ def sum_slice_all_reduce(a_loc: Tensor, b_loc: Tensor, inds_c, group=None, phase
     if st is None:
         ws_bytes, flag_bytes = allreduce_workspace(a_loc, b_loc, inds_c, nranks)
         st = _ALLREDUCE[key] = _SymmetricBuffers(dev, ws_bytes, flag_bytes, numel * T.itemsize, group)
-    st.epoch += 1
+    if bump_epoch:                                   # False: a later phase of the call that raised the epoch (diagnostics, tests)
+        st.epoch += 1
     h = _lib.Handle.get(dev)
     cm = st.comm(st.epoch)
     _lib.check(_lib.lib().mb200_binary_einsum_allreduce(
