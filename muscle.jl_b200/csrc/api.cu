@@ -465,18 +465,28 @@ int contract_device(mb200_handle_t h, void *C, TensorDesc &dC, const int64_t *st
             DistDesc dd{};
             if (dist) {
                 dd = *dist;
-                // Overlap policy. Reserving SMs costs the persistent GEMM whole rounds (512 pair tiles on 74 TPCs are 6.92 rounds: ANY
-                // reservation makes them 8, +14 %), so it only pays when the reduction is long: each rank pulls and pushes
-                // 2 |C| / nranks bytes. Measured (tools/diag_allreduce.py): N = 2 (134 MB per rank) 1.14 ms overlapped vs 1.35 ms
-                // one after the other; at N = 8 (34 MB) the reducer on all 148 SMs takes ~30 us and running it after the GEMM wins.
-                // MB200_DIST_OVERLAP = 0 / 1 forces one-after-the-other / overlapped; MB200_DIST_REDUCER_SMS sets the reservation
-                // (default 12 SMs with an NVLS multicast mapping, 24 with peer loads / stores).
-                static const int overlap = [] { const char *e = getenv("MB200_DIST_OVERLAP"); return e ? atoi(e) : -1; }();
+                // Overlap policy (tools/diag_allreduce.py, globaltimer stamps). Every rank exports (N - 1) / N of its partial C over
+                // NVLink whatever N is (117 MB of 134 MB at N = 8: ~0.26 ms at the ~450 GB/s the switch reduction sustains), so the
+                // reduction is as long as the sliced GEMM and overlapping always pays: N = 2 1.14 ms overlapped vs 1.35 ms one after the
+                // other, N = 8 0.47 vs 0.61. Reserving SMs costs the persistent GEMM whole rounds (512 pair tiles on 74 TPCs are 6.92
+                // rounds: ANY reservation makes them 8), so the reducer gets the LARGEST reservation that adds no further round.
+                // MB200_DIST_OVERLAP=0 runs the reducer after the GEMM on every SM; MB200_DIST_REDUCER_SMS fixes the reservation.
+                static const int overlap = [] { const char *e = getenv("MB200_DIST_OVERLAP"); return e ? atoi(e) : 1; }();
                 static const int rsms = [] { const char *e = getenv("MB200_DIST_REDUCER_SMS"); return e ? atoi(e) : 0; }();
-                const double reduce_bytes = 2.0 * (double)p.M * (double)p.N * (double)p.L * (double)dtype_size(p.dtype) / dd.nranks;
-                const bool want_overlap = overlap >= 0 ? overlap != 0 : reduce_bytes >= 64.0e6;
-                const bool fused_now = (phases & DIST_REDUCE) && (phases & DIST_CONTRACT) && want_overlap;
-                dd.reserve_sms = fused_now ? std::min(96, std::max(2, rsms > 0 ? rsms : (dd.mc_ws ? 12 : 24))) & ~1 : 0;
+                const bool fused_now = (phases & DIST_REDUCE) && (phases & DIST_CONTRACT) && overlap != 0;
+                int reserve = 0;
+                if (fused_now) {
+                    const DistGeometry geo = tf32_dist_geometry(p.dtype, p.M, p.N, p.L);
+                    const int64_t walkers = geo.pair ? 74 : 148, tiles = geo.pair ? geo.nunits / 2 : geo.nunits;
+                    const int step = geo.pair ? 1 : 2;                       // reserve whole TPCs
+                    auto rounds = [&](int64_t r) { return (tiles + (walkers - r) - 1) / (walkers - r); };
+                    int64_t r = step * (dd.mc_ws ? 3 : 6);                    // at least 6 / 12 SMs
+                    const int64_t cap = step * 16;                           // at most 32 SMs
+                    while (r + step <= cap && rounds(r + step) == rounds(r)) r += step;
+                    reserve = (int)(geo.pair ? 2 * r : r);
+                    if (rsms > 0) reserve = std::min(96, std::max(2, rsms)) & ~1;
+                }
+                dd.reserve_sms = reserve;
                 if (fused_now) {
                     // the reducer first, on the side stream (it must not start before everything the caller enqueued so far: the
                     // previous consumer of C and of the workspace); it occupies its reserved SMs and polls unit flags while the

@@ -48,6 +48,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
+#include <string>
 #include <type_traits>
 
 #include "kernels.cuh"
@@ -208,7 +209,7 @@ struct Tf32Params {
     int mixed;   // 1: TF32 + BF16 operand format (8 / 4 MMAs per line), 0: 3xTF32 (12 / 6)
     // cross-GPU split-K (kernels.cuh DistDesc): partial sub-tiles go to ws (this rank's own workspace), then the unit's flag is
     // raised in its owner's flag array
-    int dist_nranks, dist_rank, dist_epoch;
+    int dist_nranks, dist_rank, dist_epoch, dist_fence_all;
     int *dist_flags[MB200_MAX_PEERS];
     unsigned long long *timeline;
 };
@@ -460,10 +461,12 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     if constexpr (REAL) reinterpret_cast<float *>(p.ws)[o] = accr[j];
                     else reinterpret_cast<float2 *>(p.ws)[o] = make_float2(accr[j], acci[j]);
                 }
-                __threadfence_system();                        // this thread's stores are visible system-wide ...
+                if (p.dist_fence_all) __threadfence_system();  // this thread's stores are visible system-wide ...
                 asm volatile("bar.sync 1, 256;" ::: "memory");   // ... and so are those of all 256 epilogue threads before the flag goes up
-                if (et == 0)
+                if (et == 0) {
+                    if (!p.dist_fence_all) __threadfence_system();   // cumulative over the barrier: orders all 256 threads' stores
                     st_release_sys(p.dist_flags[u % p.dist_nranks] + u * p.dist_nranks + p.dist_rank, p.dist_epoch);
+                }
                 continue;
             }
             if (p.nsplit > 1) {   // partial tile -> workspace, row fastest (coalesced), every row / column of the tile (1-CTA only)
@@ -743,6 +746,10 @@ cudaError_t launch_bn(const void *packA, const void *packB, const GettParams &g,
         for (int r = 0; r < dist->nranks; r++) p.dist_flags[r] = dist->flags[r];
         p.ws = dist->ws[dist->rank];
         p.timeline = dist->timeline;
+        // default: one cumulative fence + release store by the signalling thread after the CTA barrier (what CUTLASS's stream-K
+        // semaphore and a cooperative-groups grid sync rely on); MB200_DIST_FENCE=all adds a system fence per epilogue thread
+        static const bool fence_all = [] { const char *e = getenv("MB200_DIST_FENCE"); return e && std::string(e) == "all"; }();
+        p.dist_fence_all = fence_all ? 1 : 0;
     }
     p.sc = g.sc;
     p.C = g.C;
