@@ -809,6 +809,11 @@ def sharded_configs(c, args, sampler):
                key=lambda v: v["value"])
     res5["value"], res5["ms"], res5["unit"] = best["value"], best["ms"], "TFLOP/s"
     res5["parity"] = {"tolerance": 1e-5, "slab": restrict}
+    try:
+        kinds = mdist.allreduce_plumbing_info()
+        res5["fused_all_reduce_plumbing"] = {"peer_buffers": kinds[0][0], "nvls_multicast": kinds[0][1]} if kinds else None
+    except Exception:  # noqa: BLE001
+        pass
     out["config5_summed_slice"] = res5
     del A5, B5
     torch.cuda.empty_cache()

@@ -233,3 +233,32 @@ def test_planner_tcgen05_eligibility_and_pack_kind():
     assert mb.plan_describe(C64, [1, 2], C64, [0, 1], [60, 2048], C64, [0, 2], [60, 2048]).tc_eligible == 0
     assert mb.plan_describe(C64, [1, 2], C64, [0, 1], [512, 2048], C64, [0, 2], [512, 16]).tc_eligible == 0
     assert mb.plan_describe(C128, [1, 2], C128, [0, 1], [512, 2048], C128, [0, 2], [512, 2048]).tc_eligible == 0
+
+
+def test_bench_headline_shard_and_oracle_helpers():
+    """bench.py's headline (config 4b, 16384^3) asks mb200_shard_plan for the cut at every N and asserts it is the free label `i`;
+    its CPU-side parity helper must agree with the general oracle when a batch label is restricted to one value."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    ext, ia, ib, ic = bench.CFG4B["ext"], bench.CFG4B["ia"], bench.CFG4B["ib"], bench.CFG4B["ic"]
+    lab = "abcdefghi"
+    for world in (2, 4, 8):
+        cover = []
+        for rank in range(world):
+            info = _lib.shard_plan([lab.index(x) for x in ic], [lab.index(x) for x in ia], [ext[x] for x in ia],
+                                   [lab.index(x) for x in ib], [ext[x] for x in ib], world, rank)
+            assert info.kind == _lib.SHARD_FREE and lab[info.mode] == "i" and not info.needs_allreduce
+            cover += list(range(info.begin, info.end))
+        assert cover == list(range(ext["i"]))            # the slabs tile the label exactly once
+    from oracle import binary_einsum_general
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((3, 4, 1)) + 1j * rng.standard_normal((3, 4, 1))
+    b = rng.standard_normal((4, 5, 1)) + 1j * rng.standard_normal((4, 5, 1))
+    ref, ic2 = bench.oracle_slab("ijz", "jkz", "kiz", np.asfortranarray(a), np.asfortranarray(b))
+    full = binary_einsum_general(list("kiz"), a, list("ijz"), b, list("jkz"))
+    assert ic2 == ["k", "i"] and np.allclose(ref, full[..., 0])
+    A, B, e2, flops = bench.cfg4b_sample(1 / 16, 1 / 16)
+    assert A.shape == tuple(e2[x] for x in ia) and e2["a"] == 2 and e2["g"] == 2 and flops == 8.0 * np.prod([e2[x] for x in e2])
