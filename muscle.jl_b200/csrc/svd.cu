@@ -23,6 +23,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "kernels.cuh"
 
@@ -129,6 +130,7 @@ struct SvdParams {
     int rows, cols, m, n, transposed;
     double tol;
     int max_sweeps;
+    int warps_per_pair;   // 1, 2, 4 or 8 warps of one CTA cooperate on a column pair (long columns: more lanes per pair)
 };
 
 template <typename T>
@@ -172,22 +174,39 @@ __global__ void __launch_bounds__(256) jacobi_svd_kernel(const __grid_constant__
     const int np = (n + 1) & ~1;          // players of the tournament (one dummy when n is odd)
     const R tol = (R)p.tol;
     bool converged = n <= 1;
+    // A column pair is handled by a GROUP of W warps of one CTA (W = 1: the original warp-per-pair form). Round 1 measured the
+    // step as a latency chain inside one warp with 3.5 warps per SM at n = 1024; W warps per pair put W times more loads in flight.
+    const int W = p.warps_per_pair;
+    const int wic = threadIdx.x >> 5, gic = wic / W, wig = wic % W;
+    const int64_t group = (int64_t)blockIdx.x * (8 / W) + gic, ngroups = (int64_t)gridDim.x * (8 / W);
+    const int glane = wig * 32 + lane, gsize = W * 32;
+    __shared__ R red[2][8][4];
     for (int sweep = 0; sweep < p.max_sweeps && n > 1; sweep++) {
         for (int r = 0; r < np - 1; r++) {
-            for (int64_t k = warp; k < np / 2; k += nwarps) {
+            int it = 0;
+            for (int64_t k = group; k < np / 2; k += ngroups, it++) {
                 int a, b;
                 if (k == 0) { a = np - 1; b = r; }
                 else { a = (int)((r + k) % (np - 1)); b = (int)((r - k + (np - 1)) % (np - 1)); }
                 const int pc = min(a, b), qc = max(a, b);
-                if (qc >= n) continue;    // the dummy player sits out
+                if (qc >= n) continue;    // the dummy player sits out (uniform over the group)
                 T *gp = G + (int64_t)pc * m, *gq = G + (int64_t)qc * m;
                 R alpha = 0, beta = 0, gre = 0, gim = 0;
-                for (int i = lane; i < m; i += 32) {
+                for (int i = glane; i < m; i += gsize) {
                     const T x = gp[i], y = gq[i];
                     alpha += abs2(x); beta += abs2(y);
                     cdot(x, y, gre, gim);
                 }
                 alpha = warp_sum(alpha); beta = warp_sum(beta); gre = warp_sum(gre); gim = warp_sum(gim);
+                if (W > 1) {              // the W warps' partial sums, added in a fixed order by every thread (identical results)
+                    if (lane == 0) { red[it & 1][wic][0] = alpha; red[it & 1][wic][1] = beta; red[it & 1][wic][2] = gre; red[it & 1][wic][3] = gim; }
+                    asm volatile("bar.sync %0, %1;" ::"r"(1 + gic), "r"(gsize) : "memory");
+                    alpha = beta = gre = gim = 0;
+                    for (int w = 0; w < W; w++) {
+                        alpha += red[it & 1][gic * W + w][0]; beta += red[it & 1][gic * W + w][1];
+                        gre += red[it & 1][gic * W + w][2]; gim += red[it & 1][gic * W + w][3];
+                    }
+                }
                 const R g2 = gre * gre + gim * gim;
                 if (!(g2 > tol * tol * alpha * beta) || g2 == (R)0) continue;
                 // four slow operations (rsqrt, sqrt, div, rsqrt) instead of eight: FP64 sqrt / div are ~40-instruction
@@ -197,18 +216,18 @@ __global__ void __launch_bounds__(256) jacobi_svd_kernel(const __grid_constant__
                 const R t = (zeta >= 0 ? (R)1 : (R)-1) / (fabs(zeta) + sqrt((R)1 + zeta * zeta));
                 const R c = inv_sqrt((R)1 + t * t), s = c * t;
                 const R phr = gre * inv_g, phi = gim * inv_g;
-                for (int i = lane; i < m; i += 32) {
+                for (int i = glane; i < m; i += gsize) {
                     T x = gp[i], y = gq[i];
                     rot(x, y, c, s, phr, phi);
                     gp[i] = x; gq[i] = y;
                 }
                 T *vp = V + (int64_t)pc * n, *vq = V + (int64_t)qc * n;
-                for (int i = lane; i < n; i += 32) {
+                for (int i = glane; i < n; i += gsize) {
                     T x = vp[i], y = vq[i];
                     rot(x, y, c, s, phr, phi);
                     vp[i] = x; vq[i] = y;
                 }
-                if (lane == 0) atomicAdd(&p.counters[0], 1);
+                if (glane == 0) atomicAdd(&p.counters[0], 1);
             }
             grid.sync();
         }
@@ -442,9 +461,17 @@ cudaError_t launch_svd(int dtype, const void *A, int rows, int cols, void *U, vo
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // one warp per column pair: n/2 warps are enough; never more CTAs than can be resident (cooperative launch)
-    const int64_t want = std::max<int64_t>(1, ((int64_t)(p.n + 1) / 2 + 7) / 8);
-    const int grid = (int)std::min<int64_t>(want, (int64_t)sms * std::max(1, std::min(per_sm, 2)));
+    // W warps per column pair (W | 8, a CTA holds 8 / W pairs): as many as keep every pair of a tournament step resident at once
+    // and give every lane at least one row; never more CTAs than can be resident (cooperative launch). MB200_SVD_WARPS pins W.
+    const int64_t pairs = ((int64_t)p.n + 1) / 2;
+    const int64_t resident = (int64_t)sms * std::max(1, per_sm);
+    static const int forced = [] { const char *e = getenv("MB200_SVD_WARPS"); return e ? atoi(e) : 0; }();
+    int W = 1;
+    while (W < 8 && (pairs * (2 * W) + 7) / 8 <= resident && p.m >= 64 * W) W *= 2;
+    if (forced == 1 || forced == 2 || forced == 4 || forced == 8) W = forced;
+    p.warps_per_pair = W;
+    const int64_t want = std::max<int64_t>(1, (pairs * W + 7) / 8);
+    const int grid = (int)std::min<int64_t>(want, resident);
     void *args[] = {(void *)&p};
     return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(256), args, 0, s);
 }

@@ -591,7 +591,10 @@ __device__ __forceinline__ void spin_until(const int *flag, int epoch) {
 // `reserve` SMs free (whole TPCs for the CTA-pair kernel: the reducer is then launched as 2-CTA clusters too) and the reducer runs
 // fat CTAs (512 threads, 8 x 16 bytes in flight per thread) on exactly those SMs.
 constexpr int RTHREADS = 512;
-constexpr int RPARTS = 2;       // a unit is reduced by 2 work items (halves of its vectors): one round of 8 vectors per thread
+// Work item = 1 / RPARTS of a unit's vectors. With the multicast mapping a thread keeps 16 multimem.ld_reduce in flight (one item = one
+// whole unit = one round): 20 reserved SMs then hold 2.6 MB in flight, which the ~3.4 us NVLS round trip turns into the ~500 GB/s per
+// direction the fabric sustains (8 in flight: 387 GB/s, reducer-bound: measured). Peer loads: 8 per rank step, two items per unit.
+template <bool MC> struct RCfg { static constexpr int U = MC ? 16 : 8, PARTS = MC ? 1 : 2; };
 
 // Work item = (owned unit, quarter); items are strided over the CTAs (one CTA per SM, next to the GEMM's CTA). A 16-byte vector is
 // 2 consecutive rows (complex) or 4 (real) of one column of the sub-tile. Memory-level parallelism is what makes this kernel: a
@@ -603,8 +606,8 @@ __global__ void __launch_bounds__(RTHREADS, 1) tf32_allreduce_kernel(const __gri
     constexpr int PM = TBM * NCTA;
     constexpr int VE = REAL ? 4 : 2;                 // elements per 16-byte vector
     constexpr int ESZ = REAL ? 4 : 8;
+    constexpr int RPARTS = RCfg<MC>::PARTS, U = RCfg<MC>::U;
     constexpr int NVEC = TBM * BN / VE, PVEC = NVEC / RPARTS;
-    constexpr int U = 8;
     static_assert(PVEC % RTHREADS == 0, "part size");
     __shared__ int64_t sRow[TBM];
     __shared__ int64_t sCol[BN];
@@ -898,8 +901,8 @@ cudaError_t launch_allreduce_bn(const GettParams &g, const DistDesc &dist, cudaS
     // a rank that owns nothing still launches one CTA: its done flag must go up
     // grid: the reserved SMs when the reducer runs next to the GEMM (overlap), every SM when it runs after it
     const int64_t want = dist.reserve_sms > 0 ? dist.reserve_sms : 148;
-    unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(owned * RPARTS, want));
     const bool mc = d.mc_ws != nullptr;
+    unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(owned * (mc ? RCfg<true>::PARTS : RCfg<false>::PARTS), want));
     cudaLaunchConfig_t cfg{};
     cfg.blockDim = dim3(RTHREADS);
     cfg.stream = s;

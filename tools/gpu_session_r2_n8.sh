@@ -4,8 +4,8 @@ N=${1:-8}
 mkdir -p gpurun_out
 export MB200_DIST_TIMELINE=1
 ( timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29621 tools/diag_allreduce.py 2>&1 | grep DIAG
-  MB200_DIST_FENCE=all timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29622 tools/diag_allreduce.py 2>&1 | grep DIAG | sed 's/^DIAG/DIAG fence=all/'
-  MB200_DIST_REDUCER_SMS=32 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29623 tools/diag_allreduce.py 2>&1 | grep DIAG
+  true
+  true
   MB200_DIST_MULTICAST=0 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29624 tools/diag_allreduce.py 2>&1 | grep DIAG
 ) | tee gpurun_out/diag_allreduce_n${N}.log | cut -c1-700
 unset MB200_DIST_TIMELINE
