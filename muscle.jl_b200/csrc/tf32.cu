@@ -591,10 +591,11 @@ __device__ __forceinline__ void spin_until(const int *flag, int epoch) {
 // `reserve` SMs free (whole TPCs for the CTA-pair kernel: the reducer is then launched as 2-CTA clusters too) and the reducer runs
 // fat CTAs (512 threads, 8 x 16 bytes in flight per thread) on exactly those SMs.
 constexpr int RTHREADS = 512;
-// Work item = 1 / RPARTS of a unit's vectors. With the multicast mapping a thread keeps 16 multimem.ld_reduce in flight (one item = one
-// whole unit = one round): 20 reserved SMs then hold 2.6 MB in flight, which the ~3.4 us NVLS round trip turns into the ~500 GB/s per
-// direction the fabric sustains (8 in flight: 387 GB/s, reducer-bound: measured). Peer loads: 8 per rank step, two items per unit.
-template <bool MC> struct RCfg { static constexpr int U = MC ? 16 : 8, PARTS = MC ? 1 : 2; };
+// Work item = half of a unit's vectors, one round of 8 vectors per thread: 20 reserved SMs hold 1.3 MB in flight, which the ~3.4 us
+// NVLS round trip turns into ~390 GB/s per direction - what NCCL's own NVLS all-reduce gets on this box for 134 MB (0.383 ms). The
+// fabric, not the reducer, is the limit: 16 vectors in flight per thread was measured SLOWER (0.523 vs 0.486 ms at N = 8: congestion
+// stretches both the reduction and the GEMM's own traffic).
+template <bool MC> struct RCfg { static constexpr int U = 8, PARTS = 2; };
 
 // Work item = (owned unit, quarter); items are strided over the CTAs (one CTA per SM, next to the GEMM's CTA). A 16-byte vector is
 // 2 consecutive rows (complex) or 4 (real) of one column of the sub-tile. Memory-level parallelism is what makes this kernel: a
