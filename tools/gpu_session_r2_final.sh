@@ -9,6 +9,7 @@ tail -6 gpurun_out/final_pytest.log
     python bench.py --steps 2 --warmup 3 --skip-cpu --skip-e2e > gpurun_out/bench_under_ncu.json 2> gpurun_out/bench_under_ncu.err ) 2>&1 | tail -3
 ( time timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -f -o gpurun_out/prof_r02 \
     python tools/run_profile_r02.py > gpurun_out/prof_r02.log 2>&1 ) 2>&1 | tail -3
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 timeout 300 python tools/bench_kernels.py --svd 2>&1 | grep SVD | tee gpurun_out/kernels_svd_r02.log
 python - <<'PY'
 import json
