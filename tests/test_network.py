@@ -204,3 +204,44 @@ def test_graph_capture_error_paths():
     torch.cuda.synchronize()
     c = mb.binary_einsum(a, b, out=I("xwz"))                         # the handle is usable again
     assert np.array_equal(c.to_host().data, 7.0 * np.ones((5, 11, 3)))
+
+
+@pytest.mark.gpu
+def test_graph_replay_survives_plan_cache_eviction():
+    """a captured graph bakes the device pointers of its plans' offset tables into its kernel nodes. The LRU plan
+    cache (128 entries per handle) used to cudaFree those tables on eviction, so a later replay gathered and scattered through freed
+    memory. Graphs now co-own their plans: after more than 128 OTHER gather-GEMM plans have been built on the same handle (each
+    allocating tables, so freed blocks would be reused and overwritten), the replay must still give the right answer."""
+    import muscle_b200 as mb
+    I = lambda s: [mb.Index(c) for c in s]
+    labels = ["awb", "bsc", "wstv", "ate"]
+    ext = dict(a=64, b=64, c=64, e=64, w=8, v=8, s=2, t=2)
+    rng = np.random.default_rng(5)
+    arrays = _make(rng, labels, ext, "complex128")
+    ts = [mb.Tensor(x, I(ix)).to_device() for x, ix in zip(arrays, labels)]
+    prog = mb.ContractionProgram([t.inds for t in ts], [t.shape for t in ts], [t.dtype for t in ts], out=I("evc"),
+                                 path=[(0, 1), (4, 2), (5, 3)])
+    ref = contract_path_oracle(arrays, [list(ix) for ix in labels], list("evc"), prog.path)
+    cap = prog.capture(ts)
+    assert rel_frobenius(cap.replay().to_host().data, ref) <= 1e-12
+    h = mb.Handle.get(0)
+    built0 = h.stats()["plans_built"]
+    # 140 distinct shapes on the tiled path (tables on the device), well past the cache capacity
+    for k in range(140):
+        m, n, kk = 72 + k, 40 + (k % 7), 48
+        a = mb.Tensor(np.ones((m, kk), np.complex128), I("ik")).to_device()
+        b = mb.Tensor(np.full((kk, n), 2.0, np.complex128), I("kj")).to_device()
+        h.set_path(mb.PATH_GETT_F64)
+        c = mb.binary_einsum(a, b, out=I("ij"))
+        h.set_path(mb.PATH_AUTO)
+    assert np.array_equal(c.to_host().data, np.full((m, n), 2.0 * kk))
+    assert h.stats()["plans_built"] - built0 >= 140
+    # the captured chain's plans have been evicted from the cache; the graph still owns them
+    assert rel_frobenius(cap.replay().to_host().data, ref) <= 1e-12
+    arrays2 = _make(rng, labels, ext, "complex128")
+    for t, x in zip(ts, arrays2):
+        t.data.copy_from_host(x)
+    ref2 = contract_path_oracle(arrays2, [list(ix) for ix in labels], list("evc"), prog.path)
+    assert rel_frobenius(cap.replay().to_host().data, ref2) <= 1e-12
+    # and an un-captured run of the same chain simply rebuilds its plans
+    assert rel_frobenius(prog.run(ts).to_host().data, ref2) <= 1e-12
