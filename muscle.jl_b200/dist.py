@@ -52,13 +52,15 @@ def _default_contract(inds_c, a, b):
 
 
 def sharded_binary_einsum(a: Tensor, b: Tensor, inds_c, *, group=None, prefer_sum=False, gather=False,
-                          contract=_default_contract):
+                          contract=_default_contract, fused=True):
     """Contract replicated host (or per-rank device) operands across the ranks of `group`.
 
     Returns (c_local, info). For a free/batch shard `c_local` is this rank's slab of C (or, with
     gather=True, the full C assembled by all_gather along the split index); for a summed-index slice
-    it is the full C after all_reduce(SUM). `contract` exists so the CPU (gloo) tests can exercise this
-    host logic without a GPU; the product default is BackendB200.
+    it is the full C after the add-reduction of the partial outputs: the all-reduce FUSED into the contraction
+    (`sum_slice_all_reduce`, cross-GPU split-K over NVLink peer memory) whenever the slice runs on the tcgen05
+    path and `fused` is left on, else contraction followed by all_reduce(SUM) (NCCL). `contract` exists so the
+    CPU (gloo) tests can exercise this host logic without a GPU; the product default is BackendB200.
     """
     import torch
     import torch.distributed as dist
@@ -71,6 +73,15 @@ def sharded_binary_einsum(a: Tensor, b: Tensor, inds_c, *, group=None, prefer_su
         return contract(inds_c, a, b), (kind, index, begin, end)     # replicas only
     a_loc = local_slab(a, index, begin, end)
     b_loc = local_slab(b, index, begin, end)
+    if needs_allreduce and contract is _default_contract and nranks > 1 and dist.get_backend(group) == "nccl":
+        # NCCL reduces device buffers: the slices go to this rank's GPU first (host operands are the data-distribution convenience)
+        dev = a_loc.data.device if a_loc.on_device else (b_loc.data.device if b_loc.on_device else _lib.current_device())
+        a_loc, b_loc = a_loc.to_device(dev), b_loc.to_device(dev)
+        if fused:
+            try:
+                return sum_slice_all_reduce(a_loc, b_loc, inds_c, group=group), (kind, index, begin, end)
+            except _lib.ArgumentError:
+                pass                              # not on the tcgen05 path (ComplexF64, small shapes): NCCL below
     c_loc = contract(inds_c, a_loc, b_loc)
     if needs_allreduce:
         c_loc = all_reduce_sum(c_loc, group)

@@ -71,6 +71,20 @@ def main():
     assert info[0] == _lib.SHARD_SUM and info[1] == Index("h"), info
     check("sum_slice_nccl_all_reduce_c64", rel_frobenius(c_ar.to_host().data.astype(np.complex128), ref), 1e-5)
 
+    # the product default of a summed-index slice: the all-reduce fused into the contraction (host operands in, full C out)
+    h5 = mb.Handle.get(local)
+    h5.reset_stats()
+    c_def, info = mdist.sharded_binary_einsum(Tensor(A, I(ia)), Tensor(B, I(ib)), I(ic), prefer_sum=True)
+    assert info[0] == _lib.SHARD_SUM and c_def.on_device and len(mdist._ALLREDUCE) == 1, (info, mdist._ALLREDUCE)
+    check("sum_slice_default_is_fused_all_reduce_c64", rel_frobenius(c_def.to_host().data.astype(np.complex128), ref), 1e-5)
+    # a ComplexF64 slice is not on the tcgen05 path: the same call falls back to contraction + NCCL all-reduce
+    A64 = random_array(np.random.default_rng(7), (24, 2 * world, 20), "complex128")
+    B64 = random_array(np.random.default_rng(8), (2 * world, 20, 28), "complex128")
+    ref64 = np.einsum("ihk,hkj->ij", A64, B64)
+    c64, info = mdist.sharded_binary_einsum(Tensor(A64, I("ihk")), Tensor(B64, I("hkj")), I("ij"), prefer_sum=True)
+    assert info[0] == _lib.SHARD_SUM and c64.on_device and len(mdist._ALLREDUCE) == 1
+    check("sum_slice_c128_nccl_fallback", rel_frobenius(c64.to_host().data, ref64), 1e-12)
+
     kind, index, lo, hi, _ = mdist.plan_shard(Tensor(A, I(ia)), Tensor(B, I(ib)), I(ic), world, rank, prefer_sum=True)
     a_loc = mdist.local_slab(Tensor(A, I(ia)), index, lo, hi).to_device(local)
     b_loc = mdist.local_slab(Tensor(B, I(ib)), index, lo, hi).to_device(local)
