@@ -344,6 +344,7 @@ class _SymmetricBuffers:
 
 
 _ALLREDUCE: dict = {}
+_ALLREDUCE_CAP = 8
 
 
 def allreduce_workspace(a_loc: Tensor, b_loc: Tensor, inds_c, nranks: int):
@@ -392,6 +393,12 @@ def sum_slice_all_reduce(a_loc: Tensor, b_loc: Tensor, inds_c, group=None, phase
     st = _ALLREDUCE.get(key)
     if st is None:
         ws_bytes, flag_bytes = allreduce_workspace(a_loc, b_loc, inds_c, nranks)
+        # at most _ALLREDUCE_CAP signatures keep their symmetric buffers (workspace + C each); the oldest goes first - every rank
+        # makes the same calls in the same order, so every rank drops the same entry at the same point
+        while len(_ALLREDUCE) >= _ALLREDUCE_CAP:
+            old = next(iter(_ALLREDUCE))
+            _lib.Handle.get(dev).synchronize()
+            del _ALLREDUCE[old]
         st = _ALLREDUCE[key] = _SymmetricBuffers(dev, ws_bytes, flag_bytes, numel * T.itemsize, group)
     if bump_epoch:                                   # False: a later phase of the call that raised the epoch (diagnostics, tests)
         st.epoch += 1
