@@ -532,7 +532,7 @@ def headline_e2e(c, args, state):
     t0 = time.perf_counter()
     run(1)
     serial_ms = max_over_ranks(c, (time.perf_counter() - t0) * 1e3)
-    Ke = max(3, min(args.steps, 6))
+    Ke = max(3, min(args.steps, 8))
     barrier(c)
     t0 = time.perf_counter()
     run(Ke)

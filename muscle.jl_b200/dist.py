@@ -368,8 +368,8 @@ def sum_slice_all_reduce(a_loc: Tensor, b_loc: Tensor, inds_c, group=None, phase
     full C, bit-identical on all ranks) - Dagger's `treereduce(AddComputeOp, ...)` over the summed blocks
     (ext/MuscleDaggerExt/binary_einsum.jl:107-115) without a separate collective pass: see mb200_binary_einsum_allreduce.
 
-    The returned Tensor aliases a symmetric buffer that the NEXT call with the same signature overwrites; copy it
-    (`permutedims`, `to_host`) if it must outlive that call. Raises ArgumentError when the contraction is not on the
+    The returned Tensor aliases a symmetric buffer that the NEXT call with the same signature overwrites (and that is
+    released once `_ALLREDUCE_CAP` other signatures have been used); copy it (`permutedims`, `to_host`) if it must outlive that. Raises ArgumentError when the contraction is not on the
     tcgen05 path; callers then use `all_reduce_sum` on the partial outputs."""
     import ctypes as C
     import torch.distributed as dist
