@@ -450,6 +450,11 @@ def headline(c, args, sampler):
                          "native layouts, permuting epilogue (one launch per step)",
                          flops / c.world, float(np.mean(per_launch)), "gett_z_cfg4b_dram_bytes_per_launch")
     roof["share_of_step"] = 1.0
+    if c.world > 1:
+        roof["traffic"] = None      # the ncu capture is of the N = 1 launch (138 GB: profiles/ncu_r02_summary.md #0); a slab launch was not captured
+    else:
+        roof["traffic_note"] = ("10.7x the algorithmic bytes at 1.7 % of DRAM bandwidth: 221 waves x (8 A panels + 18.5 B panels = 578 MB) "
+                                "that no 126 MB L2 keeps from one wave to the next (DESIGN 3.1)")
     roof["algorithmic_bytes_per_launch"] = 16.0 * (np.prod([ext[x] for x in ia]) + np.prod([ext_loc[x] for x in ib])
                                                    + np.prod([ext_loc[x] for x in ic]))
     out = dict(value=value, ms_per_step=ms_per_step, flops=flops, clocks=clocks, roofline=roof, stats=stats,
