@@ -41,7 +41,7 @@ for it in range(iters):
     dist.all_gather(allc, csum)
     same = all(bool(torch.equal(allc[0], c)) for c in allc)
     worst = max(worst, err)
-    if err > 1e-5 or not same:
+    if not (err <= 1e-5) or not same:          # a non-finite error counts as a mismatch
         bad += 1
         if rank == 0 and bad <= 5:
             print(f"SOAK mismatch at iteration {it}: err {err:.3e} identical_across_ranks {same}", flush=True)
