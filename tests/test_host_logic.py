@@ -262,3 +262,18 @@ def test_bench_headline_shard_and_oracle_helpers():
     assert ic2 == ["k", "i"] and np.allclose(ref, full[..., 0])
     A, B, e2, flops = bench.cfg4b_sample(1 / 16, 1 / 16)
     assert A.shape == tuple(e2[x] for x in ia) and e2["a"] == 2 and e2["g"] == 2 and flops == 8.0 * np.prod([e2[x] for x in e2])
+
+
+def test_reference_arm_uses_every_host_thread_whatever_the_launcher_exported():
+    """torchrun exports OMP_NUM_THREADS=1; round 1's N > 1 reference arm therefore ran single-threaded. bench.set_blas_threads() asks
+    threadpoolctl for os.cpu_count() BLAS threads regardless."""
+    import importlib.util
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import importlib.util,os;s=importlib.util.spec_from_file_location('b',r'%s');b=importlib.util.module_from_spec(s);"
+            "s.loader.exec_module(b);import numpy;print(b.set_blas_threads(), os.cpu_count())" % os.path.join(root, "bench.py"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, OMP_NUM_THREADS="1"), timeout=120)
+    got, ncpu = map(int, out.stdout.split()[-2:])
+    assert got == ncpu or ncpu == 1, out.stdout + out.stderr

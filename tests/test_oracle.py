@@ -134,3 +134,17 @@ def test_integer_inputs_are_exact():
     c1 = binary_einsum_base(list("li"), a, list("ijk"), b, list("klj"))
     c2 = einsum_loops(list("li"), a, list("ijk"), b, list("klj"))
     assert np.array_equal(c1, c2)
+
+
+def test_dangling_label_semantics_of_the_two_oracles():
+    """A label carried by one operand only and absent from the output: BackendBase throws (binary_einsum.jl:82-83) while the general
+    einsum - OMEinsum / cuTENSOR semantics (ext/MuscleOMEinsumExt.jl:40-59, ext/MuscleCUDAExt.jl:30-38), the ones BackendB200
+    replaces - sums it. The GPU tests (tests/test_at_size.py::test_dangling_*) check the CUDA path against the second."""
+    import oracle
+    rng = np.random.default_rng(4)
+    a = rng.standard_normal((3, 5, 4))      # i x j
+    b = rng.standard_normal((4, 6))         # j k
+    with pytest.raises(oracle.ArgumentError):
+        oracle.binary_einsum_base(list("ik"), a, list("ixj"), b, list("jk"))
+    got = oracle.binary_einsum_general(list("ik"), a, list("ixj"), b, list("jk"))
+    assert np.allclose(got, a.sum(axis=1) @ b)
