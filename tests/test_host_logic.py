@@ -277,3 +277,97 @@ def test_reference_arm_uses_every_host_thread_whatever_the_launcher_exported():
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, OMP_NUM_THREADS="1"), timeout=120)
     got, ncpu = map(int, out.stdout.split()[-2:])
     assert got == ncpu or ncpu == 1, out.stdout + out.stderr
+
+
+def test_planner_classification_fuzz():
+    """Randomised label bookkeeping (hypothesis): for arbitrary label sets, extents (incl. 1), operand orders and output orders - with
+    dangling labels thrown in - the planner's batch / summed / free classification, GEMM sizes, swap rule and walk order agree with the
+    set arithmetic of the reference's front-end and backends (binary_einsum.jl:33-41, 76-79; ext/MuscleReactantExt.jl:94-109)."""
+    from hypothesis import given, settings, strategies as st
+
+    letters = "abcdefghijkl"
+
+    @st.composite
+    def problem(draw):
+        n = draw(st.integers(2, 9))
+        labs = list(letters[:n])
+        ext = {c: draw(st.sampled_from([1, 2, 3, 4, 5, 8])) for c in labs}
+        # where each label lives: 1 = A only, 2 = B only, 3 = both
+        where = {c: draw(st.sampled_from([1, 2, 3])) for c in labs}
+        ia = draw(st.permutations([c for c in labs if where[c] & 1]))
+        ib = draw(st.permutations([c for c in labs if where[c] & 2]))
+        # output: every label may be kept or dropped (dropping a single-operand label makes it dangling: summed by the entry points)
+        keep = [c for c in labs if draw(st.booleans())]
+        ic = draw(st.permutations(keep))
+        return ext, "".join(ia), "".join(ib), "".join(ic)
+
+    @settings(max_examples=300, deadline=None)
+    @given(problem())
+    def check(pr):
+        ext, ia, ib, ic = pr
+        info, labels = _describe(ext, ia, ib, ic)
+        inv = {v: k for k, v in labels.items()}
+        left = [inv[info.left[i]] for i in range(info.n_left)]
+        right = [inv[info.right[i]] for i in range(info.n_right)]
+        summed = [inv[info.sum[i]] for i in range(info.n_sum)]
+        batch = [inv[info.batch[i]] for i in range(info.n_batch)]
+        live = lambda s: {c for c in s if ext[c] > 1}
+        sa, sb, sc = set(ia), set(ib), set(ic)
+        dangling = ((sa - sb) | (sb - sa)) - sc           # summed away before planning: in none of the plan's groups
+        row, col = (ib, ia) if info.swapped else (ia, ib)
+        assert set(batch) == live(sa & sb & sc)
+        assert set(summed) == live((sa & sb) - sc)
+        assert set(left) == live(set(row) - set(col) - dangling)
+        assert set(right) == live(set(col) - set(row) - dangling)
+        prod = lambda s: int(np.prod([ext[c] for c in s], dtype=np.int64)) if s else 1
+        assert (info.M, info.N, info.K, info.L) == (prod(left), prod(right), prod(summed), prod(batch))
+        live_c = [c for c in ic if ext[c] > 1]
+        if live_c:
+            assert live_c[0] in left + batch              # C's unit-stride live label is a row (or batch) label
+        for grp in (left, right, batch):
+            pos = [ic.index(c) for c in grp]
+            assert pos == sorted(pos)                     # groups are walked in C's memory order
+
+    check()
+
+
+def test_shard_plan_fuzz():
+    """mb200_shard_plan (Dagger's block scheme, ext/MuscleDaggerExt/binary_einsum.jl:64-119): for random contractions and rank counts the
+    per-rank ranges tile the chosen label exactly once, every rank picks the same label and kind, a summed cut asks for the add-reduction
+    and a free / batch cut does not, and prefer_sum only ever picks a label that is summed."""
+    from hypothesis import given, settings, strategies as st
+
+    @st.composite
+    def problem(draw):
+        n = draw(st.integers(2, 8))
+        labs = list("abcdefgh"[:n])
+        ext = {c: draw(st.sampled_from([1, 2, 3, 4, 6, 8, 16])) for c in labs}
+        where = {c: draw(st.sampled_from([1, 2, 3])) for c in labs}
+        ia = [c for c in labs if where[c] & 1]
+        ib = [c for c in labs if where[c] & 2]
+        ic = [c for c in labs if where[c] != 3 or draw(st.booleans())]     # single-operand labels are kept, shared ones kept (batch) or summed
+        return ext, ia, ib, draw(st.permutations(ic)), draw(st.integers(1, 8)), draw(st.booleans())
+
+    @settings(max_examples=200, deadline=None)
+    @given(problem())
+    def check(pr):
+        ext, ia, ib, ic, nranks, prefer_sum = pr
+        ids = {c: k for k, c in enumerate("abcdefgh")}
+        infos = [_lib.shard_plan([ids[c] for c in ic], [ids[c] for c in ia], [ext[c] for c in ia], [ids[c] for c in ib],
+                                 [ext[c] for c in ib], nranks, r, prefer_sum) for r in range(nranks)]
+        assert len({(i.kind, i.mode) for i in infos}) == 1
+        kind, mode = infos[0].kind, infos[0].mode
+        if kind == _lib.SHARD_NONE:
+            return
+        lab = "abcdefgh"[mode]
+        cover = [x for i in infos for x in range(i.begin, i.end)]
+        assert cover == list(range(ext[lab])) and ext[lab] >= nranks
+        in_a, in_b, in_c = lab in ia, lab in ib, lab in ic
+        if kind == _lib.SHARD_SUM:
+            assert in_a and in_b and not in_c and all(i.needs_allreduce for i in infos)
+        elif kind == _lib.SHARD_BATCH:
+            assert in_a and in_b and in_c and not any(i.needs_allreduce for i in infos)
+        else:
+            assert (in_a != in_b) and in_c and not any(i.needs_allreduce for i in infos)
+
+    check()
