@@ -85,6 +85,9 @@ struct DomainB200 <: Muscle.Domain end
 Muscle.Domain(::Type{<:B200Array}) = DomainB200()
 Muscle.choose_backend_rule(::typeof(Muscle.binary_einsum), ::DomainB200, ::DomainB200) = BackendB200()
 Muscle.choose_backend_rule(::typeof(Muscle.binary_einsum!), ::DomainB200, ::DomainB200, ::DomainB200) = BackendB200()
+# hybrid host / device operands (pattern of binary_einsum.jl:23-24 for Reactant): the host operand is uploaded by binary_einsum!
+Muscle.choose_backend_rule(::typeof(Muscle.binary_einsum), ::DomainB200, ::Muscle.DomainHost) = BackendB200()
+Muscle.choose_backend_rule(::typeof(Muscle.binary_einsum), ::Muscle.DomainHost, ::DomainB200) = BackendB200()
 
 dtype_enum(::Type{Float32}) = Cint(0)
 dtype_enum(::Type{Float64}) = Cint(1)
