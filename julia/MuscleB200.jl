@@ -111,7 +111,9 @@ function Muscle.binary_einsum(::BackendB200, inds_c, a::Tensor, b::Tensor)
     dims = map(inds_c) do i
         i ∈ inds(a) ? size(a, i) : i ∈ inds(b) ? size(b, i) : throw(ArgumentError("index $i not found in a nor b"))
     end
-    c = Tensor(similar(parent(a), T, Tuple(dims)), collect(Index, inds_c))
+    # the result lives where the device operand lives (hybrid host / device operands: on the device)
+    proto = parent(a) isa B200Array ? parent(a) : (parent(b) isa B200Array ? parent(b) : parent(a))
+    c = Tensor(similar(proto, T, Tuple(dims)), collect(Index, inds_c))
     Muscle.binary_einsum!(BackendB200(), c, a, b)
     return c
 end
