@@ -308,3 +308,26 @@ def test_fused_allreduce_rejects_other_paths():
         _lib.check(mb.lib().mb200_allreduce_workspace(h.ptr, _lib.C128, 2, _lib.i32([1, 2]), _lib.C128, 2, _lib.i32([0, 1]),
                                                       _lib.i64((512, 512)), _lib.C128, 2, _lib.i32([0, 2]), _lib.i64((512, 512)),
                                                       4, C.byref(ws_b), C.byref(fl_b)))
+
+
+def test_dangling_golden_vectors():
+    """The CUDA path against tests/golden/dangling_golden.npz (outputs of the plain-C loop nest): both routes - the sum folded into the
+    direct kernel, and the unary_einsum pre-reduce for the case above 2^20 MACs."""
+    import importlib.util
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("mgd", os.path.join(here, "golden", "make_golden_dangling.py"))
+    mgd = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mgd)
+    z = np.load(os.path.join(here, "golden", "dangling_golden.npz"))
+    h = _lib.Handle.get()
+    for name, ext, ia, ib, ic in mgd.CASES:
+        for dt in mgd.DTYPES:
+            a, b, c = z[f"{name}__{dt}__a"], z[f"{name}__{dt}__b"], z[f"{name}__{dt}__c"]
+            h.reset_stats()
+            got = binary_einsum(mb.BackendB200(), I(ic), Tensor(a, I(ia)).to_device(), Tensor(b, I(ib)).to_device()).to_host().data
+            st = h.stats()
+            assert (st["launches_unary"] > 0) == (name == "prereduce_a"), (name, st)     # which route ran
+            wide = np.complex128 if np.dtype(dt).kind == "c" else np.float64
+            tol = 1e-12 if dt in ("float64", "complex128") else 1e-5
+            assert got.shape == c.shape and rel_frobenius(got.astype(wide), c.astype(wide)) <= tol, (name, dt)

@@ -148,3 +148,22 @@ def test_dangling_label_semantics_of_the_two_oracles():
         oracle.binary_einsum_base(list("ik"), a, list("ixj"), b, list("jk"))
     got = oracle.binary_einsum_general(list("ik"), a, list("ixj"), b, list("jk"))
     assert np.allclose(got, a.sum(axis=1) @ b)
+
+
+def test_dangling_golden_vectors_pin_the_general_oracle():
+    """tests/golden/dangling_golden.npz (plain-C loop nest, tests/golden/make_golden_dangling.py): the NumPy general oracle sums dangling
+    labels exactly as the explicit loop does."""
+    import importlib.util
+    import oracle
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("mgd", os.path.join(here, "golden", "make_golden_dangling.py"))
+    mgd = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mgd)
+    z = np.load(os.path.join(here, "golden", "dangling_golden.npz"))
+    for name, ext, ia, ib, ic in mgd.CASES:
+        for dt in mgd.DTYPES:
+            a, b, c = z[f"{name}__{dt}__a"], z[f"{name}__{dt}__b"], z[f"{name}__{dt}__c"]
+            wide = np.complex128 if np.dtype(dt).kind == "c" else np.float64
+            got = oracle.binary_einsum_general(list(ic), a.astype(wide), list(ia), b.astype(wide), list(ib))
+            tol = 1e-12 if dt in ("float64", "complex128") else 1e-6
+            assert got.shape == c.shape and oracle.rel_frobenius(got, c.astype(wide)) <= tol, (name, dt)
